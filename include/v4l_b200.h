@@ -1,0 +1,179 @@
+/*
+ * v4l_b200.h — C ABI of libv4l_b200.so: the B200 (sm_100a) PPO-update hot path of
+ * Mehooz/vision4leg.
+ *
+ * The reference has no FFI for this path: its boundary is a set of Python classes
+ * (SURVEY.md §8(b)).  The host-side mirror of those classes lives in vision4leg_b200/ (Python)
+ * and calls ONLY the entry points declared here.  Each entry point cites the reference code
+ * whose arithmetic it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; v4l_last_error() gives the message;
+ *   - all data pointers are CALLER-OWNED DEVICE pointers (tensor.data_ptr()) unless a name
+ *     starts with `h_` (host, pinned) — no torch types cross this boundary;
+ *   - `stream` is a cudaStream_t passed as void* (the caller's current stream);
+ *   - no allocation of user-visible memory; the only library-owned memory is the per-context
+ *     scratch (split-K partials), so a context must be used from one stream at a time;
+ *   - no exceptions, no global state besides the last-error string.
+ */
+#ifndef V4L_B200_H_
+#define V4L_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define V4L_ABI_VERSION 1
+
+typedef struct v4l_ctx v4l_ctx;
+
+/* ---- library / context ------------------------------------------------------------------- */
+int         v4l_version(void);
+const char* v4l_last_error(void);
+/* scratch_bytes: size of the context-owned scratch buffer (0 = default 256 MiB). */
+int         v4l_ctx_create(v4l_ctx** out, int device, size_t scratch_bytes);
+int         v4l_ctx_destroy(v4l_ctx* ctx);
+int         v4l_ctx_sm_count(const v4l_ctx* ctx);
+
+/* ---- addressing ---------------------------------------------------------------------------
+ * A "row map" addresses logical row m of a matrix that lives inside a larger activation
+ * tensor:   item = m / P,  pos = m % P,  item' = idx ? idx[item] : item
+ *           addr(m) = base + item' * item_stride + (pos_off ? pos_off[pos] : pos * pos_stride)
+ * (all in elements).  It expresses on-the-fly im2col (pos_off = receptive-field origin of an
+ * output pixel), minibatch row gathers (idx) and token-slot writes without copies.          */
+typedef struct {
+  int32_t        P;
+  int64_t        item_stride;
+  int64_t        pos_stride;
+  int64_t        base;
+  const int32_t* idx;      /* [M / P] or NULL */
+  const int32_t* pos_off;  /* [P] or NULL */
+} v4l_rowmap;
+
+enum { V4L_RELU = 1, V4L_ACCUM = 2 };
+
+/* C(m,n) (+)= act( sum_k A(m,k) * B(k,n) + bias[n] ) * (mask(m,n) > 0)
+ *   A(m,k) = a[ addr_a(m) + (a_koff ? a_koff[k] : k) ]      (gathered operand)
+ *   B(k,n) = b[ k * b_sk + n * b_sn ]                       (weights, either orientation)
+ *   C(m,n) = c[ addr_c(m) + cn ],  mask(m,n) = mask[ addr_mask(m) + cn ],
+ *            cn = c_koff ? c_koff[n] : n   (column scatter, e.g. (c,p) -> (p,c) of a flatten)
+ * Forward of every Linear / Conv2d on the path (reference torchrl/networks/base.py:8-44,
+ * 209-230, 317-324, 531, nets.py:973-992, torch.nn.MultiheadAttention projections) and, with
+ * B transposed, their data-gradients.                                                       */
+typedef struct {
+  const float* a;  v4l_rowmap a_map;  const int32_t* a_koff;
+  const float* b;  int64_t b_sk;  int64_t b_sn;
+  const float* bias;
+  float*       c;  v4l_rowmap c_map;  const int32_t* c_koff;
+  const float* mask;  v4l_rowmap mask_map;
+  int32_t M, N, K;
+  int32_t flags;
+} v4l_gemm_args;
+int v4l_gemm_rows(v4l_ctx* ctx, void* stream, const v4l_gemm_args* args);
+
+/* dW[n*ldw + k] = sum_m dY(m,n) * A(m,k);  dbias[n] = sum_m dY(m,n)   (deterministic split-M)
+ * Weight/bias gradients of the same layers.                                                  */
+typedef struct {
+  const float* dy;  v4l_rowmap dy_map;
+  const float* a;   v4l_rowmap a_map;  const int32_t* a_koff;
+  float*       dw;  int64_t ldw;
+  float*       dbias;          /* or NULL */
+  int32_t M, N, K;
+} v4l_wgrad_args;
+int v4l_gemm_wgrad(v4l_ctx* ctx, void* stream, const v4l_wgrad_args* args);
+
+/* out(m,n) = dy(m,n) * (act(m,n) > 0): ReLU backward between two row-mapped [M,N] views (used
+ * where a layer output lands in a token slot, reference base.py:613-615).                   */
+int v4l_relu_bwd(v4l_ctx* ctx, void* stream, const float* dy, const v4l_rowmap* dy_map,
+                 const float* act, const v4l_rowmap* act_map, float* out,
+                 const v4l_rowmap* out_map, int M, int N);
+
+/* dx[b,h,w,c] = (x[b,h,w,c] > 0) * sum_{kh,kw} dcol[(b,oh,ow), (c,kh,kw)]  with
+ * oh*stride + kh == h, ow*stride + kw == w.  NHWC activations, (c,kh,kw) column order (the
+ * OIHW weight order of torch.nn.Conv2d).  Data-gradient of conv2/conv3
+ * (reference torchrl/networks/base.py:320-323).  x may be NULL (no ReLU mask).               */
+int v4l_col2im(v4l_ctx* ctx, void* stream, const float* dcol, const float* x, float* dx,
+               int B, int Hin, int Win, int C, int KH, int KW, int stride, int Hout, int Wout);
+
+/* ---- transformer block pieces (nn.TransformerEncoderLayer(d, n_head, ff, dropout=0),
+ *      instantiated at reference torchrl/networks/nets.py:949-955; math: SURVEY Appendix A2) */
+/* qkv [B,T,3d] (q|k|v) -> o [B,T,d], p [B,nh,T,T] (softmax probabilities, saved for bwd)    */
+int v4l_attn_fwd(v4l_ctx* ctx, void* stream, const float* qkv, float* o, float* p,
+                 int B, int T, int d, int n_head);
+int v4l_attn_bwd(v4l_ctx* ctx, void* stream, const float* qkv, const float* p, const float* d_o,
+                 float* d_qkv, int B, int T, int d, int n_head);
+/* y = LayerNorm(a + res) * gamma + beta; z = a + res and stats = (mean, rstd) per row saved */
+int v4l_ln_fwd(v4l_ctx* ctx, void* stream, const float* a, const float* res, const float* gamma,
+               const float* beta, float* y, float* z, float* stats, int rows, int d, float eps);
+int v4l_ln_bwd(v4l_ctx* ctx, void* stream, const float* dy, const float* z, const float* stats,
+               const float* gamma, float* dz, float* dgamma, float* dbeta, int rows, int d);
+/* mode 0: out[b] = [ tok[b,0,:] | mean_t>=1 tok[b,t,:] ]  (LocoTransformer, nets.py:1015-1034)
+ * mode 1: out[b] = mean_t tok[b,t,:]                       (Transformer, nets.py:887-900)   */
+int v4l_pool_fwd(v4l_ctx* ctx, void* stream, const float* tok, float* out, int B, int T, int d, int mode);
+int v4l_pool_bwd(v4l_ctx* ctx, void* stream, const float* dout, float* dtok, int B, int T, int d, int mode);
+
+/* ---- GAE / discounted return: reverse segmented scan over the rollout buffer
+ *      (reference torchrl/replay_buffers/on_policy.py:17-71; recurrence: SURVEY Appendix A4).
+ * rewards/values/terminals/advs/rets: [T,E] fp32; time_limits addressed t*tl_st + e*tl_se
+ * ([T,1] -> (1,0), [T,E] -> (E,1)); last_value [E].  Arithmetic is float64 in registers.
+ * mode 0 = GAE(gamma,tau), mode 1 = discount_reward(gamma).                                  */
+int v4l_gae(v4l_ctx* ctx, void* stream, const float* rewards, const float* values,
+            const float* terminals, const float* time_limits, int64_t tl_st, int64_t tl_se,
+            const float* last_value, float* advs, float* rets, int T, int E,
+            double gamma, double tau, int time_limit_filter, int mode);
+
+/* ---- PPO loss epilogue (reference torchrl/algo/on_policy/ppo.py:42-153,
+ *      torchrl/policies/continuous_policy.py:127-146) --------------------------------------
+ * `info` rows are float[32]; the row written is info + 32 * (*slot).  Layout: V4L_INFO_*.   */
+enum {
+  V4L_INFO_ADV_MEAN = 0, V4L_INFO_ADV_STD, V4L_INFO_ADV_MAX, V4L_INFO_ADV_MIN,
+  V4L_INFO_VF_LOSS, V4L_INFO_GRAD_NORM_VF, V4L_INFO_POLICY_LOSS,
+  V4L_INFO_LP_MEAN, V4L_INFO_LP_STD, V4L_INFO_LP_MAX, V4L_INFO_LP_MIN,
+  V4L_INFO_LS_MEAN, V4L_INFO_LS_STD, V4L_INFO_LS_MAX, V4L_INFO_LS_MIN,
+  V4L_INFO_RATIO_MAX, V4L_INFO_RATIO_MIN, V4L_INFO_GRAD_NORM_PF,
+  V4L_INFO_COUNT = 18, V4L_INFO_STRIDE = 32
+};
+/* cur_idx[i] = flat_idx[(*slot) * n + i]  — selects this minibatch's rollout rows            */
+int v4l_select_rows(v4l_ctx* ctx, void* stream, const int32_t* flat_idx, const int32_t* slot,
+                    int32_t* cur_idx, int n);
+int v4l_slot_advance(v4l_ctx* ctx, void* stream, int32_t* slot, int32_t wrap);
+/* stats (double[8]) = { sum, sumsq, n, max, min } of adv[idx[i]], i<n  (ppo.py:142-148)     */
+int v4l_adv_stats(v4l_ctx* ctx, void* stream, const float* adv, const int32_t* idx, int n,
+                  double* stats);
+/* critic loss + d loss / d value  (ppo.py:94-114).  values [n]; returns/old_values gathered
+ * through idx.  inv_global = 1 / (global minibatch), inv_local = 1 / n.                      */
+int v4l_vf_loss(v4l_ctx* ctx, void* stream, const float* values, const float* returns,
+                const float* old_values, const int32_t* idx, float* d_values, int n,
+                float inv_global, float inv_local, int clipped, float clip_para,
+                float* info, const int32_t* slot);
+/* actor loss: log-prob, ratio, clipped surrogate, entropy bonus and their gradients w.r.t.
+ * mean [n,A] and logstd [A]  (ppo.py:42-92).  target_mean/target_logstd come from the frozen
+ * target policy; adv is normalised with the (possibly all-reduced) stats of v4l_adv_stats.   */
+int v4l_pf_loss(v4l_ctx* ctx, void* stream, const float* mean, const float* logstd,
+                const float* target_mean, const float* target_logstd, const float* acts,
+                const float* adv, const int32_t* idx, const double* adv_stats,
+                float* d_mean, float* d_logstd, int n, int A, float inv_global, float inv_local,
+                float clip_para, float entropy_coeff, float* info, const int32_t* slot);
+
+/* ---- clip_grad_norm_(0.5) + Adam(eps=1e-5) over a flat bucket
+ *      (reference ppo.py:71-75,116-120; a2c.py:30-40).
+ * hyper (device, float[8]) = { lr, beta1, beta2, eps, max_norm, step (as float), 0, 0 };
+ * the kernel reads step, uses step+1 for the bias corrections and stores step+1 back.
+ * norm_slot: index into the info row that receives the pre-clip total norm (or -1).          */
+int v4l_clip_adam(v4l_ctx* ctx, void* stream, float* param, const float* grad, float* m,
+                  float* v, int64_t n, float* hyper, float* info, const int32_t* slot,
+                  int norm_slot);
+
+/* ---- rollout ingest: strided host->device copy (pinned host rows -> aligned device planes);
+ *      replaces the float64 fancy-index copy + torch.Tensor(...).to(device) of
+ *      reference on_policy.py:83-89 / ppo.py:136-140.  Sizes in bytes.                       */
+int v4l_h2d_2d(void* stream, void* dst, size_t dpitch, const void* h_src, size_t spitch,
+               size_t width, size_t height);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* V4L_B200_H_ */

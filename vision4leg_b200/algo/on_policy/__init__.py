@@ -1,0 +1,3 @@
+from .a2c import A2C            # noqa: F401
+from .ppo import PPO            # noqa: F401
+from .on_rl_algo import OnRLAlgo  # noqa: F401

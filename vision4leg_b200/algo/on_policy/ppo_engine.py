@@ -1,0 +1,380 @@
+"""Device-resident PPO update engine: everything `PPO.update_per_epoch` does after the rollout
+reaches the GPU (reference torchrl/algo/on_policy/ppo.py:28-153).
+
+Layout in HBM
+  * parameters: ONE flat fp32 bucket  [ pf-only | shared encoder | vf-only ]  (16-byte aligned
+    segments); the modules' nn.Parameters are views into it, so checkpoints are unchanged.  The
+    actor's optimiser bucket is the prefix, the critic's the suffix — each is one contiguous
+    range for the fused clip+Adam kernel and for the (single) gradient all-reduce, and the
+    shared encoder is stepped by BOTH with separate Adam moments.
+  * rollout: aligned planes state[N,S], img[N,4*64*64], acts[N,A], values/advs/returns[N]
+    (the host buffer's rows are split by a strided H2D copy; SURVEY §7 hard part 7).
+  * a minibatch is a row-index list (time rows x envs, reference on_policy.py:73-92) consumed
+    by the first-layer gathers — no minibatch copy is ever materialised.
+
+One minibatch = the fixed kernel sequence of `_minibatch`; it is captured once in a CUDA graph
+and replayed (the minibatch number lives in a device-side slot counter).  Logged statistics
+accumulate in a device info table read back once per epoch.
+"""
+import numpy as np
+import torch
+
+from ... import engine
+from ..._lib import INFO_KEYS, INFO_STRIDE, INFO_GRAD_NORM_PF, INFO_GRAD_NORM_VF, V4LError
+
+_ALIGN = 4   # floats (16 B)
+
+
+def _round_up(n, a):
+  return (n + a - 1) // a * a
+
+
+class _Bucket:
+  """Flat parameter storage with named views."""
+
+  def __init__(self, named_groups, device):
+    # named_groups: [(group_name, [(name, Parameter)])] in layout order
+    self.offsets = {}
+    self.group_range = {}
+    off = 0
+    for gname, items in named_groups:
+      start = off
+      for name, p in items:
+        self.offsets[id(p)] = (off, p.numel(), tuple(p.shape))
+        off += _round_up(p.numel(), _ALIGN)
+      self.group_range[gname] = (start, off)
+    self.size = off
+    self.flat = torch.zeros(off, device=device, dtype=torch.float32)
+    for gname, items in named_groups:
+      for name, p in items:
+        o, n, shape = self.offsets[id(p)]
+        view = self.flat[o:o + n].view(shape)
+        view.copy_(p.data)
+        p.data = view
+
+  def view_of(self, flat, p, base=0):
+    o, n, shape = self.offsets[id(p)]
+    return flat[o - base:o - base + n].view(shape)
+
+
+class PPOUpdateEngine:
+  def __init__(self, pf, vf, target_pf, device, clip_para, entropy_coeff, clipped_value_loss,
+               use_cuda_graph=True, process_group=None):
+    self.device = torch.device(device)
+    if self.device.type != "cuda":
+      raise V4LError("the PPO update runs on a CUDA device (got %s); there is no CPU fallback"
+                     % (self.device,))
+    if getattr(pf, "tanh_action", False):
+      raise NotImplementedError("tanh_action policies are not implemented on the CUDA PPO path "
+                                "(no shipped config uses them)")
+    self.ops = engine.ops_for(self.device)
+    self.device = self.ops.device
+    self.pf, self.vf, self.target_pf = pf, vf, target_pf
+    self.family = pf._family
+    if vf._family != self.family:
+      raise V4LError("pf and vf must be the same network family")
+    self.S = pf._state_dim
+    self.A = pf._out_dim
+    self.has_img = pf._has_img
+    self.clip_para = float(clip_para)
+    self.entropy_coeff = float(entropy_coeff)
+    self.clipped_value_loss = bool(clipped_value_loss)
+    self.use_cuda_graph = use_cuda_graph
+    self.pg = process_group
+    self.world = 1
+    if process_group is not None:
+      import torch.distributed as dist
+      self.world = dist.get_world_size(process_group)
+    self._build_buckets()
+    kw = getattr(pf, "_plan_kwargs", {})
+    self.plan_pf = engine.make_plan(self.family, self.ops, self.S, self.A, **kw)
+    self.plan_vf = engine.make_plan(self.family, self.ops, self.S, 1, **kw)
+    self.plan_t = engine.make_plan(self.family, self.ops, self.S, self.A, **kw)
+    self._graphs = {}
+    self._roll = None
+    self._mb_bufs = {}
+
+  # ---------------------------------------------------------------------------------------------
+  def _build_buckets(self):
+    dev = self.device
+    pf_named = list(self.pf.named_parameters())
+    vf_named = list(self.vf.named_parameters())
+    vf_ids = {id(p) for _, p in vf_named}
+    pf_ids = {id(p) for _, p in pf_named}
+    pf_only = [(n, p) for n, p in pf_named if id(p) not in vf_ids]
+    shared = [(n, p) for n, p in pf_named if id(p) in vf_ids]
+    vf_only = [(n, p) for n, p in vf_named if id(p) not in pf_ids]
+    for _, p in pf_named + vf_named:
+      if p.device != dev or p.dtype != torch.float32:
+        raise V4LError("all parameters must be fp32 on %s before the PPO engine is built" % dev)
+    self.bucket = b = _Bucket([("pf_only", pf_only), ("shared", shared), ("vf_only", vf_only)], dev)
+    self.pf_range = (b.group_range["pf_only"][0], b.group_range["shared"][1])
+    self.vf_range = (b.group_range["shared"][0], b.group_range["vf_only"][1])
+    self.n_pf = self.pf_range[1] - self.pf_range[0]
+    self.n_vf = self.vf_range[1] - self.vf_range[0]
+    self.pf_flat = b.flat[self.pf_range[0]:self.pf_range[1]]
+    self.vf_flat = b.flat[self.vf_range[0]:self.vf_range[1]]
+    z = lambda n: torch.zeros(n, device=dev, dtype=torch.float32)
+    self.g_pf, self.g_vf = z(self.n_pf), z(self.n_vf)
+    self.m_pf, self.v_pf, self.m_vf, self.v_vf = z(self.n_pf), z(self.n_pf), z(self.n_vf), z(self.n_vf)
+    hyper = lambda: torch.tensor([0.0, 0.9, 0.999, 1e-5, 0.5, 0.0, 0.0, 0.0], device=dev)
+    self.hyper_pf, self.hyper_vf = hyper(), hyper()
+    # name -> tensor dicts the plans consume (logstd is not a network weight)
+    self.P_pf = {n: p.data for n, p in pf_named if n != "logstd"}
+    self.P_vf = {n: p.data for n, p in vf_named}
+    self.G_pf = {n: b.view_of(self.g_pf, p, self.pf_range[0]) for n, p in pf_named}
+    self.G_vf = {n: b.view_of(self.g_vf, p, self.vf_range[0]) for n, p in vf_named}
+    self.logstd = dict(pf_named)["logstd"].data
+    # frozen target policy: own flat copy in the actor-bucket layout
+    t_named = list(self.target_pf.named_parameters())
+    assert [n for n, _ in t_named] == [n for n, _ in pf_named]
+    self.t_flat = torch.zeros(self.n_pf, device=dev, dtype=torch.float32)
+    self.P_t = {}
+    for (n, tp), (_, p) in zip(t_named, pf_named):
+      view = b.view_of(self.t_flat, p, self.pf_range[0])
+      view.copy_(tp.data)
+      tp.data = view
+      if n != "logstd":
+        self.P_t[n] = view
+    self.t_logstd = dict(t_named)["logstd"].data
+    self._param_ptrs = [(p, p.data_ptr()) for _, p in pf_named + vf_named + t_named]
+
+  def check_views(self):
+    for p, ptr in self._param_ptrs:
+      if p.data_ptr() != ptr:
+        raise V4LError("a network parameter was re-allocated (e.g. .to()/.half()) after the PPO "
+                       "engine flattened it; rebuild the algorithm object")
+
+  # ---------------------------------------------------------------------------------------------
+  # rollout store
+  # ---------------------------------------------------------------------------------------------
+  def _alloc_rollout(self, T, E):
+    N, dev = T * E, self.device
+    f = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+    r = dict(T=T, E=E, N=N, state=f(N, self.S), acts=f(N, self.A), values=f(N), rewards=f(N),
+             terminals=f(N), advs=f(N), rets=f(N), last_value=f(E))
+    if self.has_img:
+      r["img"] = f(N, engine.IMG_ELEMS)
+    self._roll = r
+    self._graphs.clear()            # captured graphs hold the old planes' addresses
+    return r
+
+  def load_rollout(self, buf):
+    """Pinned host rows -> device planes (async on the current stream)."""
+    host = buf._host
+    T, E = buf._max_replay_buffer_size, buf.env_nums
+    r = self._roll
+    if r is None or r["T"] != T or r["E"] != E:
+      r = self._alloc_rollout(T, E)
+    obs = host["obs"]
+    D = obs.shape[-1]
+    expect = self.S + (engine.IMG_ELEMS if self.has_img else 0)
+    if D != expect:
+      raise V4LError("rollout observation width %d, expected %d" % (D, expect))
+    self.ops.h2d_2d(r["state"], self.S * 4, obs.data_ptr(), D * 4, self.S * 4, T * E)
+    if self.has_img:
+      self.ops.h2d_2d(r["img"], engine.IMG_ELEMS * 4, obs.data_ptr() + self.S * 4, D * 4,
+                      engine.IMG_ELEMS * 4, T * E)
+    self.h2d_bytes = T * E * D * 4
+    for key in ("acts", "values", "rewards", "terminals"):
+      src = host[key].reshape(T * E, -1)
+      r[key].view(T * E, -1).copy_(src, non_blocking=True)
+      self.h2d_bytes += src.numel() * 4
+    tl = host.get("time_limits")
+    if tl is not None:
+      r["time_limits"] = tl.reshape(T, -1).to(self.device, non_blocking=True)
+      self.h2d_bytes += tl.numel() * 4
+    else:
+      r["time_limits"] = None
+    return r
+
+  def load_rollout_arrays(self, roll):
+    """Test/bench helper: same as load_rollout from a dict of [T,E,*] numpy arrays."""
+    class _B:
+      pass
+    b = _B()
+    T, E = roll["rewards"].shape[:2]
+    b._max_replay_buffer_size, b.env_nums = T, E
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).pin_memory()
+    b._host = {k: pin(roll[k]) for k in ("obs", "acts", "values", "rewards", "terminals", "time_limits")
+               if k in roll}
+    self._pinned_keepalive = b._host
+    return self.load_rollout(b)
+
+  def compute_advantages(self, last_obs, last_terminals, gamma, tau, time_limit_filter, use_gae=True):
+    """process_epoch_samples on the device (reference on_rl_algo.py:23-34)."""
+    r = self._roll
+    T, E = r["T"], r["E"]
+    x = torch.as_tensor(np.ascontiguousarray(last_obs, dtype=np.float32)).to(self.device).reshape(E, -1)
+    v = torch.empty((E, 1), device=self.device, dtype=torch.float32)
+    plan = self._aux_plan(E)
+    plan.forward(self.P_vf, engine.Input.from_flat(x, self.S, self.has_img), v)
+    notdone = 1.0 - torch.as_tensor(np.asarray(last_terminals, np.float32).reshape(E)).to(self.device)
+    r["last_value"].copy_(v.view(E) * notdone)
+    tl = r["time_limits"]
+    use_tl = bool(time_limit_filter and tl is not None)
+    tl_st, tl_se = (tl.shape[1], 1) if (tl is not None and tl.shape[1] == E and E > 1) else (1, 0)
+    self.ops.gae(r["rewards"], r["values"], r["terminals"], tl, tl_st, tl_se, r["last_value"],
+                 r["advs"], r["rets"], T, E, float(gamma), float(tau if use_gae else 1.0), use_tl,
+                 0 if use_gae else 1)
+
+  def _aux_plan(self, B):
+    key = ("aux", B)
+    p = self._mb_bufs.get(key)
+    if p is None:
+      kw = getattr(self.pf, "_plan_kwargs", {})
+      p = self._mb_bufs[key] = engine.make_plan(self.family, self.ops, self.S, 1, **kw)
+    return p
+
+  # ---------------------------------------------------------------------------------------------
+  # one epoch
+  # ---------------------------------------------------------------------------------------------
+  def set_lr(self, plr, vlr):
+    self.hyper_pf[0] = float(plr)
+    self.hyper_vf[0] = float(vlr)
+
+  def sync_target(self):
+    """copy_model_params_from_to(pf, target_pf) as one D2D copy (reference utils.py:23-25)."""
+    self.t_flat.copy_(self.pf_flat)
+
+  def _bufs(self, B):
+    b = self._mb_bufs.get(B)
+    if b is None:
+      dev = self.device
+      f = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+      b = dict(cur_idx=torch.zeros(B, device=dev, dtype=torch.int32), values=f(B, 1), d_values=f(B, 1),
+               mean=f(B, self.A), tmean=f(B, self.A), d_mean=f(B, self.A),
+               stats=torch.zeros(8, device=dev, dtype=torch.float64))
+      if self.world > 1:
+        b["stats_all"] = torch.zeros((self.world, 8), device=dev, dtype=torch.float64)
+      self._mb_bufs[B] = b
+    return b
+
+  def _input(self, B, idx):
+    r = self._roll
+    if self.has_img:
+      return engine.Input(B, r["state"], self.S, 0, r["img"], engine.IMG_ELEMS, 0, idx)
+    return engine.Input(B, r["state"], self.S, 0, idx=idx)
+
+  def _minibatch(self, B):
+    """The fixed kernel sequence of one PPO.update (reference ppo.py:125-153): critic first,
+    then the actor on the encoder the critic just stepped."""
+    ops, r, b = self.ops, self._roll, self._bufs(B)
+    idx = b["cur_idx"]
+    inv_local = 1.0 / B
+    inv_global = 1.0 / (B * self.world)
+    ops.select_rows(self._flat_idx, self._slot, idx, B)
+    ops.adv_stats(r["advs"], idx, B, b["stats"])
+    if self.world > 1:
+      self._allreduce_stats(b)
+    inp = self._input(B, idx)
+    # ---- critic
+    self.plan_vf.forward(self.P_vf, inp, b["values"])
+    ops.vf_loss(b["values"], r["rets"], r["values"], idx, b["d_values"], B, inv_global, inv_local,
+                self.clipped_value_loss, self.clip_para, self._info, self._slot)
+    self.plan_vf.backward(self.P_vf, self.G_vf, b["d_values"])
+    if self.world > 1:
+      self._allreduce(self.g_vf)
+    ops.clip_adam(self.vf_flat, self.g_vf, self.m_vf, self.v_vf, self.n_vf, self.hyper_vf, self._info,
+                  self._slot, INFO_GRAD_NORM_VF)
+    # ---- actor
+    self.plan_pf.forward(self.P_pf, inp, b["mean"])
+    self.plan_t.forward(self.P_t, inp, b["tmean"])
+    ops.pf_loss(b["mean"], self.logstd, b["tmean"], self.t_logstd, r["acts"], r["advs"], idx, b["stats"],
+                b["d_mean"], self.G_pf["logstd"], B, self.A, inv_global, inv_local, self.clip_para,
+                self.entropy_coeff, self._info, self._slot)
+    self.plan_pf.backward(self.P_pf, self.G_pf, b["d_mean"])
+    if self.world > 1:
+      self._allreduce(self.g_pf)
+    ops.clip_adam(self.pf_flat, self.g_pf, self.m_pf, self.v_pf, self.n_pf, self.hyper_pf, self._info,
+                  self._slot, INFO_GRAD_NORM_PF)
+    ops.slot_advance(self._slot, 0)
+
+  def _allreduce(self, t):
+    import torch.distributed as dist
+    dist.all_reduce(t, group=self.pg)
+
+  def _allreduce_stats(self, b):
+    """global (sum, sumsq, n, max, min) of the advantages across ranks: one all-gather of 8
+    doubles, combined on the device (advantage normalisation is over the GLOBAL minibatch)."""
+    import torch.distributed as dist
+    dist.all_gather_into_tensor(b["stats_all"], b["stats"], group=self.pg)
+    a = b["stats_all"]
+    b["stats"][0:3] = a[:, 0:3].sum(0)
+    b["stats"][3] = a[:, 3].max()
+    b["stats"][4] = a[:, 4].min()
+
+  def run_epoch(self, perms, batch_size):
+    """opt_epochs x minibatches.  perms: [opt_epochs, T] time-row permutations.  Returns the
+    per-minibatch info dicts (one D2H read of the info table)."""
+    self.check_views()
+    r = self._roll
+    T, E = r["T"], r["E"]
+    assert batch_size % E == 0, "batch size should be dividable by env_nums"
+    rows = batch_size // E
+    perms = np.asarray(perms)
+    flat = (perms[:, :, None].astype(np.int64) * E + np.arange(E)[None, None, :]).reshape(len(perms), T * E)
+    n_full, tail = divmod(T, rows)
+    n_mb = len(perms) * (n_full + (1 if tail else 0))
+    dev = self.device
+    self._flat_idx = torch.from_numpy(flat.astype(np.int32)).to(dev)
+    self._slot = getattr(self, "_slot", None)
+    if self._slot is None:
+      self._slot = torch.zeros(1, device=dev, dtype=torch.int32)
+    if getattr(self, "_info", None) is None or self._info.shape[0] < n_mb:
+      self._info = torch.zeros((n_mb, INFO_STRIDE), device=dev, dtype=torch.float32)
+      self._graphs.clear()
+    B = rows * E
+    if tail == 0 and len(perms) > 0:
+      # uniform minibatches: flat_idx is [n_mb, B] and the device slot counter indexes it
+      if getattr(self, "_flat_idx_static", None) is None or self._flat_idx_static.numel() != flat.size:
+        self._flat_idx_static = torch.empty(flat.size, device=dev, dtype=torch.int32)
+        self._graphs.clear()
+      self._flat_idx_static.copy_(self._flat_idx.view(-1))
+      self._flat_idx = self._flat_idx_static
+      self._slot.zero_()
+      for _ in range(n_mb):
+        self._launch(B)
+    else:
+      self._run_ragged(flat, T, E, rows)
+    info = self._info[:n_mb, :len(INFO_KEYS)].cpu().numpy()
+    self.d2h_bytes = info.nbytes
+    return [dict(zip(INFO_KEYS, (float(x) for x in row))) for row in info]
+
+  def _launch(self, B):
+    if not self.use_cuda_graph or self.world > 1:
+      self._minibatch(B)
+      return
+    g = self._graphs.get(B)
+    if g is None:
+      if not self._graphs.get(("warm", B)):
+        # first minibatch at this size runs eagerly: allocates workspaces, loads modules
+        self._minibatch(B)
+        self._graphs[("warm", B)] = True
+        return
+      torch.cuda.synchronize(self.device)
+      g = torch.cuda.CUDAGraph()
+      launches0 = self.ops.launches
+      with torch.cuda.graph(g):
+        self._minibatch(B)
+      self._graph_launches = self.ops.launches - launches0
+      self._graphs[B] = g
+    else:
+      self.ops.launches += self._graph_launches
+    g.replay()
+
+  def _run_ragged(self, flat, T, E, rows):
+    """T not divisible by the minibatch rows: the reference yields a short last minibatch."""
+    slot = 0
+    saved = self._flat_idx
+    for ep in range(flat.shape[0]):
+      for pos in range(0, T, rows):
+        n = min(rows, T - pos) * E
+        self._flat_idx = saved[ep, pos * E:pos * E + n].contiguous()
+        self._slot.fill_(0)
+        info_row = self._info
+        self._info = info_row[slot:slot + 1]
+        self._minibatch(n)
+        self._info = info_row
+        slot += 1
+    self._flat_idx = saved

@@ -1,0 +1,59 @@
+// Context, error reporting and copy helpers of libv4l_b200.so.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void v4l_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int v4l_version(void) { return V4L_ABI_VERSION; }
+
+extern "C" const char* v4l_last_error(void) { return g_err; }
+
+extern "C" int v4l_ctx_create(v4l_ctx** out, int device, size_t scratch_bytes) {
+  V4L_REQUIRE(out != nullptr, "v4l_ctx_create: out is NULL");
+  int count = 0;
+  V4L_CHECK_CUDA(cudaGetDeviceCount(&count));
+  V4L_REQUIRE(device >= 0 && device < count, "v4l_ctx_create: bad device %d (have %d)", device, count);
+  V4L_CHECK_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  V4L_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  V4L_REQUIRE(prop.major == 10, "libv4l_b200 is built for sm_100a only; device %d is sm_%d%d",
+              device, prop.major, prop.minor);
+  v4l_ctx* c = new v4l_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (scratch_bytes == 0) scratch_bytes = (size_t)256 << 20;
+  c->scratch_elems = scratch_bytes / sizeof(float);
+  cudaError_t e = cudaMalloc(&c->scratch, scratch_bytes);
+  if (e != cudaSuccess) {
+    v4l_set_error("v4l_ctx_create: cudaMalloc(%zu) -> %s", scratch_bytes, cudaGetErrorString(e));
+    delete c;
+    return -2;
+  }
+  *out = c;
+  return 0;
+}
+
+extern "C" int v4l_ctx_destroy(v4l_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaFree(ctx->scratch);
+  delete ctx;
+  return 0;
+}
+
+extern "C" int v4l_ctx_sm_count(const v4l_ctx* ctx) { return ctx ? ctx->sm_count : -1; }
+
+extern "C" int v4l_h2d_2d(void* stream, void* dst, size_t dpitch, const void* h_src, size_t spitch,
+                          size_t width, size_t height) {
+  V4L_CHECK_CUDA(cudaMemcpy2DAsync(dst, dpitch, h_src, spitch, width, height,
+                                   cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return 0;
+}

@@ -1,0 +1,52 @@
+// Shared declarations for libv4l_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "v4l_b200.h"
+
+struct v4l_ctx {
+  int device;
+  int sm_count;
+  float* scratch;        // context-owned scratch (split partials)
+  size_t scratch_elems;
+};
+
+void v4l_set_error(const char* fmt, ...);
+
+#define V4L_CHECK_CUDA(expr)                                                          \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      v4l_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return -2;                                                                      \
+    }                                                                                 \
+  } while (0)
+
+#define V4L_CHECK_LAUNCH()                                                            \
+  do {                                                                                \
+    cudaError_t _e = cudaGetLastError();                                              \
+    if (_e != cudaSuccess) {                                                          \
+      v4l_set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return -3;                                                                      \
+    }                                                                                 \
+  } while (0)
+
+#define V4L_REQUIRE(cond, ...)                                                        \
+  do {                                                                                \
+    if (!(cond)) {                                                                    \
+      v4l_set_error(__VA_ARGS__);                                                     \
+      return -1;                                                                      \
+    }                                                                                 \
+  } while (0)
+
+__device__ __forceinline__ long long v4l_row_addr(const v4l_rowmap& rm, int m) {
+  int item = m / rm.P;
+  int pos = m - item * rm.P;
+  if (rm.idx) item = rm.idx[item];
+  long long off = rm.pos_off ? (long long)rm.pos_off[pos] : (long long)pos * rm.pos_stride;
+  return rm.base + (long long)item * rm.item_stride + off;
+}
+
+static inline int v4l_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -1,0 +1,564 @@
+"""Host-side orchestration of the CUDA path: layer plans for the three policy families.
+
+A *plan* knows, for one network (policy mean head or value head) and one batch size, which
+C-ABI calls (include/v4l_b200.h) make up its forward and backward pass, and owns the device
+workspace for the saved activations.  Parameters are passed in as {state_dict key: fp32 CUDA
+tensor}; gradients are written to a parallel dict.  Nothing here computes on the CPU and
+nothing calls a torch math op on the hot path (torch supplies memory and streams only).
+
+Reference semantics reproduced (paths relative to the reference root):
+  MLPPlan     torchrl/networks/nets.py:16-55 (Net) + base.py:8-44 (MLPBase)
+  NaturePlan  nets.py:194-262 (ImpalaEncoderProjNet) + base.py:345-385 (NatureFuseEncoder)
+  LocoPlan    nets.py:909-1038 (LocoTransformer) + base.py:497-626 (LocoTransformerEncoder)
+  VisionTransformerPlan  nets.py:784-906 (Transformer) + base.py:388-494 (TransformerEncoder)
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import RowMap, GemmArgs, WgradArgs, RELU, ACCUM, check, ptr
+
+IMG_C, IMG_H, IMG_W = 4, 64, 64
+IMG_ELEMS = IMG_C * IMG_H * IMG_W
+
+
+class RM:
+  """Python mirror of v4l_rowmap (keeps the index tensors alive)."""
+  __slots__ = ("P", "item_stride", "pos_stride", "base", "idx", "pos_off")
+
+  def __init__(self, P=1, item_stride=0, pos_stride=0, base=0, idx=None, pos_off=None):
+    self.P, self.item_stride, self.pos_stride, self.base = P, item_stride, pos_stride, base
+    self.idx, self.pos_off = idx, pos_off
+
+  def c(self):
+    return RowMap(self.P, self.item_stride, self.pos_stride, self.base, ptr(self.idx),
+                  ptr(self.pos_off))
+
+  @staticmethod
+  def dense(ld):
+    return RM(1, ld, 0, 0)
+
+  @staticmethod
+  def slots(P, slot_count, d, first):
+    """rows (b, p<P) -> token slot (first + p) of a [B, slot_count, d] tensor."""
+    return RM(P, slot_count * d, d, first * d)
+
+
+class Input:
+  """Where a batch's observations live: proprio rows and CHW image planes, optionally
+  through a row-index gather (minibatch rows of the device-resident rollout)."""
+  __slots__ = ("state", "state_stride", "state_base", "img", "img_stride", "img_base", "idx", "B")
+
+  def __init__(self, B, state=None, state_stride=0, state_base=0, img=None, img_stride=0,
+               img_base=0, idx=None):
+    self.B = B
+    self.state, self.state_stride, self.state_base = state, state_stride, state_base
+    self.img, self.img_stride, self.img_base = img, img_stride, img_base
+    self.idx = idx
+
+  @staticmethod
+  def from_flat(x, S, has_img=True):
+    """x [B, S (+16384)] fp32 contiguous CUDA (the layout the reference modules receive,
+    nets.py:997-1000)."""
+    B, D = x.shape
+    if has_img:
+      return Input(B, x, D, 0, x, D, S)
+    return Input(B, x, D, 0)
+
+
+class Ops:
+  """Typed wrappers over the C ABI for one device."""
+
+  def __init__(self, device):
+    self.ctx = _lib.ctx(device)
+    self.lib = self.ctx.lib
+    self.h = self.ctx.handle
+    self.device = self.ctx.device
+    self.launches = 0     # kernel launches issued through this object (bench `gpu_launches`)
+
+  # ---- GEMMs
+  def gemm(self, a, a_map, koff, b, b_sk, b_sn, bias, c, c_map, M, N, K, flags=0, mask=None,
+           mask_map=None, c_koff=None):
+    g = GemmArgs(ptr(a), a_map.c(), ptr(koff), ptr(b), b_sk, b_sn, ptr(bias), ptr(c), c_map.c(),
+                 ptr(c_koff), ptr(mask), (mask_map or RM()).c(), M, N, K, flags)
+    check(self.lib.v4l_gemm_rows(self.h, self.ctx.stream(), C.byref(g)))
+    self.launches += 1
+
+  def linear_fwd(self, a, a_map, koff, w, bias, c, c_map, M, N, K, relu):
+    """c = act(a_gather @ w[N,K]^T + bias)"""
+    self.gemm(a, a_map, koff, w, 1, K, bias, c, c_map, M, N, K, RELU if relu else 0)
+
+  def linear_dgrad(self, dy, dy_map, w, dx, dx_map, M, N, K, mask=None, mask_map=None, accum=False,
+                   dx_koff=None):
+    """dx[M,K] (+)= dy[M,N] @ w[N,K], optionally masked by (mask > 0) (ReLU of the producer)"""
+    self.gemm(dy, dy_map, None, w, K, 1, None, dx, dx_map, M, K, N, ACCUM if accum else 0, mask,
+              mask_map, dx_koff)
+
+  def relu_bwd(self, dy, dy_map, act, act_map, out, out_map, M, N):
+    a, b, c = dy_map.c(), act_map.c(), out_map.c()
+    check(self.lib.v4l_relu_bwd(self.h, self.ctx.stream(), ptr(dy), C.byref(a), ptr(act), C.byref(b),
+                                ptr(out), C.byref(c), M, N))
+    self.launches += 1
+
+  def linear_wgrad(self, dy, dy_map, a, a_map, koff, dw, dbias, M, N, K):
+    g = WgradArgs(ptr(dy), dy_map.c(), ptr(a), a_map.c(), ptr(koff), ptr(dw), K, ptr(dbias), M, N, K)
+    check(self.lib.v4l_gemm_wgrad(self.h, self.ctx.stream(), C.byref(g)))
+    self.launches += 2
+
+  def col2im(self, dcol, x, dx, B, Hin, Win, Cc, KH, KW, stride, Hout, Wout):
+    check(self.lib.v4l_col2im(self.h, self.ctx.stream(), ptr(dcol), ptr(x), ptr(dx), B, Hin, Win, Cc,
+                              KH, KW, stride, Hout, Wout))
+    self.launches += 1
+
+  # ---- transformer pieces
+  def attn_fwd(self, qkv, o, p, B, T, d, nh):
+    check(self.lib.v4l_attn_fwd(self.h, self.ctx.stream(), ptr(qkv), ptr(o), ptr(p), B, T, d, nh))
+    self.launches += 1
+
+  def attn_bwd(self, qkv, p, d_o, d_qkv, B, T, d, nh):
+    check(self.lib.v4l_attn_bwd(self.h, self.ctx.stream(), ptr(qkv), ptr(p), ptr(d_o), ptr(d_qkv),
+                                B, T, d, nh))
+    self.launches += 1
+
+  def ln_fwd(self, a, res, gamma, beta, y, z, stats, rows, d, eps=1e-5):
+    check(self.lib.v4l_ln_fwd(self.h, self.ctx.stream(), ptr(a), ptr(res), ptr(gamma), ptr(beta),
+                              ptr(y), ptr(z), ptr(stats), rows, d, eps))
+    self.launches += 1
+
+  def ln_bwd(self, dy, z, stats, gamma, dz, dgamma, dbeta, rows, d):
+    check(self.lib.v4l_ln_bwd(self.h, self.ctx.stream(), ptr(dy), ptr(z), ptr(stats), ptr(gamma),
+                              ptr(dz), ptr(dgamma), ptr(dbeta), rows, d))
+    self.launches += 2
+
+  def pool_fwd(self, tok, out, B, T, d, mode):
+    check(self.lib.v4l_pool_fwd(self.h, self.ctx.stream(), ptr(tok), ptr(out), B, T, d, mode))
+    self.launches += 1
+
+  def pool_bwd(self, dout, dtok, B, T, d, mode):
+    check(self.lib.v4l_pool_bwd(self.h, self.ctx.stream(), ptr(dout), ptr(dtok), B, T, d, mode))
+    self.launches += 1
+
+  # ---- PPO pieces
+  def gae(self, rewards, values, terminals, time_limits, tl_st, tl_se, last_value, advs, rets, T, E,
+          gamma, tau, time_limit_filter, mode=0):
+    check(self.lib.v4l_gae(self.h, self.ctx.stream(), ptr(rewards), ptr(values), ptr(terminals),
+                           ptr(time_limits), tl_st, tl_se, ptr(last_value), ptr(advs), ptr(rets), T, E,
+                           gamma, tau, 1 if time_limit_filter else 0, mode))
+    self.launches += 3
+
+  def select_rows(self, flat_idx, slot, cur_idx, n):
+    check(self.lib.v4l_select_rows(self.h, self.ctx.stream(), ptr(flat_idx), ptr(slot), ptr(cur_idx), n))
+    self.launches += 1
+
+  def slot_advance(self, slot, wrap=0):
+    check(self.lib.v4l_slot_advance(self.h, self.ctx.stream(), ptr(slot), wrap))
+    self.launches += 1
+
+  def adv_stats(self, adv, idx, n, stats):
+    check(self.lib.v4l_adv_stats(self.h, self.ctx.stream(), ptr(adv), ptr(idx), n, ptr(stats)))
+    self.launches += 1
+
+  def vf_loss(self, values, returns, old_values, idx, d_values, n, inv_global, inv_local, clipped,
+              clip_para, info, slot):
+    check(self.lib.v4l_vf_loss(self.h, self.ctx.stream(), ptr(values), ptr(returns), ptr(old_values),
+                               ptr(idx), ptr(d_values), n, inv_global, inv_local, 1 if clipped else 0,
+                               clip_para, ptr(info), ptr(slot)))
+    self.launches += 2
+
+  def pf_loss(self, mean, logstd, tmean, tlogstd, acts, adv, idx, stats, d_mean, d_logstd, n, A,
+              inv_global, inv_local, clip_para, entropy_coeff, info, slot):
+    check(self.lib.v4l_pf_loss(self.h, self.ctx.stream(), ptr(mean), ptr(logstd), ptr(tmean),
+                               ptr(tlogstd), ptr(acts), ptr(adv), ptr(idx), ptr(stats), ptr(d_mean),
+                               ptr(d_logstd), n, A, inv_global, inv_local, clip_para, entropy_coeff,
+                               ptr(info), ptr(slot)))
+    self.launches += 2
+
+  def clip_adam(self, param, grad, m, v, n, hyper, info, slot, norm_slot):
+    check(self.lib.v4l_clip_adam(self.h, self.ctx.stream(), ptr(param), ptr(grad), ptr(m), ptr(v), n,
+                                 ptr(hyper), ptr(info), ptr(slot), norm_slot))
+    self.launches += 3
+
+  def h2d_2d(self, dst, dpitch, src_ptr, spitch, width, height):
+    check(self.lib.v4l_h2d_2d(self.ctx.stream(), ptr(dst), dpitch, src_ptr, spitch, width, height))
+
+
+_ops = {}
+
+
+def ops_for(device):
+  device = torch.device(device)
+  index = device.index if device.index is not None else torch.cuda.current_device()
+  o = _ops.get(index)
+  if o is None:
+    o = _ops[index] = Ops(torch.device("cuda", index))
+  return o
+
+
+# =================================================================================================
+# gather tables (im2col expressed as row-origin + per-k offsets)
+# =================================================================================================
+
+def _i32(a, device):
+  return torch.tensor(np.ascontiguousarray(a, dtype=np.int32), device=device)
+
+
+def conv_tables(device, Hin, Win, Cin, KH, KW, stride, chw_input):
+  """Returns (pos_off [Hout*Wout], k_off [Cin*KH*KW], Hout, Wout) for a VALID conv whose k
+  index runs (c, kh, kw) — torch's OIHW weight order — over an input stored CHW
+  (chw_input=True: the observation image) or HWC (our activations)."""
+  Hout, Wout = (Hin - KH) // stride + 1, (Win - KW) // stride + 1
+  oh, ow = np.meshgrid(np.arange(Hout), np.arange(Wout), indexing="ij")
+  c, kh, kw = np.meshgrid(np.arange(Cin), np.arange(KH), np.arange(KW), indexing="ij")
+  if chw_input:
+    pos = (oh * stride) * Win + ow * stride
+    k = c * (Hin * Win) + kh * Win + kw
+  else:
+    pos = ((oh * stride) * Win + ow * stride) * Cin
+    k = (kh * Win + kw) * Cin + c
+  return _i32(pos.ravel(), device), _i32(k.ravel(), device), Hout, Wout
+
+
+class _Plan:
+  """Common machinery: workspace cache and dense Linear-stack helpers."""
+
+  def __init__(self, ops, out_dim):
+    self.ops = ops
+    self.device = ops.device
+    self.out_dim = out_dim
+    self._ws = {}
+
+  def buf(self, name, *shape):
+    key = (name,) + tuple(shape)
+    t = self._ws.get(key)
+    if t is None:
+      t = self._ws[key] = torch.empty(shape, device=self.device, dtype=torch.float32)
+    return t
+
+  def release(self):
+    self._ws.clear()
+
+  def _stack_fwd(self, P, keys, x, x_map, koff, B, din, tag, last_relu, out=None, out_map=None):
+    """Linear stack: every layer has ReLU except (optionally) the last.  The last layer may
+    write into a caller-provided view (out, out_map).  Returns [(act, map, width)]."""
+    acts = []
+    a, a_map, ko, K = x, x_map, koff, din
+    for i, (wk, bk) in enumerate(keys):
+      w = P[wk]
+      N = w.shape[0]
+      last = i + 1 == len(keys)
+      if last and out is not None:
+        y, y_map = out, out_map
+      else:
+        y = self.buf("%s%d" % (tag, i), B, N)
+        y_map = RM.dense(N)
+      self.ops.linear_fwd(a, a_map, ko, w, P[bk], y, y_map, B, N, K, relu=(not last) or last_relu)
+      acts.append((y, y_map, N))
+      a, a_map, ko, K = y, y_map, None, N
+    return acts
+
+  def _stack_bwd(self, P, G, keys, x, x_map, koff, B, din, acts, dy, dy_map, tag, dx=None,
+                 dx_map=None, dx_mask=None, dx_mask_map=None):
+    """dy: gradient w.r.t. the last layer's PRE-activation.  If dx is given, the gradient
+    w.r.t. the stack input is written there (masked by dx_mask > 0 when the input is itself a
+    ReLU output)."""
+    for i in reversed(range(len(keys))):
+      wk, bk = keys[i]
+      w = P[wk]
+      N, K = w.shape
+      if i > 0:
+        a, a_map, _ = acts[i - 1]
+        ko = None
+      else:
+        a, a_map, ko = x, x_map, koff
+      self.ops.linear_wgrad(dy, dy_map, a, a_map, ko, G[wk], G[bk], B, N, K)
+      if i > 0:
+        dprev = self.buf("%s_d%d" % (tag, i - 1), B, K)
+        self.ops.linear_dgrad(dy, dy_map, w, dprev, RM.dense(K), B, N, K, mask=a, mask_map=a_map)
+        dy, dy_map = dprev, RM.dense(K)
+      elif dx is not None:
+        self.ops.linear_dgrad(dy, dy_map, w, dx, dx_map, B, N, K, mask=dx_mask, mask_map=dx_mask_map)
+
+
+def _head_keys(P, prefix):
+  idx = sorted(int(k[len(prefix):].split(".")[0]) for k in P
+               if k.startswith(prefix) and k.endswith(".weight"))
+  return [(prefix + "%d.weight" % i, prefix + "%d.bias" % i) for i in idx]
+
+
+# =================================================================================================
+# proprio-only MLP (reference starter/ppo_state.py:90-104; nets.py:16-55; base.py:8-44)
+# =================================================================================================
+class MLPPlan(_Plan):
+  family = "mlp"
+
+  def __init__(self, ops, S, out_dim):
+    super().__init__(ops, out_dim)
+    self.S = S
+
+  def forward(self, P, inp, out):
+    B = inp.B
+    self._inp = inp
+    x_map = RM(1, inp.state_stride, 0, inp.state_base, idx=inp.idx)
+    self._bk = _head_keys(P, "base.seq_fcs.")
+    self._hk = _head_keys(P, "seq_append_fcs.")
+    self._bacts = self._stack_fwd(P, self._bk, inp.state, x_map, None, B, self.S, "b", True)
+    h, h_map, hd = self._bacts[-1]
+    self._hacts = self._stack_fwd(P, self._hk, h, h_map, None, B, hd, "h", False, out,
+                                  RM.dense(self.out_dim))
+    return out
+
+  def backward(self, P, G, d_out):
+    inp = self._inp
+    B = inp.B
+    h, h_map, hd = self._bacts[-1]
+    dh = self.buf("dh", B, hd)
+    self._stack_bwd(P, G, self._hk, h, h_map, None, B, hd, self._hacts, d_out,
+                    RM.dense(self.out_dim), "h", dx=dh, dx_map=RM.dense(hd), dx_mask=h,
+                    dx_mask_map=h_map)
+    x_map = RM(1, inp.state_stride, 0, inp.state_base, idx=inp.idx)
+    self._stack_bwd(P, G, self._bk, inp.state, x_map, None, B, self.S, self._bacts, dh,
+                    RM.dense(hd), "b")
+
+
+# =================================================================================================
+# NatureCNN trunk shared by NaturePlan / LocoPlan (reference base.py:304-342)
+# =================================================================================================
+class _ConvTrunk:
+  """conv 8x8/4 -> 4x4/2 -> 3x3/1 (+ReLU each) on a [4,64,64] CHW image; activations NHWC."""
+
+  def __init__(self, plan, prefix):
+    self.plan = plan
+    self.prefix = prefix
+    dev = plan.device
+    self.pos1, self.k1, h1, w1 = conv_tables(dev, 64, 64, IMG_C, 8, 8, 4, True)     # 15x15
+    self.pos2, self.k2, h2, w2 = conv_tables(dev, h1, w1, 32, 4, 4, 2, False)       # 6x6
+    self.pos3, self.k3, h3, w3 = conv_tables(dev, h2, w2, 64, 3, 3, 1, False)       # 4x4
+    assert (h1, h2, h3) == (15, 6, 4)
+
+  def keys(self, i):
+    return self.prefix + "layers.%d.weight" % (2 * i), self.prefix + "layers.%d.bias" % (2 * i)
+
+  def forward(self, P, inp):
+    pl, ops, B = self.plan, self.plan.ops, inp.B
+    self.inp = inp
+    self.img_map = RM(225, inp.img_stride, 0, inp.img_base, idx=inp.idx, pos_off=self.pos1)
+    w, b = self.keys(0)
+    self.a1 = pl.buf("a1", B, 225, 32)
+    ops.linear_fwd(inp.img, self.img_map, self.k1, P[w], P[b], self.a1, RM.dense(32), B * 225, 32, 256, True)
+    self.a1_map = RM(36, 225 * 32, 0, 0, pos_off=self.pos2)
+    w, b = self.keys(1)
+    self.a2 = pl.buf("a2", B, 36, 64)
+    ops.linear_fwd(self.a1, self.a1_map, self.k2, P[w], P[b], self.a2, RM.dense(64), B * 36, 64, 512, True)
+    self.a2_map = RM(16, 36 * 64, 0, 0, pos_off=self.pos3)
+    w, b = self.keys(2)
+    self.a3 = pl.buf("a3", B, 16, 64)
+    ops.linear_fwd(self.a2, self.a2_map, self.k3, P[w], P[b], self.a3, RM.dense(64), B * 16, 64, 576, True)
+    return self.a3
+
+  def backward(self, P, G, da3):
+    """da3 [B,16,64]: gradient w.r.t. conv3's PRE-activation (already ReLU-masked)."""
+    pl, ops, B = self.plan, self.plan.ops, self.inp.B
+    inp = self.inp
+    w3, b3 = self.keys(2)
+    ops.linear_wgrad(da3, RM.dense(64), self.a2, self.a2_map, self.k3, G[w3], G[b3], B * 16, 64, 576)
+    dcol = pl.buf("dcol", B * 36 * 512)             # shared by conv3 (B*16*576) and conv2 (B*36*512)
+    ops.linear_dgrad(da3, RM.dense(64), P[w3], dcol, RM.dense(576), B * 16, 64, 576)
+    da2 = pl.buf("da2", B, 36, 64)
+    ops.col2im(dcol, self.a2, da2, B, 6, 6, 64, 3, 3, 1, 4, 4)
+    w2, b2 = self.keys(1)
+    ops.linear_wgrad(da2, RM.dense(64), self.a1, self.a1_map, self.k2, G[w2], G[b2], B * 36, 64, 512)
+    ops.linear_dgrad(da2, RM.dense(64), P[w2], dcol, RM.dense(512), B * 36, 64, 512)
+    da1 = pl.buf("da1", B, 225, 32)
+    ops.col2im(dcol, self.a1, da1, B, 15, 15, 32, 4, 4, 2, 6, 6)
+    w1, b1 = self.keys(0)
+    ops.linear_wgrad(da1, RM.dense(32), inp.img, self.img_map, self.k1, G[w1], G[b1], B * 225, 32, 256)
+
+
+# =================================================================================================
+# NatureCNN + concat MLP  (reference nets.py:194-262, base.py:345-385; starter/ppo_nature_cnn.py)
+# =================================================================================================
+class NaturePlan(_Plan):
+  family = "nature"
+
+  def __init__(self, ops, S, out_dim):
+    super().__init__(ops, out_dim)
+    self.S = S
+    self.trunk = _ConvTrunk(self, "encoder.visual_base.")
+    # flatten of [B,64,4,4] is (c, p); our a3 is (p, c)
+    c, p = np.meshgrid(np.arange(64), np.arange(16), indexing="ij")
+    self.kflat = _i32((p * 64 + c).ravel(), self.device)
+
+  def forward(self, P, inp, out):
+    ops, B = self.ops, inp.B
+    self._inp = inp
+    a3 = self.trunk.forward(P, inp)
+    wv, bv = "encoder.visual_projector.projection.0.weight", "encoder.visual_projector.projection.0.bias"
+    self.vd = P[wv].shape[0]
+    self._bk = _head_keys(P, "encoder.base.seq_fcs.")
+    self._hk = _head_keys(P, "seq_append_fcs.")
+    self.sd = P[self._bk[-1][0]].shape[0]
+    W = self.vd + self.sd
+    self.cat = self.buf("cat", B, W)
+    ops.linear_fwd(a3, RM.dense(1024), self.kflat, P[wv], P[bv], self.cat, RM(1, W, 0, 0), B, self.vd, 1024, True)
+    x_map = RM(1, inp.state_stride, 0, inp.state_base, idx=inp.idx)
+    self._bacts = self._stack_fwd(P, self._bk, inp.state, x_map, None, B, self.S, "s", True,
+                                  self.cat, RM(1, W, 0, self.vd))
+    self._hacts = self._stack_fwd(P, self._hk, self.cat, RM.dense(W), None, B, W, "h", False, out,
+                                  RM.dense(self.out_dim))
+    return out
+
+  def backward(self, P, G, d_out):
+    ops, inp = self.ops, self._inp
+    B, W = inp.B, self.vd + self.sd
+    dcat = self.buf("dcat", B, W)
+    self._stack_bwd(P, G, self._hk, self.cat, RM.dense(W), None, B, W, self._hacts, d_out,
+                    RM.dense(self.out_dim), "h", dx=dcat, dx_map=RM.dense(W), dx_mask=self.cat,
+                    dx_mask_map=RM.dense(W))
+    x_map = RM(1, inp.state_stride, 0, inp.state_base, idx=inp.idx)
+    self._stack_bwd(P, G, self._bk, inp.state, x_map, None, B, self.S, self._bacts, dcat,
+                    RM(1, W, 0, self.vd), "s")
+    wv, bv = "encoder.visual_projector.projection.0.weight", "encoder.visual_projector.projection.0.bias"
+    dv_map = RM(1, W, 0, 0)
+    ops.linear_wgrad(dcat, dv_map, self.trunk.a3, RM.dense(1024), self.kflat, G[wv], G[bv], B, self.vd, 1024)
+    da3 = self.buf("da3", B, 16, 64)
+    ops.linear_dgrad(dcat, dv_map, P[wv], da3, RM.dense(1024), B, self.vd, 1024, mask=self.trunk.a3,
+                     mask_map=RM.dense(1024), dx_koff=self.kflat)
+    self.trunk.backward(P, G, da3)
+
+
+# =================================================================================================
+# LocoTransformer (reference nets.py:909-1038, base.py:497-626) and the vision-only
+# Transformer (nets.py:784-906, base.py:388-494; has_state=False)
+# =================================================================================================
+class LocoPlan(_Plan):
+  family = "loco"
+
+  def __init__(self, ops, S, out_dim, n_heads=(1, 1), has_state=True, token_dim=64):
+    super().__init__(ops, out_dim)
+    self.S = S
+    self.has_state = has_state
+    self.d = token_dim
+    self.n_heads = list(n_heads)
+    self.T = 16 + (1 if has_state else 0)
+    self.trunk = _ConvTrunk(self, "encoder.depth_visual_base.")
+
+  def _layer_keys(self, l):
+    p = "visual_append_layers.%d." % l
+    return {k: p + v for k, v in {
+      "win": "self_attn.in_proj_weight", "bin": "self_attn.in_proj_bias",
+      "wo": "self_attn.out_proj.weight", "bo": "self_attn.out_proj.bias",
+      "w1": "linear1.weight", "b1": "linear1.bias", "w2": "linear2.weight", "b2": "linear2.bias",
+      "g1": "norm1.weight", "be1": "norm1.bias", "g2": "norm2.weight", "be2": "norm2.bias"}.items()}
+
+  def forward(self, P, inp, out):
+    ops, B, T, d = self.ops, inp.B, self.T, self.d
+    self._inp = inp
+    first = 1 if self.has_state else 0
+    a3 = self.trunk.forward(P, inp)
+    tok = self.buf("tok0", B, T, d)
+    self.vis_map = RM.slots(16, T, d, first)
+    ops.linear_fwd(a3, RM.dense(64), None, P["encoder.depth_up_conv.weight"],
+                   P["encoder.depth_up_conv.bias"], tok, self.vis_map, B * 16, d, 64, False)
+    if self.has_state:
+      self._sk = _head_keys(P, "encoder.base.seq_fcs.") + [
+        ("encoder.state_projector.projection.0.weight", "encoder.state_projector.projection.0.bias")]
+      x_map = RM(1, inp.state_stride, 0, inp.state_base, idx=inp.idx)
+      self._sacts = self._stack_fwd(P, self._sk, inp.state, x_map, None, B, self.S, "s", True, tok,
+                                    RM.slots(1, T, d, 0))
+    R = B * T
+    x = tok
+    self._layers = []
+    for l, nh in enumerate(self.n_heads):
+      k = self._layer_keys(l)
+      ff = P[k["w1"]].shape[0]
+      qkv = self.buf("qkv%d" % l, R, 3 * d)
+      ops.linear_fwd(x, RM.dense(d), None, P[k["win"]], P[k["bin"]], qkv, RM.dense(3 * d), R, 3 * d, d, False)
+      o = self.buf("o%d" % l, R, d)
+      p = self.buf("p%d" % l, B, nh, T, T)
+      ops.attn_fwd(qkv, o, p, B, T, d, nh)
+      proj = self.buf("proj", R, d)
+      ops.linear_fwd(o, RM.dense(d), None, P[k["wo"]], P[k["bo"]], proj, RM.dense(d), R, d, d, False)
+      h = self.buf("h%d" % l, R, d)
+      z1 = self.buf("z1_%d" % l, R, d)
+      st1 = self.buf("st1_%d" % l, R, 2)
+      ops.ln_fwd(proj, x, P[k["g1"]], P[k["be1"]], h, z1, st1, R, d)
+      f1 = self.buf("f1_%d" % l, R, ff)
+      ops.linear_fwd(h, RM.dense(d), None, P[k["w1"]], P[k["b1"]], f1, RM.dense(ff), R, ff, d, True)
+      f2 = self.buf("f2", R, d)
+      ops.linear_fwd(f1, RM.dense(ff), None, P[k["w2"]], P[k["b2"]], f2, RM.dense(d), R, d, ff, False)
+      y = self.buf("y%d" % l, R, d)
+      z2 = self.buf("z2_%d" % l, R, d)
+      st2 = self.buf("st2_%d" % l, R, 2)
+      ops.ln_fwd(f2, h, P[k["g2"]], P[k["be2"]], y, z2, st2, R, d)
+      self._layers.append(dict(k=k, nh=nh, ff=ff, x=x, qkv=qkv, o=o, p=p, h=h, z1=z1, st1=st1, f1=f1,
+                               z2=z2, st2=st2))
+      x = y
+    self._tok0 = tok
+    pd = 2 * d if self.has_state else d
+    self.pooled = self.buf("pooled", B, pd)
+    ops.pool_fwd(x, self.pooled, B, T, d, 0 if self.has_state else 1)
+    self._hk = _head_keys(P, "visual_seq_append_fcs.")
+    self._hacts = self._stack_fwd(P, self._hk, self.pooled, RM.dense(pd), None, B, pd, "h", False, out,
+                                  RM.dense(self.out_dim))
+    return out
+
+  def backward(self, P, G, d_out):
+    ops, inp = self.ops, self._inp
+    B, T, d = inp.B, self.T, self.d
+    R = B * T
+    pd = 2 * d if self.has_state else d
+    dpool = self.buf("dpool", B, pd)
+    self._stack_bwd(P, G, self._hk, self.pooled, RM.dense(pd), None, B, pd, self._hacts, d_out,
+                    RM.dense(self.out_dim), "h", dx=dpool, dx_map=RM.dense(pd))
+    dx = self.buf("dx", R, d)
+    ops.pool_bwd(dpool, dx, B, T, d, 0 if self.has_state else 1)
+    for L in reversed(self._layers):
+      k, nh, ff = L["k"], L["nh"], L["ff"]
+      dz2 = self.buf("dz2", R, d)
+      ops.ln_bwd(dx, L["z2"], L["st2"], P[k["g2"]], dz2, G[k["g2"]], G[k["be2"]], R, d)
+      ops.linear_wgrad(dz2, RM.dense(d), L["f1"], RM.dense(ff), None, G[k["w2"]], G[k["b2"]], R, d, ff)
+      df1 = self.buf("df1", R, ff)
+      ops.linear_dgrad(dz2, RM.dense(d), P[k["w2"]], df1, RM.dense(ff), R, d, ff, mask=L["f1"],
+                       mask_map=RM.dense(ff))
+      ops.linear_wgrad(df1, RM.dense(ff), L["h"], RM.dense(d), None, G[k["w1"]], G[k["b1"]], R, ff, d)
+      ops.linear_dgrad(df1, RM.dense(ff), P[k["w1"]], dz2, RM.dense(d), R, ff, d, accum=True)   # dh
+      dz1 = self.buf("dz1", R, d)
+      ops.ln_bwd(dz2, L["z1"], L["st1"], P[k["g1"]], dz1, G[k["g1"]], G[k["be1"]], R, d)
+      ops.linear_wgrad(dz1, RM.dense(d), L["o"], RM.dense(d), None, G[k["wo"]], G[k["bo"]], R, d, d)
+      do = self.buf("do", R, d)
+      ops.linear_dgrad(dz1, RM.dense(d), P[k["wo"]], do, RM.dense(d), R, d, d)
+      dqkv = self.buf("dqkv", R, 3 * d)
+      ops.attn_bwd(L["qkv"], L["p"], do, dqkv, B, T, d, nh)
+      ops.linear_wgrad(dqkv, RM.dense(3 * d), L["x"], RM.dense(d), None, G[k["win"]], G[k["bin"]], R, 3 * d, d)
+      ops.linear_dgrad(dqkv, RM.dense(3 * d), P[k["win"]], dz1, RM.dense(d), R, 3 * d, d, accum=True)
+      # dx for the next (earlier) layer lives in dz1; swap so the buffers are not clobbered
+      self._ws[("dx", R, d)], self._ws[("dz1", R, d)] = dz1, dx
+      dx = dz1
+    tok = self._tok0
+    if self.has_state:
+      ds = self.buf("ds", B, d)
+      smap = RM.slots(1, T, d, 0)
+      ops.relu_bwd(dx, smap, tok, smap, ds, RM.dense(d), B, d)
+      x_map = RM(1, inp.state_stride, 0, inp.state_base, idx=inp.idx)
+      self._stack_bwd(P, G, self._sk, inp.state, x_map, None, B, self.S, self._sacts, ds, RM.dense(d), "s")
+    a3 = self.trunk.a3
+    ops.linear_wgrad(dx, self.vis_map, a3, RM.dense(64), None, G["encoder.depth_up_conv.weight"],
+                     G["encoder.depth_up_conv.bias"], B * 16, d, 64)
+    da3 = self.buf("da3", B, 16, 64)
+    ops.linear_dgrad(dx, self.vis_map, P["encoder.depth_up_conv.weight"], da3, RM.dense(64), B * 16, d, 64,
+                     mask=a3, mask_map=RM.dense(64))
+    self.trunk.backward(P, G, da3)
+
+
+def make_plan(family, ops, S, out_dim, **kw):
+  if family == "mlp":
+    return MLPPlan(ops, S, out_dim)
+  if family == "nature":
+    return NaturePlan(ops, S, out_dim)
+  if family == "loco":
+    return LocoPlan(ops, S, out_dim, **kw)
+  if family == "vit":
+    return LocoPlan(ops, 0, out_dim, has_state=False, **kw)
+  raise ValueError("unknown family %r" % (family,))

@@ -1,0 +1,48 @@
+"""Parameter initialisers with the reference's semantics (torchrl/networks/init.py:5-47).
+
+Kept numerically identical (including the quirk that a Linear weight's "fan-in" is taken from
+size[0] = out_features) so that a seeded construction reproduces the reference's
+initial weights bit for bit; verified by tests/test_modules_cpu.py against golden fingerprints.
+"""
+import math
+
+import torch.nn as nn
+
+
+def _fanin_init(tensor, alpha=0):
+  shape = tensor.size()
+  if len(shape) < 2:
+    raise Exception("Shape must be have dimension at least 2.")
+  fan = shape[0] if len(shape) == 2 else int(math.prod(shape[1:]))
+  bound = math.sqrt(1.0 / ((1 + alpha * alpha) * fan))
+  return tensor.data.uniform_(-bound, bound)
+
+
+def _uniform_init(tensor, param=3e-3):
+  return tensor.data.uniform_(-param, param)
+
+
+def _constant_bias_init(tensor, constant=0.1):
+  tensor.data.fill_(constant)
+
+
+def _orthogonal_init(tensor, gain=math.sqrt(2)):
+  nn.init.orthogonal_(tensor, gain=gain)
+
+
+def layer_init(layer, weight_init=_fanin_init, bias_init=_constant_bias_init):
+  weight_init(layer.weight)
+  bias_init(layer.bias)
+
+
+def basic_init(layer):
+  layer_init(layer, _fanin_init, _constant_bias_init)
+
+
+def uniform_init(layer):
+  layer_init(layer, _uniform_init, _uniform_init)
+
+
+def orthogonal_init(layer, scale=math.sqrt(2), constant=0):
+  layer_init(layer, lambda w: _orthogonal_init(w, gain=scale),
+             lambda b: _constant_bias_init(b, constant))
