@@ -130,14 +130,46 @@ def cpu_minibatch(model, S, A, batch, seed):
           "values": roll["values"].reshape(batch, 1)}
 
 
-def cpu_baseline(args, budget_s):
-  """samples/s of reference-equivalent PPO.update on the host cores (tensors pre-converted)."""
+def host_cores():
+  """Usable host cores: min(affinity mask, cgroup CPU quota)."""
   cores = os.cpu_count() or 1
   try:
     cores = min(cores, len(os.sched_getaffinity(0)))
   except Exception:
     pass
-  torch.set_num_threads(cores)
+  try:
+    quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+    if quota != "max":
+      cores = max(1, min(cores, int(float(quota) / float(period))))
+  except Exception:
+    pass
+  return cores
+
+
+def pick_threads():
+  """torch-CPU threads for the reference arm: the fastest of a few candidates on a small
+  conv fwd+bwd probe (oversubscribing a shared 128-core host is 50x slower than 16 threads)."""
+  import torch.nn.functional as F
+  cores = host_cores()
+  cands = sorted({c for c in (4, 8, 16, 32, 64, cores) if c <= cores} | {min(cores, 8)})
+  x = torch.randn(128, 4, 64, 64)
+  w = torch.randn(32, 4, 8, 8, requires_grad=True)
+  best, best_t = cands[0], float("inf")
+  for c in cands:
+    torch.set_num_threads(c)
+    for rep in range(3):
+      t0 = time.perf_counter()
+      F.conv2d(x, w, stride=4).sum().backward()
+      dt = time.perf_counter() - t0
+      if rep and dt < best_t:
+        best, best_t = c, dt
+  torch.set_num_threads(best)
+  return best, cores
+
+
+def cpu_baseline(args, budget_s):
+  """samples/s of reference-equivalent PPO.update on the host cores (tensors pre-converted)."""
+  cores, avail = pick_threads()
   orc = make_oracle(args.model, args.S, args.A, args.batch)
   mb = cpu_minibatch(args.model, args.S, args.A, args.batch, 5)
   mb = {k: torch.as_tensor(v, dtype=torch.float32) for k, v in mb.items()}
@@ -150,21 +182,17 @@ def cpu_baseline(args, budget_s):
     if dt >= budget_s or n >= 32:
       break
   return {"value": n * args.batch / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-          "sample": "%d PPO.update minibatches of %d (%s, S=%d, A=%d) after 1 warm-up, %.1f s; "
-                    "oracle/ppo_oracle.py = torch-CPU restatement of the reference path" %
-                    (n, args.batch, args.model, args.S, args.A, dt)}
+          "sample": "%d PPO.update minibatches of %d (%s, S=%d, A=%d) after 1 warm-up, %.1f s, %d torch "
+                    "threads (best of a probe; %d usable cores); oracle/ppo_oracle.py = torch-CPU "
+                    "restatement of the reference path" %
+                    (n, args.batch, args.model, args.S, args.A, dt, cores, avail)}
 
 
 def run_reference(args):
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
-  cores = os.cpu_count() or 1
-  try:
-    cores = min(cores, len(os.sched_getaffinity(0)))
-  except Exception:
-    pass
-  torch.set_num_threads(cores)
+  cores, avail = pick_threads()
   orc = make_oracle(args.model, args.S, args.A, args.batch)
   mb = cpu_minibatch(args.model, args.S, args.A, args.batch, 5)
   mb = {k: torch.as_tensor(v, dtype=torch.float32) for k, v in mb.items()}
@@ -176,7 +204,8 @@ def run_reference(args):
     orc.update(mb)
   dt = time.perf_counter() - t0
   value = args.steps * per_step * args.batch / dt
-  sample = "%d steps x %d PPO.update minibatches of %d" % (args.steps, per_step, args.batch)
+  sample = "%d steps x %d PPO.update minibatches of %d, %d torch threads (%d usable cores)" % (
+    args.steps, per_step, args.batch, cores, avail)
   print(json.dumps({
     "impl": "reference", "metric": "ppo_update_samples_per_sec", "value": value, "unit": "samples/s",
     "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,

@@ -10,6 +10,14 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
   config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+  try:
+    import torch
+    # the torch restatements the kernels are checked against must be true fp32 (cuDNN convs
+    # default to TF32, ~1e-3 relative error — the size of the tolerance being tested)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+  except Exception:
+    pass
 
 
 def pytest_collection_modifyitems(config, items):
