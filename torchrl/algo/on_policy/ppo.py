@@ -1,0 +1,3 @@
+from vision4leg_b200.algo.on_policy.ppo import *  # noqa: F401,F403
+from vision4leg_b200.algo.on_policy import ppo as _m
+globals().update({k: v for k, v in vars(_m).items() if not k.startswith('__')})

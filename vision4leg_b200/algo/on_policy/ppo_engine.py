@@ -298,7 +298,7 @@ class PPOUpdateEngine:
     """global (sum, sumsq, n, max, min) of the advantages across ranks: one all-gather of 8
     doubles, combined on the device (advantage normalisation is over the GLOBAL minibatch)."""
     import torch.distributed as dist
-    dist.all_gather_into_tensor(b["stats_all"], b["stats"], group=self.pg)
+    dist.all_gather_into_tensor(b["stats_all"].view(-1), b["stats"], group=self.pg)
     a = b["stats_all"]
     b["stats"][0:3] = a[:, 0:3].sum(0)
     b["stats"][3] = a[:, 3].max()
