@@ -167,6 +167,32 @@ int v4l_clip_adam(v4l_ctx* ctx, void* stream, float* param, const float* grad, f
                   float* v, int64_t n, float* hyper, float* info, const int32_t* slot,
                   int norm_slot);
 
+/* ---- tensor-core tier (bf16 operands, fp32 accumulate; tcgen05.mma fed by TMA) ---------------
+ * D[row tile, N] = sum_{tap,kc} A_tap[rows, 64k] * W[N, (tap,kc,64k)]^T  (+bias, ReLU, ReLU-mask,
+ * accumulate), see vision4leg_b200/csrc/tc_gemm.cu.  A: bf16 NHWC activation [a_B,a_H,a_W,a_C]
+ * (plain matrices: a_H = a_W = 1); a row tile is the TMA box {64, bw, bh, bb} shifted per tap by
+ * (tap_dw, tap_dh) with hardware zero fill outside the tensor.  W: packed bf16
+ * [N_pad, n_taps*kchunks*64].  Output rows are the logical positions (b, h, w) of a
+ * [B, Hout, Wout] grid addressed through c_map (+ column n); c is bf16 unless c_f32.
+ * Same reference layers as v4l_gemm_rows.                                                    */
+typedef struct {
+  const void* a;  int32_t a_B, a_H, a_W, a_C;
+  int32_t B, Hout, Wout;
+  int32_t bw, bh, bb;
+  int32_t n_taps, kchunks;
+  int32_t tap_dw[16], tap_dh[16];
+  const void* w;  int32_t N_pad, N_valid;
+  const float* bias;
+  void* c;  v4l_rowmap c_map;  int32_t c_f32;
+  const void* mask;
+  int32_t flags;
+} v4l_tc_gemm_args;
+int v4l_tc_gemm(v4l_ctx* ctx, void* stream, const v4l_tc_gemm_args* args);
+/* dst_bf16[i] = index ? (index[i] >= 0 ? src[index[i]] : 0) : src[i]  — weight packing /
+ * fp32 -> bf16 conversion for the tensor-core tier                                            */
+int v4l_pack_bf16(v4l_ctx* ctx, void* stream, const float* src, const int32_t* index, void* dst,
+                  int64_t n);
+
 /* ---- rollout ingest: strided host->device copy (pinned host rows -> aligned device planes);
  *      replaces the float64 fancy-index copy + torch.Tensor(...).to(device) of
  *      reference on_policy.py:83-89 / ppo.py:136-140.  Sizes in bytes.                       */

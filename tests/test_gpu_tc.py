@@ -1,0 +1,126 @@
+"""Tensor-core tier (tcgen05 + TMA) kernel parity against torch on bf16-rounded operands.
+The GEMM itself is exact up to fp32 accumulation order, so errors are ~1e-6 relative except for
+the final bf16 rounding of the stored output (2^-9 relative) — tolerance 1e-2 is the bf16 tier's
+north-star bound; we assert the much tighter 5e-3 on outputs of O(1)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ops():
+  from vision4leg_b200 import engine
+  return engine, engine.ops_for(DEV)
+
+
+def rel(a, b):
+  a, b = a.detach().double().cpu(), b.detach().double().cpu()
+  return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def bf(x):
+  return x.to(torch.bfloat16)
+
+
+def _linear_case(M, N, K, relu, f32_out, N_valid=None):
+  engine, ops = _ops()
+  RM = engine.RM
+  torch.manual_seed(M * 7 + N * 3 + K)
+  N_valid = N_valid or N
+  kch = (K + 63) // 64
+  x = bf(torch.randn(M, K, device=DEV))
+  w = torch.zeros(N, kch * 64, device=DEV)
+  w[:N_valid, :K] = torch.randn(N_valid, K, device=DEV) / math.sqrt(K)
+  w = bf(w)
+  bias = torch.randn(N_valid, device=DEV)
+  out = torch.full((M, N_valid), float("nan"), device=DEV, dtype=torch.float32 if f32_out else torch.bfloat16)
+  ops.tc_gemm(x, (M, 1, 1, K), (M, 1, 1), (1, 1, 128), [(0, 0)], kch, w, N, N_valid, bias, out,
+              RM.dense(N_valid), c_f32=f32_out, flags=engine.RELU if relu else 0)
+  torch.cuda.synchronize()
+  ref = F.linear(x.float(), w[:N_valid, :K].float(), bias)
+  if relu:
+    ref = F.relu(ref)
+  return rel(out.float(), ref)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 64, 128), (1000, 256, 256), (77, 192, 64),
+                                   (5000, 32, 256), (260, 16, 256), (513, 1024, 256)])
+def test_tc_linear_forward(M, N, K):
+  assert _linear_case(M, N, K, True, False) < 5e-3
+
+
+def test_tc_linear_fp32_out_and_padded_n():
+  assert _linear_case(200, 16, 256, False, True, N_valid=12) < 1e-5
+  assert _linear_case(200, 16, 256, False, True, N_valid=1) < 1e-5
+  assert _linear_case(333, 64, 93 + 35, True, True) < 1e-5
+
+
+def test_tc_mask_and_accumulate():
+  engine, ops = _ops()
+  RM = engine.RM
+  torch.manual_seed(3)
+  M, N, K = 400, 128, 64
+  x = bf(torch.randn(M, K, device=DEV)); w = bf(torch.randn(N, K, device=DEV) / 8)
+  mask = bf(torch.randn(M, N, device=DEV))
+  out = bf(torch.randn(M, N, device=DEV))
+  old = out.clone()
+  ops.tc_gemm(x, (M, 1, 1, K), (M, 1, 1), (1, 1, 128), [(0, 0)], 1, w, N, N, None, out, RM.dense(N),
+              mask=mask, flags=engine.ACCUM)
+  ref = (x.float() @ w.float().t()) * (mask.float() > 0) + old.float()
+  assert rel(out.float(), ref) < 5e-3
+
+
+def test_tc_conv3_taps_and_dgrad():
+  """3x3 stride-1 conv on [B,6,6,64] as 9 tap-shifted boxes {64,4,4,8}; its data-gradient as
+  the same kernel with negative shifts over dY [B,4,4,64] and zero fill."""
+  engine, ops = _ops()
+  RM = engine.RM
+  torch.manual_seed(5)
+  B = 21
+  x = bf(torch.randn(B, 6, 6, 64, device=DEV))                 # NHWC
+  w = bf(torch.randn(64, 64, 3, 3, device=DEV) / 24)           # OIHW
+  bias = torch.randn(64, device=DEV)
+  taps = [(kw, kh) for kh in range(3) for kw in range(3)]
+  wp = w.permute(0, 2, 3, 1).reshape(64, 9 * 64).contiguous()  # [n][(kh,kw),c]
+  out = torch.zeros(B, 4, 4, 64, device=DEV, dtype=torch.bfloat16)
+  ops.tc_gemm(x, (B, 6, 6, 64), (B, 4, 4), (4, 4, 8), taps, 1, wp, 64, 64, bias, out, RM(16, 16 * 64, 64, 0),
+              flags=engine.RELU)
+  ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias)).permute(0, 2, 3, 1)
+  assert rel(out.float(), ref) < 5e-3
+  # data gradient: dx[b,y,x,c] = sum_{kh,kw,n} dy[b,y-kh,x-kw,n] w[n,c,kh,kw]
+  dy = bf(torch.randn(B, 4, 4, 64, device=DEV))
+  wd = w.permute(1, 2, 3, 0).reshape(64, 9 * 64).contiguous()  # [c][(kh,kw),n]
+  dtaps = [(-kw, -kh) for kh in range(3) for kw in range(3)]
+  dx = torch.zeros(B, 6, 6, 64, device=DEV, dtype=torch.bfloat16)
+  ops.tc_gemm(dy, (B, 4, 4, 64), (B, 6, 6), (6, 6, 3), dtaps, 1, wd, 64, 64, None, dx, RM(36, 36 * 64, 64, 0),
+              mask=x)
+  xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+  F.conv2d(xr, w.float()).backward(dy.float().permute(0, 3, 1, 2))
+  ref = xr.grad.permute(0, 2, 3, 1) * (x.float() > 0)
+  assert rel(dx.float(), ref) < 5e-3
+
+
+def test_tc_conv1_space_to_depth():
+  """8x8 stride-4 conv on [4,64,64] == 2x2 stride-1 conv on the 4x4 space-to-depth image
+  [16,16,64] (channel = (py*4+px)*4+c): 4 taps, rows = 15x15 valid outputs, 2 tiles/image."""
+  engine, ops = _ops()
+  RM = engine.RM
+  torch.manual_seed(6)
+  B = 5
+  img = bf(torch.randn(B, 4, 64, 64, device=DEV))
+  w = bf(torch.randn(32, 4, 8, 8, device=DEV) / 16)
+  bias = torch.randn(32, device=DEV)
+  s2d = img.reshape(B, 4, 16, 4, 16, 4).permute(0, 2, 4, 3, 5, 1).reshape(B, 16, 16, 64).contiguous()
+  # w[n, c, 4dy+py, 4dx+px] -> wp[n][(dy,dx)][(py,px,c)]
+  wp = w.reshape(32, 4, 2, 4, 2, 4).permute(0, 2, 4, 3, 5, 1).reshape(32, 4 * 64).contiguous()
+  taps = [(dx, dy) for dy in range(2) for dx in range(2)]
+  out = torch.zeros(B, 15, 15, 32, device=DEV, dtype=torch.bfloat16)
+  ops.tc_gemm(s2d, (B, 16, 16, 64), (B, 15, 15), (15, 8, 1), taps, 1, wp, 32, 32, bias, out,
+              RM(225, 225 * 32, 32, 0), flags=engine.RELU)
+  ref = F.relu(F.conv2d(img.float(), w.float(), bias, stride=4)).permute(0, 2, 3, 1)
+  assert rel(out.float(), ref) < 5e-3

@@ -48,6 +48,18 @@ class WgradArgs(C.Structure):
               ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32)]
 
 
+class TcGemmArgs(C.Structure):
+  _fields_ = [("a", C.c_void_p), ("a_B", C.c_int32), ("a_H", C.c_int32), ("a_W", C.c_int32), ("a_C", C.c_int32),
+              ("B", C.c_int32), ("Hout", C.c_int32), ("Wout", C.c_int32),
+              ("bw", C.c_int32), ("bh", C.c_int32), ("bb", C.c_int32),
+              ("n_taps", C.c_int32), ("kchunks", C.c_int32),
+              ("tap_dw", C.c_int32 * 16), ("tap_dh", C.c_int32 * 16),
+              ("w", C.c_void_p), ("N_pad", C.c_int32), ("N_valid", C.c_int32),
+              ("bias", C.c_void_p),
+              ("c", C.c_void_p), ("c_map", RowMap), ("c_f32", C.c_int32),
+              ("mask", C.c_void_p), ("flags", C.c_int32)]
+
+
 _vp, _i, _i64, _f, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
 
 # name -> argtypes (restype is int unless listed in _RESTYPE)
@@ -76,6 +88,8 @@ SIGNATURES = {
   "v4l_pf_loss": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _f,
                   _f, _vp, _vp],
   "v4l_clip_adam": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i],
+  "v4l_tc_gemm": [_vp, _vp, C.POINTER(TcGemmArgs)],
+  "v4l_pack_bf16": [_vp, _vp, _vp, _vp, _vp, _i64],
   "v4l_h2d_2d": [_vp, _vp, _sz, _vp, _sz, _sz, _sz],
 }
 _RESTYPE = {"v4l_last_error": C.c_char_p}

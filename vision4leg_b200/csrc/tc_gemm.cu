@@ -1,0 +1,345 @@
+// Tensor-core tier: tap-shifted TMA + tcgen05 GEMM (bf16 operands, fp32 accumulators in TMEM).
+//
+//   D[128-row tile, N] = sum_{tap, kc} A_tap[rows, 64 k] * W[N, (tap, kc, 64 k)]^T
+//
+// One kernel covers every forward layer and every data-gradient of the PPO networks:
+//   * A is an NHWC bf16 activation viewed as a 4-D TMA tensor {C, W, H, B}; a row tile is a TMA
+//     box {64, bw, bh, bb} (<= 128 rows).  Convolutions are a sum over taps of the SAME box
+//     shifted by (dw, dh) — implicit im2col done by the TMA unit, out-of-range pixels zero-filled
+//     by the hardware (this also gives the "full" correlation of the data-gradient with negative
+//     shifts).  Plain matrices are the degenerate case W = H = 1, B = M.
+//   * W is a packed bf16 weight matrix [N, taps*kchunks*64] (K-major), one TMA box {64, N}.
+//   * both land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes.
+// Warp roles (192 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 =
+// TMEM allocator + single-thread MMA issuer, warps 2-5 = epilogue (TMEM -> registers -> bias /
+// ReLU / ReLU-mask / accumulate -> global).  4-stage smem ring, 2 TMEM accumulator stages so
+// the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_STAGES = 4;
+constexpr int A_TILE_BYTES = 128 * 128;          // 128 rows x 64 bf16
+constexpr int ACC_COLS = 256;                    // TMEM columns per accumulator stage
+constexpr int MAX_TAPS = 16;
+
+struct TcGemmParams {
+  CUtensorMap tmap_a;
+  CUtensorMap tmap_b;
+  int B, Hout, Wout;
+  int bw, bh, bb;
+  int h_tiles, num_tiles;
+  int n_taps, kchunks;
+  int tap_dw[MAX_TAPS], tap_dh[MAX_TAPS];
+  int N, N_total, N_valid;        // UMMA N per chunk (<=256), padded rows of W, real outputs
+  const float* bias;
+  void* c;
+  v4l_rowmap c_map;
+  int c_f32;
+  const __nv_bfloat16* mask;
+  int flags;
+};
+
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem base is only guaranteed 16-B aligned: round up to 1024 (SWIZZLE_128B atoms)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_chunk = blockIdx.y;
+  const int n0 = n_chunk * 256;
+  const int N = min(p.N, p.N_total - n0);                 // UMMA N of this chunk (multiple of 16)
+  const uint32_t b_bytes = static_cast<uint32_t>(N) * 128u;
+  const uint32_t stage_bytes = A_TILE_BYTES + static_cast<uint32_t>(p.N) * 128u;
+  const int box_rows = p.bw * p.bh * p.bb;
+  const uint32_t a_bytes = static_cast<uint32_t>(box_rows) * 128u;
+  const int k_iters = p.n_taps * p.kchunks;
+
+  if (threadIdx.x == 0) {
+    tc::tma_prefetch_desc(&p.tmap_a);
+    tc::tma_prefetch_desc(&p.tmap_b);
+    for (int s = 0; s < TC_STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&tmem_full[s], 1); tc::mbar_init(&tmem_empty[s], 128); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(&tmem_base_slot, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int b0, h0;
+        if (p.bb == 1) { b0 = tile / p.h_tiles; h0 = (tile - b0 * p.h_tiles) * p.bh; }
+        else           { b0 = tile * p.bb; h0 = 0; }
+        for (int it = 0; it < k_iters; ++it) {
+          const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
+          tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sb = sa + A_TILE_BYTES;
+          tc::mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+          tc::tma_load_4d(sa, &p.tmap_a, &full_bar[stage], kc * 64, p.tap_dw[tap], h0 + p.tap_dh[tap], b0);
+          tc::tma_load_2d(sb, &p.tmap_b, &full_bar[stage], it * 64, n0);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t idesc = tc::umma_idesc_bf16(128, N, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+        for (int it = 0; it < k_iters; ++it) {
+          tc::mbar_wait(&full_bar[stage], phase);
+          tc::tc_fence_after();
+          const uint32_t sa = tc::smem_u32(smem + stage * stage_bytes);
+          const uint32_t sb = sa + A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {                      // 4 x UMMA_K(16) = 64
+            const uint64_t adesc = tc::umma_smem_desc(sa + k * 32, 0, 1024);
+            const uint64_t bdesc = tc::umma_smem_desc(sb + k * 32, 0, 1024);
+            tc::umma_f16(d_tmem, adesc, bdesc, idesc, (it | k) ? 1u : 0u);
+          }
+          tc::umma_commit(&empty_bar[stage]);                // frees the smem stage when MMAs retire
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc::umma_commit(&tmem_full[acc]);                    // accumulator ready for the epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ============================== epilogue ==================================
+    const int quad = warp & 3;                               // TMEM lane quadrant of this warp
+    const int r = quad * 32 + lane;                          // row inside the tile
+    const bool relu = p.flags & V4L_RELU, accum = p.flags & V4L_ACCUM;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int b0, h0;
+      if (p.bb == 1) { b0 = tile / p.h_tiles; h0 = (tile - b0 * p.h_tiles) * p.bh; }
+      else           { b0 = tile * p.bb; h0 = 0; }
+      // row r of the box = (w fastest, then h, then b)
+      const int ww = r % p.bw;
+      const int t2 = r / p.bw;
+      const int hh = t2 % p.bh;
+      const int bi = t2 / p.bh;
+      const int b = b0 + bi, h = h0 + hh;
+      const bool row_ok = (r < box_rows) && (b < p.B) && (h < p.Hout);
+      long long row_addr = 0;
+      if (row_ok) row_addr = v4l_row_addr(p.c_map, (b * p.Hout + h) * p.Wout + ww) + n0;
+
+      tc::mbar_wait(&tmem_full[acc], acc_phase);
+      tc::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * ACC_COLS;
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        if (N - c0 >= 32) {
+          tc::tmem_ld_32x32(taddr + c0, v);
+        } else {
+          uint32_t v16[16];
+          tc::tmem_ld_32x16(taddr + c0, v16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { v[j] = v16[j]; v[16 + j] = 0; }
+        }
+        tc::tmem_ld_wait();
+        if (!row_ok) continue;
+        const int ncols = min(32, N - c0);
+#pragma unroll
+        for (int j0 = 0; j0 < 32; j0 += 8) {
+          if (j0 >= ncols) break;
+          const int n = n0 + c0 + j0;                        // absolute output column
+          if (n >= p.N_valid) break;
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            f[j] = __uint_as_float(v[j0 + j]);
+            if (p.bias && n + j < p.N_valid) f[j] += p.bias[n + j];
+            if (relu) f[j] = fmaxf(f[j], 0.f);
+          }
+          const long long addr = row_addr + c0 + j0;
+          const bool full8 = (n + 8 <= p.N_valid);
+          if (!p.c_f32 && full8 && ((addr & 7) == 0)) {
+            __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.c) + addr;
+            if (p.mask) {
+              const uint4 m = *reinterpret_cast<const uint4*>(p.mask + addr);
+              const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (!(bf16_lo(mw[j]) > 0.f)) f[2 * j] = 0.f;
+                if (!(bf16_hi(mw[j]) > 0.f)) f[2 * j + 1] = 0.f;
+              }
+            }
+            if (accum) {
+              const uint4 o = *reinterpret_cast<const uint4*>(cp);
+              const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { f[2 * j] += bf16_lo(ow[j]); f[2 * j + 1] += bf16_hi(ow[j]); }
+            }
+            uint4 o;
+            o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+            o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+            *reinterpret_cast<uint4*>(cp) = o;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (n + j >= p.N_valid) break;
+              float x = f[j];
+              if (p.mask && !(__bfloat162float(p.mask[addr + j]) > 0.f)) x = 0.f;
+              if (p.c_f32) {
+                float* cp = reinterpret_cast<float*>(p.c) + addr + j;
+                if (accum) x += *cp;
+                *cp = x;
+              } else {
+                __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.c) + addr + j;
+                if (accum) x += __bfloat162float(*cp);
+                *cp = __float2bfloat16(x);
+              }
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+      tc::mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+}  // namespace
+
+int v4l_encode_tmap(CUtensorMap* out, const void* gaddr, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, const char* who) {
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !fn) {
+      v4l_set_error("%s: cuTensorMapEncodeTiled entry point unavailable (%s)", who, cudaGetErrorString(e));
+      return -2;
+    }
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  cuuint64_t gd[5], gs[5];
+  cuuint32_t bx[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(gaddr), gd, gs, bx, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    v4l_set_error("%s: cuTensorMapEncodeTiled failed (CUresult %d; rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u)",
+                  who, (int)r, rank, (unsigned long long)gd[0], (unsigned long long)(rank > 1 ? gd[1] : 0),
+                  (unsigned long long)(rank > 2 ? gd[2] : 0), (unsigned long long)(rank > 3 ? gd[3] : 0), bx[0],
+                  rank > 1 ? bx[1] : 0, rank > 2 ? bx[2] : 0, rank > 3 ? bx[3] : 0);
+    return -2;
+  }
+  return 0;
+}
+
+extern "C" int v4l_tc_gemm(v4l_ctx* ctx, void* stream, const v4l_tc_gemm_args* a) {
+  V4L_REQUIRE(ctx && a && a->a && a->w && a->c, "v4l_tc_gemm: NULL argument");
+  V4L_REQUIRE(a->n_taps >= 1 && a->n_taps <= MAX_TAPS && a->kchunks >= 1, "v4l_tc_gemm: bad taps/kchunks");
+  V4L_REQUIRE(a->a_C % 8 == 0 && a->kchunks * 64 <= ((a->a_C + 63) / 64) * 64, "v4l_tc_gemm: bad channel count %d", a->a_C);
+  V4L_REQUIRE(a->N_pad % 16 == 0 && a->N_pad >= 16, "v4l_tc_gemm: N_pad=%d must be a multiple of 16", a->N_pad);
+  V4L_REQUIRE(a->N_pad <= 256 || a->N_pad % 256 == 0, "v4l_tc_gemm: N_pad > 256 must be a multiple of 256");
+  V4L_REQUIRE(a->N_valid >= 1 && a->N_valid <= a->N_pad, "v4l_tc_gemm: bad N_valid");
+  const int rows = a->bw * a->bh * a->bb;
+  V4L_REQUIRE(rows >= 1 && rows <= 128 && a->bw == a->Wout && a->bw <= 256 && a->bh <= 256 && a->bb <= 256,
+              "v4l_tc_gemm: bad box %dx%dx%d (Wout=%d)", a->bw, a->bh, a->bb, a->Wout);
+  V4L_REQUIRE(a->bb == 1 || a->bh == a->Hout, "v4l_tc_gemm: multi-item boxes must cover the whole image");
+  V4L_REQUIRE(a->c_map.P > 0, "v4l_tc_gemm: row map with P <= 0");
+  if (a->B == 0) return 0;
+
+  TcGemmParams p;
+  memset(&p, 0, sizeof(p));
+  {
+    uint64_t dims[4] = {(uint64_t)a->a_C, (uint64_t)a->a_W, (uint64_t)a->a_H, (uint64_t)a->a_B};
+    uint64_t str[3] = {(uint64_t)a->a_C * 2, (uint64_t)a->a_C * a->a_W * 2, (uint64_t)a->a_C * a->a_W * a->a_H * 2};
+    uint32_t box[4] = {64, (uint32_t)a->bw, (uint32_t)a->bh, (uint32_t)a->bb};
+    if (int r = v4l_encode_tmap(&p.tmap_a, a->a, 4, dims, str, box, "v4l_tc_gemm(A)")) return r;
+  }
+  const int Ktot = a->n_taps * a->kchunks * 64;
+  const int Nchunk = a->N_pad > 256 ? 256 : a->N_pad;
+  {
+    uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)a->N_pad};
+    uint64_t str[1] = {(uint64_t)Ktot * 2};
+    uint32_t box[2] = {64, (uint32_t)Nchunk};
+    if (int r = v4l_encode_tmap(&p.tmap_b, a->w, 2, dims, str, box, "v4l_tc_gemm(W)")) return r;
+  }
+  p.B = a->B; p.Hout = a->Hout; p.Wout = a->Wout;
+  p.bw = a->bw; p.bh = a->bh; p.bb = a->bb;
+  p.h_tiles = (a->bb == 1) ? v4l_cdiv(a->Hout, a->bh) : 1;
+  p.num_tiles = (a->bb == 1) ? a->B * p.h_tiles : v4l_cdiv(a->B, a->bb);
+  p.n_taps = a->n_taps; p.kchunks = a->kchunks;
+  for (int t = 0; t < a->n_taps; ++t) { p.tap_dw[t] = a->tap_dw[t]; p.tap_dh[t] = a->tap_dh[t]; }
+  p.N = Nchunk; p.N_total = a->N_pad; p.N_valid = a->N_valid;
+  p.bias = a->bias; p.c = a->c; p.c_map = a->c_map; p.c_f32 = a->c_f32;
+  p.mask = reinterpret_cast<const __nv_bfloat16*>(a->mask);
+  p.flags = a->flags;
+
+  const size_t smem = (size_t)TC_STAGES * (A_TILE_BYTES + (size_t)Nchunk * 128) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    V4L_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const int n_chunks = a->N_pad / Nchunk;
+  dim3 grid(min(p.num_tiles, max(1, ctx->sm_count / n_chunks)), n_chunks);
+  tc_gemm_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
+  V4L_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---- helper kernels of the tier: packing / conversion ------------------------------------------
+namespace {
+__global__ void pack_bf16_kernel(const float* __restrict__ src, const int32_t* __restrict__ index,
+                                 __nv_bfloat16* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long s = index ? (long long)index[i] : i;
+    dst[i] = __float2bfloat16(s >= 0 ? src[s] : 0.f);
+  }
+}
+}  // namespace
+
+extern "C" int v4l_pack_bf16(v4l_ctx* ctx, void* stream, const float* src, const int32_t* index, void* dst,
+                             int64_t n) {
+  V4L_REQUIRE(ctx && src && dst && n >= 0, "v4l_pack_bf16: bad argument");
+  if (n == 0) return 0;
+  const int blocks = (int)min((long long)8 * ctx->sm_count, (long long)((n + 255) / 256));
+  pack_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, index, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  V4L_CHECK_LAUNCH();
+  return 0;
+}

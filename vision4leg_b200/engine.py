@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import RowMap, GemmArgs, WgradArgs, RELU, ACCUM, check, ptr
+from ._lib import RowMap, GemmArgs, WgradArgs, TcGemmArgs, RELU, ACCUM, check, ptr
 
 IMG_C, IMG_H, IMG_W = 4, 64, 64
 IMG_ELEMS = IMG_C * IMG_H * IMG_W
@@ -110,6 +110,28 @@ class Ops:
   def col2im(self, dcol, x, dx, B, Hin, Win, Cc, KH, KW, stride, Hout, Wout):
     check(self.lib.v4l_col2im(self.h, self.ctx.stream(), ptr(dcol), ptr(x), ptr(dx), B, Hin, Win, Cc,
                               KH, KW, stride, Hout, Wout))
+    self.launches += 1
+
+  # ---- tensor-core tier
+  def tc_gemm(self, a, a_shape, out_grid, box, taps, kchunks, w, N_pad, N_valid, bias, c, c_map,
+              c_f32=False, mask=None, flags=0):
+    """a: bf16 [a_B, a_H, a_W, a_C]; out_grid (B, Hout, Wout); box (bw, bh, bb); taps [(dw, dh)]"""
+    g = TcGemmArgs()
+    g.a = ptr(a)
+    g.a_B, g.a_H, g.a_W, g.a_C = a_shape
+    g.B, g.Hout, g.Wout = out_grid
+    g.bw, g.bh, g.bb = box
+    g.n_taps, g.kchunks = len(taps), kchunks
+    for i, (dw, dh) in enumerate(taps):
+      g.tap_dw[i], g.tap_dh[i] = dw, dh
+    g.w, g.N_pad, g.N_valid = ptr(w), N_pad, N_valid
+    g.bias, g.c, g.c_map, g.c_f32 = ptr(bias), ptr(c), c_map.c(), 1 if c_f32 else 0
+    g.mask, g.flags = ptr(mask), flags
+    check(self.lib.v4l_tc_gemm(self.h, self.ctx.stream(), C.byref(g)))
+    self.launches += 1
+
+  def pack_bf16(self, src, index, dst, n):
+    check(self.lib.v4l_pack_bf16(self.h, self.ctx.stream(), ptr(src), ptr(index), ptr(dst), n))
     self.launches += 1
 
   # ---- transformer pieces
