@@ -188,6 +188,25 @@ typedef struct {
   int32_t flags;
 } v4l_tc_gemm_args;
 int v4l_tc_gemm(v4l_ctx* ctx, void* stream, const v4l_tc_gemm_args* args);
+/* dw[index[n*Kp + kp]] = sum_rows X_tap[row, kp] * dY[row, n], Kp = n_taps * x_C, through
+ * tcgen05 with MN-major operands (no transposed copies); x: bf16 [x_B,x_H,x_W,x_C], dy: bf16
+ * [B,Hout,Wout,dy_C]; the row tiles are the same boxes as the forward pass.  index = the
+ * weight-packing table (or NULL for dw[n*Kp + kp]).  Deterministic (fixed split order).       */
+typedef struct {
+  const void* x;   int32_t x_B, x_H, x_W, x_C;
+  const void* dy;  int32_t dy_C;
+  int32_t B, Hout, Wout;
+  int32_t bw, bh, bb;
+  int32_t n_taps;
+  int32_t tap_dw[16], tap_dh[16];
+  int32_t N_valid;
+  const int32_t* index;
+  float* dw;
+} v4l_tc_wgrad_args;
+int v4l_tc_wgrad(v4l_ctx* ctx, void* stream, const v4l_tc_wgrad_args* args);
+/* out[n] = sum_m dy(m, n) for a row-mapped bf16 [M, N<=256] view (bias gradients)            */
+int v4l_colsum_bf16(v4l_ctx* ctx, void* stream, const void* dy, const v4l_rowmap* map, int M, int N,
+                    float* out);
 /* dst_bf16[i] = index ? (index[i] >= 0 ? src[index[i]] : 0) : src[i]  — weight packing /
  * fp32 -> bf16 conversion for the tensor-core tier                                            */
 int v4l_pack_bf16(v4l_ctx* ctx, void* stream, const float* src, const int32_t* index, void* dst,

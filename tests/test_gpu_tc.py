@@ -124,3 +124,55 @@ def test_tc_conv1_space_to_depth():
               RM(225, 225 * 32, 32, 0), flags=engine.RELU)
   ref = F.relu(F.conv2d(img.float(), w.float(), bias, stride=4)).permute(0, 2, 3, 1)
   assert rel(out.float(), ref) < 5e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 64, 256), (4096, 192, 64), (300, 16, 256), (17408, 256, 64), (1024, 256, 1024)])
+def test_tc_wgrad_linear(M, N, K):
+  engine, ops = _ops()
+  RM = engine.RM
+  torch.manual_seed(M + N + K)
+  x = bf(torch.randn(M, K, device=DEV))
+  N_valid = 12 if N == 16 else N
+  dy = torch.zeros(M, N, device=DEV)
+  dy[:, :N_valid] = torch.randn(M, N_valid, device=DEV)
+  dy = bf(dy)
+  dw = torch.full((N_valid, K), float("nan"), device=DEV)
+  ops.tc_wgrad(x, (M, 1, 1, K), dy, N, (M, 1, 1), (1, 1, 128), [(0, 0)], N_valid, None, dw)
+  ref = dy.float()[:, :N_valid].t() @ x.float()
+  assert rel(dw, ref) < 1e-4
+  db = torch.empty(N_valid, device=DEV)
+  ops.colsum_bf16(dy, RM.dense(N), M, N_valid, db)
+  assert rel(db, dy.float()[:, :N_valid].sum(0)) < 1e-4
+
+
+def test_tc_wgrad_conv3_and_conv1():
+  engine, ops = _ops()
+  torch.manual_seed(11)
+  # conv3: 9 taps x 64 channels = 576 packed K (4.5 tiles of 128)
+  B = 37
+  x = bf(torch.randn(B, 6, 6, 64, device=DEV))
+  dy = bf(torch.randn(B, 4, 4, 64, device=DEV))
+  taps = [(kw, kh) for kh in range(3) for kw in range(3)]
+  # packed kp = (kh,kw,c) -> reference OIHW flat index n*576 + c*9 + kh*3 + kw
+  n_, kh_, kw_, c_ = np.meshgrid(np.arange(64), np.arange(3), np.arange(3), np.arange(64), indexing="ij")
+  index = torch.tensor((n_ * 576 + c_ * 9 + kh_ * 3 + kw_).reshape(64, 576).astype(np.int32), device=DEV)
+  dw = torch.full((64, 64, 3, 3), float("nan"), device=DEV)
+  ops.tc_wgrad(x, (B, 6, 6, 64), dy, 64, (B, 4, 4), (4, 4, 4), taps, 64, index, dw)
+  w = torch.zeros(64, 64, 3, 3, device=DEV, requires_grad=True)
+  F.conv2d(x.float().permute(0, 3, 1, 2), w).backward(dy.float().permute(0, 3, 1, 2))
+  assert rel(dw, w.grad) < 1e-4
+  # conv1 in space-to-depth form: dy has 32 channels (TMA zero-fills 32..63), 120-row boxes
+  B = 9
+  img = bf(torch.randn(B, 4, 64, 64, device=DEV))
+  s2d = img.reshape(B, 4, 16, 4, 16, 4).permute(0, 2, 4, 3, 5, 1).reshape(B, 16, 16, 64).contiguous()
+  dy = bf(torch.randn(B, 15, 15, 32, device=DEV))
+  taps = [(dx, dy_) for dy_ in range(2) for dx in range(2)]
+  n_, dy_, dx_, py_, px_, c_ = np.meshgrid(np.arange(32), np.arange(2), np.arange(2), np.arange(4), np.arange(4),
+                                           np.arange(4), indexing="ij")
+  index = torch.tensor((n_ * 256 + c_ * 64 + (4 * dy_ + py_) * 8 + (4 * dx_ + px_)).reshape(32, 256).astype(np.int32),
+                       device=DEV)
+  dw = torch.full((32, 4, 8, 8), float("nan"), device=DEV)
+  ops.tc_wgrad(s2d, (B, 16, 16, 64), dy, 32, (B, 15, 15), (15, 8, 1), taps, 32, index, dw)
+  w = torch.zeros(32, 4, 8, 8, device=DEV, requires_grad=True)
+  F.conv2d(img.float(), w, stride=4).backward(dy.float().permute(0, 3, 1, 2))
+  assert rel(dw, w.grad) < 1e-4

@@ -60,6 +60,15 @@ class TcGemmArgs(C.Structure):
               ("mask", C.c_void_p), ("flags", C.c_int32)]
 
 
+class TcWgradArgs(C.Structure):
+  _fields_ = [("x", C.c_void_p), ("x_B", C.c_int32), ("x_H", C.c_int32), ("x_W", C.c_int32), ("x_C", C.c_int32),
+              ("dy", C.c_void_p), ("dy_C", C.c_int32),
+              ("B", C.c_int32), ("Hout", C.c_int32), ("Wout", C.c_int32),
+              ("bw", C.c_int32), ("bh", C.c_int32), ("bb", C.c_int32),
+              ("n_taps", C.c_int32), ("tap_dw", C.c_int32 * 16), ("tap_dh", C.c_int32 * 16),
+              ("N_valid", C.c_int32), ("index", C.c_void_p), ("dw", C.c_void_p)]
+
+
 _vp, _i, _i64, _f, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
 
 # name -> argtypes (restype is int unless listed in _RESTYPE)
@@ -89,6 +98,8 @@ SIGNATURES = {
                   _f, _vp, _vp],
   "v4l_clip_adam": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i],
   "v4l_tc_gemm": [_vp, _vp, C.POINTER(TcGemmArgs)],
+  "v4l_tc_wgrad": [_vp, _vp, C.POINTER(TcWgradArgs)],
+  "v4l_colsum_bf16": [_vp, _vp, _vp, C.POINTER(RowMap), _i, _i, _vp],
   "v4l_pack_bf16": [_vp, _vp, _vp, _vp, _vp, _i64],
   "v4l_h2d_2d": [_vp, _vp, _sz, _vp, _sz, _sz, _sz],
 }

@@ -343,3 +343,279 @@ extern "C" int v4l_pack_bf16(v4l_ctx* ctx, void* stream, const float* src, const
   V4L_CHECK_LAUNCH();
   return 0;
 }
+
+// =================================================================================================
+// Weight gradient on tensor cores:  D[kin (128 lanes), n] = sum_rows X_tap[row, kin] * dY[row, n]
+//
+// Both operands are read exactly as they sit in HBM (row = reduction index, 64 contiguous
+// channels) by the same tap-shifted TMA boxes as the forward pass and consumed as MN-major
+// SWIZZLE_128B operands (instruction-descriptor transpose bits), so no transposed copy of any
+// activation or gradient is ever written.  A CTA owns one 128-wide slice of the packed K index
+// (tap, c) and one split of the row tiles; fp32 partials go to the context scratch and
+// tc_wgrad_reduce_kernel sums the splits in a fixed order and scatters into the reference-layout
+// fp32 gradient through the weight-packing index table.
+// =================================================================================================
+namespace {
+
+constexpr int WG_THREADS = 192;
+constexpr int ATOM_BYTES = 128 * 128;           // [<=128 reduction rows][64 channels] bf16
+
+struct TcWgradParams {
+  CUtensorMap tmap_x;
+  CUtensorMap tmap_dy;
+  int B, Hout, Wout;
+  int bw, bh, bb;
+  int h_tiles, num_tiles, tiles_per_split;
+  int n_taps, x_C;
+  int tap_dw[MAX_TAPS], tap_dh[MAX_TAPS];
+  int n_atoms;                 // dY atoms of 64 channels (UMMA N = 64 * n_atoms)
+  int stages;
+  float* partial;              // [splits][kin_tiles][128][64 * n_atoms]
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ TcWgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full_bar[4], empty_bar[4], tmem_full;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, kt = blockIdx.y;
+  const int Nmma = 64 * p.n_atoms;
+  const int box_rows = p.bw * p.bh * p.bb;
+  const int ksteps = (box_rows + 15) / 16;
+  const uint32_t stage_bytes = (2 + p.n_atoms) * ATOM_BYTES;
+  const int tile_lo = split * p.tiles_per_split;
+  const int tile_hi = min(p.num_tiles, tile_lo + p.tiles_per_split);
+
+  // zero the ring once: rows beyond the TMA box stay zero for the whole kernel, so the padded
+  // K-steps (box rows not a multiple of 16) contribute exactly 0
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const int n16 = p.stages * stage_bytes / 16;
+    for (int i = threadIdx.x; i < n16; i += WG_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (threadIdx.x == 0) {
+    tc::tma_prefetch_desc(&p.tmap_x);
+    tc::tma_prefetch_desc(&p.tmap_dy);
+    for (int s = 0; s < 4; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    tc::mbar_init(&tmem_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(&tmem_base_slot, 256);
+  tc::fence_proxy_async();          // generic-proxy zero fill -> visible to the async (TMA/UMMA) proxy
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // the two 64-channel atoms of this CTA's K slice: packed index kp = tap * x_C + c
+      int a_tap[2], a_c0[2];
+      for (int j = 0; j < 2; ++j) {
+        const int kp0 = kt * 128 + j * 64;
+        int tap = kp0 / p.x_C, c0 = kp0 - tap * p.x_C;
+        if (tap >= p.n_taps) { tap = p.n_taps - 1; c0 = p.x_C; }       // beyond K: all-OOB box -> zeros
+        a_tap[j] = tap; a_c0[j] = c0;
+      }
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = tile_lo; tile < tile_hi; ++tile) {
+        int b0, h0;
+        if (p.bb == 1) { b0 = tile / p.h_tiles; h0 = (tile - b0 * p.h_tiles) * p.bh; }
+        else           { b0 = tile * p.bb; h0 = 0; }
+        tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* s = smem + stage * stage_bytes;
+        tc::mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(2 + p.n_atoms) * box_rows * 128u);
+        for (int j = 0; j < 2; ++j)
+          tc::tma_load_4d(s + j * ATOM_BYTES, &p.tmap_x, &full_bar[stage], a_c0[j], p.tap_dw[a_tap[j]],
+                          h0 + p.tap_dh[a_tap[j]], b0);
+        for (int j = 0; j < p.n_atoms; ++j)
+          tc::tma_load_4d(s + (2 + j) * ATOM_BYTES, &p.tmap_dy, &full_bar[stage], j * 64, 0, h0, b0);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = tc::umma_idesc_bf16(128, Nmma, 1, 1);     // both operands MN-major
+      int stage = 0; uint32_t phase = 0;
+      uint32_t first = 1;
+      for (int tile = tile_lo; tile < tile_hi; ++tile) {
+        tc::mbar_wait(&full_bar[stage], phase);
+        tc::tc_fence_after();
+        const uint32_t sa = tc::smem_u32(smem + stage * stage_bytes);
+        const uint32_t sb = sa + 2 * ATOM_BYTES;
+        for (int k = 0; k < ksteps; ++k) {
+          // MN-major SW128: 16 reduction rows per MMA = 2 groups of 8 rows (SBO = 1024 B);
+          // consecutive 64-channel atoms are ATOM_BYTES apart (LBO)
+          const uint64_t adesc = tc::umma_smem_desc(sa + k * 2048, ATOM_BYTES, 1024);
+          const uint64_t bdesc = tc::umma_smem_desc(sb + k * 2048, ATOM_BYTES, 1024);
+          tc::umma_f16(tmem_base, adesc, bdesc, idesc, first ? 0u : 1u);
+          first = 0;
+        }
+        tc::umma_commit(&empty_bar[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      tc::umma_commit(&tmem_full);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    float* out = p.partial + ((static_cast<long long>(split) * gridDim.y + kt) * 128 + r) * Nmma;
+    if (tile_hi > tile_lo) {
+      tc::mbar_wait(&tmem_full, 0);
+      tc::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+      for (int c0 = 0; c0 < Nmma; c0 += 32) {
+        uint32_t v[32];
+        tc::tmem_ld_32x32(taddr + c0, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(out + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    } else {
+      for (int c = 0; c < Nmma; c += 4) *reinterpret_cast<uint4*>(out + c) = make_uint4(0, 0, 0, 0);
+    }
+    tc::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// dw[index[n*Kp + kp]] = sum_split partial[split][kp/128][kp%128][n]
+__global__ void tc_wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int kin_tiles, int Nmma,
+                                       int N_valid, int Kp, const int32_t* __restrict__ index,
+                                       float* __restrict__ dw) {
+  const long long total = (long long)N_valid * Kp;
+  const long long split_stride = (long long)kin_tiles * 128 * Nmma;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int kp = (int)(e % Kp), n = (int)(e / Kp);        // consecutive threads: consecutive kp
+    const long long dst = index ? (long long)index[(long long)n * Kp + kp] : e;
+    if (dst < 0) continue;
+    const float* src = partial + (long long)kp * Nmma + n;
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += src[z * split_stride];
+    dw[dst] = s;
+  }
+}
+
+// column sums of a row-mapped bf16 [M, N] matrix (bias gradients), two deterministic stages
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                          const v4l_rowmap map, int M, int N,
+                                                          int rows_per_cta, float* __restrict__ part) {
+  __shared__ float red[8][256];
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  const int c = threadIdx.x & 31, w = threadIdx.x >> 5;     // 8 row-lanes x 32 column-lanes
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int m = r0 + w; m < r1; m += 8) {
+    const long long a = v4l_row_addr(map, m);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int n = c + 32 * i;
+      if (n < N) acc[i] += __bfloat162float(dy[a + n]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[w][c + 32 * i] = acc[i];
+  __syncthreads();
+  for (int n = threadIdx.x; n < N; n += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][n];
+    part[(long long)blockIdx.x * N + n] = s;
+  }
+}
+__global__ void colsum_reduce_kernel(const float* __restrict__ part, int nparts, int N, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += part[(long long)p * N + n];
+  out[n] = s;
+}
+
+}  // namespace
+
+extern "C" int v4l_tc_wgrad(v4l_ctx* ctx, void* stream, const v4l_tc_wgrad_args* a) {
+  V4L_REQUIRE(ctx && a && a->x && a->dy && a->dw, "v4l_tc_wgrad: NULL argument");
+  V4L_REQUIRE(a->n_taps >= 1 && a->n_taps <= MAX_TAPS, "v4l_tc_wgrad: bad taps");
+  V4L_REQUIRE(a->x_C % 64 == 0 && a->dy_C % 8 == 0, "v4l_tc_wgrad: x_C must be a multiple of 64, dy_C of 8");
+  V4L_REQUIRE(a->N_valid >= 1 && a->N_valid <= a->dy_C && a->dy_C <= 256, "v4l_tc_wgrad: bad N");
+  const int rows = a->bw * a->bh * a->bb;
+  V4L_REQUIRE(rows >= 1 && rows <= 128 && a->bw == a->Wout, "v4l_tc_wgrad: bad box %dx%dx%d", a->bw, a->bh, a->bb);
+  V4L_REQUIRE(a->bb == 1 || a->bh == a->Hout, "v4l_tc_wgrad: multi-item boxes must cover the whole image");
+  if (a->B == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+
+  TcWgradParams p;
+  memset(&p, 0, sizeof(p));
+  {
+    uint64_t dims[4] = {(uint64_t)a->x_C, (uint64_t)a->x_W, (uint64_t)a->x_H, (uint64_t)a->x_B};
+    uint64_t str[3] = {(uint64_t)a->x_C * 2, (uint64_t)a->x_C * a->x_W * 2, (uint64_t)a->x_C * a->x_W * a->x_H * 2};
+    uint32_t box[4] = {64, (uint32_t)a->bw, (uint32_t)a->bh, (uint32_t)a->bb};
+    if (int r = v4l_encode_tmap(&p.tmap_x, a->x, 4, dims, str, box, "v4l_tc_wgrad(X)")) return r;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)a->dy_C, (uint64_t)a->Wout, (uint64_t)a->Hout, (uint64_t)a->B};
+    uint64_t str[3] = {(uint64_t)a->dy_C * 2, (uint64_t)a->dy_C * a->Wout * 2,
+                       (uint64_t)a->dy_C * a->Wout * a->Hout * 2};
+    uint32_t box[4] = {64, (uint32_t)a->bw, (uint32_t)a->bh, (uint32_t)a->bb};
+    if (int r = v4l_encode_tmap(&p.tmap_dy, a->dy, 4, dims, str, box, "v4l_tc_wgrad(dY)")) return r;
+  }
+  p.B = a->B; p.Hout = a->Hout; p.Wout = a->Wout;
+  p.bw = a->bw; p.bh = a->bh; p.bb = a->bb;
+  p.h_tiles = (a->bb == 1) ? v4l_cdiv(a->Hout, a->bh) : 1;
+  p.num_tiles = (a->bb == 1) ? a->B * p.h_tiles : v4l_cdiv(a->B, a->bb);
+  p.n_taps = a->n_taps; p.x_C = a->x_C;
+  for (int t = 0; t < a->n_taps; ++t) { p.tap_dw[t] = a->tap_dw[t]; p.tap_dh[t] = a->tap_dh[t]; }
+  p.n_atoms = v4l_cdiv(a->dy_C, 64);
+  const int Nmma = 64 * p.n_atoms;
+  const int Kp = a->n_taps * a->x_C;
+  const int kin_tiles = v4l_cdiv(Kp, 128);
+  const size_t stage_bytes = (size_t)(2 + p.n_atoms) * ATOM_BYTES;
+  p.stages = (int)min((size_t)4, (size_t)(200 * 1024 - 1024) / stage_bytes);
+  int splits = max(1, min(p.num_tiles, ctx->sm_count / kin_tiles));
+  splits = (int)min((size_t)splits, ctx->scratch_elems / ((size_t)kin_tiles * 128 * Nmma));
+  V4L_REQUIRE(splits >= 1, "v4l_tc_wgrad: scratch too small");
+  p.tiles_per_split = v4l_cdiv(p.num_tiles, splits);
+  splits = v4l_cdiv(p.num_tiles, p.tiles_per_split);
+  p.partial = ctx->scratch;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    V4L_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  tc_wgrad_kernel<<<dim3(splits, kin_tiles), WG_THREADS, smem, s>>>(p);
+  V4L_CHECK_LAUNCH();
+  const long long total = (long long)a->N_valid * Kp;
+  const int rblocks = (int)min((long long)4 * ctx->sm_count, (total + 255) / 256);
+  tc_wgrad_reduce_kernel<<<rblocks, 256, 0, s>>>(ctx->scratch, splits, kin_tiles, Nmma, a->N_valid, Kp, a->index, a->dw);
+  V4L_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int v4l_colsum_bf16(v4l_ctx* ctx, void* stream, const void* dy, const v4l_rowmap* map, int M, int N,
+                               float* out) {
+  V4L_REQUIRE(ctx && dy && map && out && map->P > 0, "v4l_colsum_bf16: bad argument");
+  V4L_REQUIRE(N >= 1 && N <= 256 && M >= 1, "v4l_colsum_bf16: bad shape M=%d N=%d", M, N);
+  cudaStream_t s = (cudaStream_t)stream;
+  int ctas = min(2 * ctx->sm_count, v4l_cdiv(M, 64));
+  const int rpc = v4l_cdiv(M, ctas);
+  ctas = v4l_cdiv(M, rpc);
+  // partials live past the region v4l_tc_wgrad uses? no: separate calls are stream-ordered
+  float* part = ctx->scratch;
+  V4L_REQUIRE((size_t)ctas * N <= ctx->scratch_elems, "v4l_colsum_bf16: scratch too small");
+  colsum_bf16_kernel<<<ctas, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), *map, M, N, rpc, part);
+  V4L_CHECK_LAUNCH();
+  colsum_reduce_kernel<<<v4l_cdiv(N, 128), 128, 0, s>>>(part, ctas, N, out);
+  V4L_CHECK_LAUNCH();
+  return 0;
+}

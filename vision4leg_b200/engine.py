@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import RowMap, GemmArgs, WgradArgs, TcGemmArgs, RELU, ACCUM, check, ptr
+from ._lib import RowMap, GemmArgs, WgradArgs, TcGemmArgs, TcWgradArgs, RELU, ACCUM, check, ptr
 
 IMG_C, IMG_H, IMG_W = 4, 64, 64
 IMG_ELEMS = IMG_C * IMG_H * IMG_W
@@ -129,6 +129,25 @@ class Ops:
     g.mask, g.flags = ptr(mask), flags
     check(self.lib.v4l_tc_gemm(self.h, self.ctx.stream(), C.byref(g)))
     self.launches += 1
+
+  def tc_wgrad(self, x, x_shape, dy, dy_C, out_grid, box, taps, N_valid, index, dw):
+    g = TcWgradArgs()
+    g.x = ptr(x)
+    g.x_B, g.x_H, g.x_W, g.x_C = x_shape
+    g.dy, g.dy_C = ptr(dy), dy_C
+    g.B, g.Hout, g.Wout = out_grid
+    g.bw, g.bh, g.bb = box
+    g.n_taps = len(taps)
+    for i, (dw_, dh_) in enumerate(taps):
+      g.tap_dw[i], g.tap_dh[i] = dw_, dh_
+    g.N_valid, g.index, g.dw = N_valid, ptr(index), ptr(dw)
+    check(self.lib.v4l_tc_wgrad(self.h, self.ctx.stream(), C.byref(g)))
+    self.launches += 2
+
+  def colsum_bf16(self, dy, dy_map, M, N, out):
+    m = dy_map.c()
+    check(self.lib.v4l_colsum_bf16(self.h, self.ctx.stream(), ptr(dy), C.byref(m), M, N, ptr(out)))
+    self.launches += 2
 
   def pack_bf16(self, src, index, dst, n):
     check(self.lib.v4l_pack_bf16(self.h, self.ctx.stream(), ptr(src), ptr(index), ptr(dst), n))
