@@ -115,6 +115,19 @@ int v4l_ln_bwd(v4l_ctx* ctx, void* stream, const float* dy, const float* z, cons
 int v4l_pool_fwd(v4l_ctx* ctx, void* stream, const float* tok, float* out, int B, int T, int d, int mode);
 int v4l_pool_bwd(v4l_ctx* ctx, void* stream, const float* dout, float* dtok, int B, int T, int d, int mode);
 
+/* bf16-IO variants of the block pieces for the tensor-core tier (activations and activation
+ * gradients bf16; softmax probabilities, LayerNorm inputs z and statistics, dgamma/dbeta fp32) */
+int v4l_attn_fwd_bf16(v4l_ctx* ctx, void* stream, const void* qkv, void* o, float* p,
+                      int B, int T, int d, int n_head);
+int v4l_attn_bwd_bf16(v4l_ctx* ctx, void* stream, const void* qkv, const float* p, const void* d_o,
+                      void* d_qkv, int B, int T, int d, int n_head);
+int v4l_ln_fwd_bf16(v4l_ctx* ctx, void* stream, const void* a, const void* res, const float* gamma,
+                    const float* beta, void* y, float* z, float* stats, int rows, int d, float eps);
+int v4l_ln_bwd_bf16(v4l_ctx* ctx, void* stream, const void* dy, const float* z, const float* stats,
+                    const float* gamma, void* dz, float* dgamma, float* dbeta, int rows, int d);
+int v4l_pool_fwd_bf16(v4l_ctx* ctx, void* stream, const void* tok, void* out, int B, int T, int d, int mode);
+int v4l_pool_bwd_bf16(v4l_ctx* ctx, void* stream, const void* dout, void* dtok, int B, int T, int d, int mode);
+
 /* ---- GAE / discounted return: reverse segmented scan over the rollout buffer
  *      (reference torchrl/replay_buffers/on_policy.py:17-71; recurrence: SURVEY Appendix A4).
  * rewards/values/terminals/advs/rets: [T,E] fp32; time_limits addressed t*tl_st + e*tl_se
@@ -177,6 +190,8 @@ int v4l_clip_adam(v4l_ctx* ctx, void* stream, float* param, const float* grad, f
  * Same reference layers as v4l_gemm_rows.                                                    */
 typedef struct {
   const void* a;  int32_t a_B, a_H, a_W, a_C;
+  int64_t a_sW, a_sH, a_sB;      /* element strides of the W/H/B dims; 0,0,0 = packed NHWC       */
+  const int32_t* a_idx;          /* optional item gather (minibatch rows); needs bb == 1         */
   int32_t B, Hout, Wout;
   int32_t bw, bh, bb;
   int32_t n_taps, kchunks;
@@ -194,7 +209,14 @@ int v4l_tc_gemm(v4l_ctx* ctx, void* stream, const v4l_tc_gemm_args* args);
  * weight-packing table (or NULL for dw[n*Kp + kp]).  Deterministic (fixed split order).       */
 typedef struct {
   const void* x;   int32_t x_B, x_H, x_W, x_C;
+  int64_t x_sW, x_sH, x_sB;      /* element strides; 0,0,0 = packed                              */
+  int32_t x_estride;             /* traversal stride of X along W and H (1 or 2)                 */
+  const int32_t* x_idx;          /* optional item gather; needs bb == 1                          */
   const void* dy;  int32_t dy_C;
+  int64_t dy_sW, dy_sH, dy_sB;
+  /* optional sub-iterations per row tile (sub-positions of a space-to-depth cell): X shifted by
+   * (sub_dw, sub_dh), dY read from channel offset sub_dyc; n_sub = 0 means one plain pass      */
+  int32_t n_sub;  int32_t sub_dw[4], sub_dh[4], sub_dyc[4];
   int32_t B, Hout, Wout;
   int32_t bw, bh, bb;
   int32_t n_taps;
@@ -204,13 +226,26 @@ typedef struct {
   float* dw;
 } v4l_tc_wgrad_args;
 int v4l_tc_wgrad(v4l_ctx* ctx, void* stream, const v4l_tc_wgrad_args* args);
-/* out[n] = sum_m dy(m, n) for a row-mapped bf16 [M, N<=256] view (bias gradients)            */
+/* out[n] = sum_m sum_f dy(m, f*N + n) for a row-mapped bf16 [M, N*fold <= 256] view (bias
+ * gradients; fold > 1 sums the sub-positions of a space-to-depth cell)                         */
 int v4l_colsum_bf16(v4l_ctx* ctx, void* stream, const void* dy, const v4l_rowmap* map, int M, int N,
-                    float* out);
+                    int fold, float* out);
 /* dst_bf16[i] = index ? (index[i] >= 0 ? src[index[i]] : 0) : src[i]  — weight packing /
  * fp32 -> bf16 conversion for the tensor-core tier                                            */
 int v4l_pack_bf16(v4l_ctx* ctx, void* stream, const float* src, const int32_t* index, void* dst,
                   int64_t n);
+
+/* fp32 CHW [n,4,64,64] depth stack -> bf16 4x4 space-to-depth NHWC [n,16,16,64]
+ * (channel = (py*4+px)*4+c): the layout the tensor-core conv1 reads (one swizzle atom per tap) */
+int v4l_ingest_img(v4l_ctx* ctx, void* stream, const float* img, void* out_s2d, int64_t n_img);
+/* dst_bf16[i, 0:dst_cols] = src[idx ? idx[i] : i, 0:src_cols] zero padded (proprio rows -> K-padded
+ * bf16 operand; also fp32 -> bf16 conversion of loss gradients)                                */
+int v4l_gather_rows_bf16(v4l_ctx* ctx, void* stream, const void* src, int src_is_f32,
+                         const int32_t* idx, void* dst, int rows, int src_cols, int64_t src_stride,
+                         int dst_cols);
+int v4l_relu_bwd_bf16(v4l_ctx* ctx, void* stream, const void* dy, const v4l_rowmap* dy_map,
+                      const void* act, const v4l_rowmap* act_map, void* out,
+                      const v4l_rowmap* out_map, int M, int N);
 
 /* ---- rollout ingest: strided host->device copy (pinned host rows -> aligned device planes);
  *      replaces the float64 fancy-index copy + torch.Tensor(...).to(device) of

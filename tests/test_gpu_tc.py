@@ -176,3 +176,83 @@ def test_tc_wgrad_conv3_and_conv1():
   w = torch.zeros(32, 4, 8, 8, device=DEV, requires_grad=True)
   F.conv2d(img.float(), w, stride=4).backward(dy.float().permute(0, 3, 1, 2))
   assert rel(dw, w.grad) < 1e-4
+
+
+# =================================================================================================
+# whole-network parity of the tensor-core tier (bf16 tier tolerance of the north star: 1e-2)
+# =================================================================================================
+def _tc_agent(B=32, graph=False):
+  from oracle import ppo_oracle as po, synth
+  from tests import _golden as g
+  from tests._harness import build_nets, load_np_sd, make_ppo
+  S, A = g.FAMILIES["loco"]
+  pf, vf = build_nets("loco", S, A)
+  pf_np, vf_np = g.family_weights("loco")
+  load_np_sd(pf, pf_np); load_np_sd(vf, vf_np)
+  pf, vf = pf.to(DEV), vf.to(DEV)
+  agent, logger = make_ppo(pf, vf, None, A, B, B, 1, device=DEV)
+  agent.precision = "bf16"
+  agent.use_cuda_graph = graph
+  agent.current_epoch = 0
+  opf, ovf = po.sd_to_torch(pf_np, vf_np)
+  orc = po.PPOOracle("loco", opf, ovf, S, batch_size=B, opt_epochs=1)
+  rng = np.random.default_rng(21)
+  roll = synth.make_rollout(21, B // 8, 8, S, A, p_term=0.01)
+  batch = {"obs": roll["obs"].reshape(B, -1), "acts": roll["acts"].reshape(B, -1),
+           "advs": rng.standard_normal((B, 1)), "estimate_returns": rng.standard_normal((B, 1)),
+           "values": roll["values"].reshape(B, 1)}
+  return agent, orc, batch, pf, vf
+
+
+def nrm_err(a, b):
+  a, b = a.detach().double().cpu().reshape(-1), torch.as_tensor(b).double().reshape(-1)
+  return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.mark.parametrize("B", [32, 1024])
+def test_tc_tier_update_matches_oracle(B):
+  agent, orc, batch, pf, vf = _tc_agent(B)
+  ref = orc.update(batch)
+  info = agent.update(batch)
+  eng = agent.engine
+  # forward outputs (values / action means): the oracle's last forward of the same weights
+  v_err = rel(eng._bufs(B)["values"], orc._last["values"])
+  m_err = rel(eng._bufs(B)["mean"], orc._last["mean"])
+  print("B=%d value err %.3e mean err %.3e" % (B, v_err, m_err))
+  assert v_err < 1e-2
+  assert m_err < 3e-2   # the actor forward runs on an encoder already stepped by (bf16) critic grads
+  for k in ("Training/vf_loss", "logprob/mean", "advs/mean", "advs/std", "log_std/mean"):
+    assert abs(info[k] - ref[k]) <= 1e-2 * abs(ref[k]) + 1e-4, (k, info[k], ref[k])
+  assert abs(info["grad_norm/vf"] - ref["grad_norm/vf"]) <= 3e-2 * ref["grad_norm/vf"]
+  assert abs(info["grad_norm/pf"] - ref["grad_norm/pf"]) <= 5e-2 * ref["grad_norm/pf"]
+  # gradients, tensor by tensor (norm-wise): bf16 activations/gradients, fp32 accumulation
+  worst = 0.0
+  for k, gr in orc._last["vgrads"].items():
+    e = nrm_err(eng.G_vf[k], gr)
+    worst = max(worst, e)
+    assert e < 6e-2, ("vf", k, e)
+  print("worst vf grad norm-err %.3e" % worst)
+
+
+def test_tc_tier_graph_replay_is_bit_identical():
+  outs = []
+  for graph in (False, True):
+    from oracle import synth
+    from tests import _golden as g
+    from tests._harness import build_nets, load_np_sd, make_ppo, fill_buffer
+    S, A = g.FAMILIES["loco"]
+    pf, vf = build_nets("loco", S, A)
+    pf_np, vf_np = g.family_weights("loco")
+    load_np_sd(pf, pf_np); load_np_sd(vf, vf_np)
+    pf, vf = pf.to(DEV), vf.to(DEV)
+    roll = synth.make_rollout(5, 16, 4, S, A, p_term=0.1)
+    buf = fill_buffer(roll, 16, 4)
+    agent, logger = make_ppo(pf, vf, buf, A, 16, 64, 2, device=DEV)
+    agent.precision = "bf16"
+    agent.use_cuda_graph = graph
+    agent.current_epoch = 3
+    np.random.seed(9)
+    agent.update_per_epoch()
+    outs.append((agent.engine.bucket.flat.clone(), [tuple(i.values()) for i in logger.infos]))
+  assert torch.equal(outs[0][0], outs[1][0])
+  assert outs[0][1] == outs[1][1]

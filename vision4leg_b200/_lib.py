@@ -50,6 +50,7 @@ class WgradArgs(C.Structure):
 
 class TcGemmArgs(C.Structure):
   _fields_ = [("a", C.c_void_p), ("a_B", C.c_int32), ("a_H", C.c_int32), ("a_W", C.c_int32), ("a_C", C.c_int32),
+              ("a_sW", C.c_int64), ("a_sH", C.c_int64), ("a_sB", C.c_int64), ("a_idx", C.c_void_p),
               ("B", C.c_int32), ("Hout", C.c_int32), ("Wout", C.c_int32),
               ("bw", C.c_int32), ("bh", C.c_int32), ("bb", C.c_int32),
               ("n_taps", C.c_int32), ("kchunks", C.c_int32),
@@ -62,7 +63,12 @@ class TcGemmArgs(C.Structure):
 
 class TcWgradArgs(C.Structure):
   _fields_ = [("x", C.c_void_p), ("x_B", C.c_int32), ("x_H", C.c_int32), ("x_W", C.c_int32), ("x_C", C.c_int32),
+              ("x_sW", C.c_int64), ("x_sH", C.c_int64), ("x_sB", C.c_int64), ("x_estride", C.c_int32),
+              ("x_idx", C.c_void_p),
               ("dy", C.c_void_p), ("dy_C", C.c_int32),
+              ("dy_sW", C.c_int64), ("dy_sH", C.c_int64), ("dy_sB", C.c_int64),
+              ("n_sub", C.c_int32), ("sub_dw", C.c_int32 * 4), ("sub_dh", C.c_int32 * 4),
+              ("sub_dyc", C.c_int32 * 4),
               ("B", C.c_int32), ("Hout", C.c_int32), ("Wout", C.c_int32),
               ("bw", C.c_int32), ("bh", C.c_int32), ("bb", C.c_int32),
               ("n_taps", C.c_int32), ("tap_dw", C.c_int32 * 16), ("tap_dh", C.c_int32 * 16),
@@ -89,6 +95,12 @@ SIGNATURES = {
   "v4l_ln_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i],
   "v4l_pool_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
   "v4l_pool_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
+  "v4l_attn_fwd_bf16": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i],
+  "v4l_attn_bwd_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i],
+  "v4l_ln_fwd_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f],
+  "v4l_ln_bwd_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i],
+  "v4l_pool_fwd_bf16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
+  "v4l_pool_bwd_bf16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
   "v4l_gae": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i, _i, _d, _d, _i, _i],
   "v4l_select_rows": [_vp, _vp, _vp, _vp, _vp, _i],
   "v4l_slot_advance": [_vp, _vp, _vp, C.c_int32],
@@ -99,7 +111,11 @@ SIGNATURES = {
   "v4l_clip_adam": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i],
   "v4l_tc_gemm": [_vp, _vp, C.POINTER(TcGemmArgs)],
   "v4l_tc_wgrad": [_vp, _vp, C.POINTER(TcWgradArgs)],
-  "v4l_colsum_bf16": [_vp, _vp, _vp, C.POINTER(RowMap), _i, _i, _vp],
+  "v4l_colsum_bf16": [_vp, _vp, _vp, C.POINTER(RowMap), _i, _i, _i, _vp],
+  "v4l_ingest_img": [_vp, _vp, _vp, _vp, _i64],
+  "v4l_gather_rows_bf16": [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i64, _i],
+  "v4l_relu_bwd_bf16": [_vp, _vp, _vp, C.POINTER(RowMap), _vp, C.POINTER(RowMap), _vp, C.POINTER(RowMap),
+                        _i, _i],
   "v4l_pack_bf16": [_vp, _vp, _vp, _vp, _vp, _i64],
   "v4l_h2d_2d": [_vp, _vp, _sz, _vp, _sz, _sz, _sz],
 }

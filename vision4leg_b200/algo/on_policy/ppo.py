@@ -28,6 +28,7 @@ class PPO(A2C):
     self.sample_key = ["obs", "acts", "advs", "estimate_returns", "values"]
     self.process_group = None       # set to a torch.distributed group for data-parallel updates
     self.use_cuda_graph = True
+    self.precision = "fp32"         # "fp32": exact CUDA-core tier; "bf16": tcgen05 tensor-core tier
     self._engine = None
 
   @property
@@ -36,7 +37,7 @@ class PPO(A2C):
       self._engine = PPOUpdateEngine(self.pf, self.vf, self.target_pf, self.device, self.clip_para,
                                      self.entropy_coeff, self.clipped_value_loss,
                                      use_cuda_graph=self.use_cuda_graph,
-                                     process_group=self.process_group)
+                                     process_group=self.process_group, precision=self.precision)
     return self._engine
 
   def _schedule(self):

@@ -20,6 +20,7 @@ import numpy as np
 import torch
 
 from ... import engine
+from ... import engine_tc
 from ..._lib import INFO_KEYS, INFO_STRIDE, INFO_GRAD_NORM_PF, INFO_GRAD_NORM_VF, V4LError
 
 _ALIGN = 4   # floats (16 B)
@@ -59,7 +60,7 @@ class _Bucket:
 
 class PPOUpdateEngine:
   def __init__(self, pf, vf, target_pf, device, clip_para, entropy_coeff, clipped_value_loss,
-               use_cuda_graph=True, process_group=None):
+               use_cuda_graph=True, process_group=None, precision="fp32"):
     self.device = torch.device(device)
     if self.device.type != "cuda":
       raise V4LError("the PPO update runs on a CUDA device (got %s); there is no CPU fallback"
@@ -87,9 +88,22 @@ class PPOUpdateEngine:
       self.world = dist.get_world_size(process_group)
     self._build_buckets()
     kw = getattr(pf, "_plan_kwargs", {})
-    self.plan_pf = engine.make_plan(self.family, self.ops, self.S, self.A, **kw)
-    self.plan_vf = engine.make_plan(self.family, self.ops, self.S, 1, **kw)
-    self.plan_t = engine.make_plan(self.family, self.ops, self.S, self.A, **kw)
+    if precision not in ("fp32", "bf16"):
+      raise ValueError("precision must be 'fp32' (exact CUDA-core tier) or 'bf16' (tcgen05 tier)")
+    self.precision = precision
+    if precision == "bf16":
+      if self.family != "loco":
+        raise NotImplementedError("the tensor-core tier currently covers the LocoTransformer family; "
+                                  "use precision='fp32' for %s" % self.family)
+      nh = kw.get("n_heads", (1, 1))
+      self.plan_pf = engine_tc.LocoPlanTC(self.ops, self.S, self.A, self.pf_layout, nh)
+      self.plan_vf = engine_tc.LocoPlanTC(self.ops, self.S, 1, self.vf_layout, nh)
+      self.plan_t = engine_tc.LocoPlanTC(self.ops, self.S, self.A, self.pf_layout, nh, with_backward=False)
+      self.plan_t.pack(self.t_flat)
+    else:
+      self.plan_pf = engine.make_plan(self.family, self.ops, self.S, self.A, **kw)
+      self.plan_vf = engine.make_plan(self.family, self.ops, self.S, 1, **kw)
+      self.plan_t = engine.make_plan(self.family, self.ops, self.S, self.A, **kw)
     self._graphs = {}
     self._roll = None
     self._mb_bufs = {}
@@ -125,6 +139,9 @@ class PPOUpdateEngine:
     self.G_pf = {n: b.view_of(self.g_pf, p, self.pf_range[0]) for n, p in pf_named}
     self.G_vf = {n: b.view_of(self.g_vf, p, self.vf_range[0]) for n, p in vf_named}
     self.logstd = dict(pf_named)["logstd"].data
+    # bucket-relative layouts {name: (offset, shape)} for the tensor-core tier's packing tables
+    self.pf_layout = {n: (b.offsets[id(p)][0] - self.pf_range[0], tuple(p.shape)) for n, p in pf_named}
+    self.vf_layout = {n: (b.offsets[id(p)][0] - self.vf_range[0], tuple(p.shape)) for n, p in vf_named}
     # frozen target policy: own flat copy in the actor-bucket layout
     t_named = list(self.target_pf.named_parameters())
     assert [n for n, _ in t_named] == [n for n, _ in pf_named]
@@ -155,6 +172,8 @@ class PPOUpdateEngine:
              terminals=f(N), advs=f(N), rets=f(N), last_value=f(E))
     if self.has_img:
       r["img"] = f(N, engine.IMG_ELEMS)
+      if self.precision == "bf16":
+        r["imgs"] = torch.empty((N, 16, 16, 64), device=dev, dtype=torch.bfloat16)
     self._roll = r
     self._graphs.clear()            # captured graphs hold the old planes' addresses
     return r
@@ -176,6 +195,8 @@ class PPOUpdateEngine:
       self.ops.h2d_2d(r["img"], engine.IMG_ELEMS * 4, obs.data_ptr() + self.S * 4, D * 4,
                       engine.IMG_ELEMS * 4, T * E)
     self.h2d_bytes = T * E * D * 4
+    if self.precision == "bf16":
+      self.ops.ingest_img(r["img"], r["imgs"], T * E)       # fp32 CHW -> bf16 space-to-depth NHWC
     for key in ("acts", "values", "rewards", "terminals"):
       src = host[key].reshape(T * E, -1)
       r[key].view(T * E, -1).copy_(src, non_blocking=True)
@@ -208,7 +229,15 @@ class PPOUpdateEngine:
     x = torch.as_tensor(np.ascontiguousarray(last_obs, dtype=np.float32)).to(self.device).reshape(E, -1)
     v = torch.empty((E, 1), device=self.device, dtype=torch.float32)
     plan = self._aux_plan(E)
-    plan.forward(self.P_vf, engine.Input.from_flat(x, self.S, self.has_img), v)
+    if self.precision == "bf16":
+      imgs = torch.empty((E, 16, 16, 64), device=self.device, dtype=torch.bfloat16)
+      self.ops.ingest_img(x[:, self.S:].contiguous(), imgs, E)
+      st = torch.empty((E, plan.Sp), device=self.device, dtype=torch.bfloat16)
+      self.ops.gather_rows_bf16(x, True, None, st, E, self.S, x.shape[1], plan.Sp)
+      plan.pack(self.vf_flat)
+      plan.forward(self.vf_flat, imgs, None, st, E, v)
+    else:
+      plan.forward(self.P_vf, engine.Input.from_flat(x, self.S, self.has_img), v)
     notdone = 1.0 - torch.as_tensor(np.asarray(last_terminals, np.float32).reshape(E)).to(self.device)
     r["last_value"].copy_(v.view(E) * notdone)
     tl = r["time_limits"]
@@ -223,7 +252,11 @@ class PPOUpdateEngine:
     p = self._mb_bufs.get(key)
     if p is None:
       kw = getattr(self.pf, "_plan_kwargs", {})
-      p = self._mb_bufs[key] = engine.make_plan(self.family, self.ops, self.S, 1, **kw)
+      if self.precision == "bf16":
+        p = engine_tc.LocoPlanTC(self.ops, self.S, 1, self.vf_layout, kw.get("n_heads", (1, 1)), with_backward=False)
+      else:
+        p = engine.make_plan(self.family, self.ops, self.S, 1, **kw)
+      self._mb_bufs[key] = p
     return p
 
   # ---------------------------------------------------------------------------------------------
@@ -236,6 +269,8 @@ class PPOUpdateEngine:
   def sync_target(self):
     """copy_model_params_from_to(pf, target_pf) as one D2D copy (reference utils.py:23-25)."""
     self.t_flat.copy_(self.pf_flat)
+    if self.precision == "bf16":
+      self.plan_t.pack(self.t_flat)
 
   def _bufs(self, B):
     b = self._mb_bufs.get(B)
@@ -247,6 +282,8 @@ class PPOUpdateEngine:
                stats=torch.zeros(8, device=dev, dtype=torch.float64))
       if self.world > 1:
         b["stats_all"] = torch.zeros((self.world, 8), device=dev, dtype=torch.float64)
+      if self.precision == "bf16":
+        b["st"] = torch.zeros((B, self.plan_pf.Sp), device=dev, dtype=torch.bfloat16)
       self._mb_bufs[B] = b
     return b
 
@@ -267,6 +304,8 @@ class PPOUpdateEngine:
     ops.adv_stats(r["advs"], idx, B, b["stats"])
     if self.world > 1:
       self._allreduce_stats(b)
+    if self.precision == "bf16":
+      return self._minibatch_tc(B, b, idx, inv_local, inv_global)
     inp = self._input(B, idx)
     # ---- critic
     self.plan_vf.forward(self.P_vf, inp, b["values"])
@@ -284,6 +323,37 @@ class PPOUpdateEngine:
                 b["d_mean"], self.G_pf["logstd"], B, self.A, inv_global, inv_local, self.clip_para,
                 self.entropy_coeff, self._info, self._slot)
     self.plan_pf.backward(self.P_pf, self.G_pf, b["d_mean"])
+    if self.world > 1:
+      self._allreduce(self.g_pf)
+    ops.clip_adam(self.pf_flat, self.g_pf, self.m_pf, self.v_pf, self.n_pf, self.hyper_pf, self._info,
+                  self._slot, INFO_GRAD_NORM_PF)
+    ops.slot_advance(self._slot, 0)
+
+  def _minibatch_tc(self, B, b, idx, inv_local, inv_global):
+    """Same sequence on the tensor-core tier: bf16 activations, tcgen05 GEMMs; weights are
+    re-packed to bf16 right before each network's forward (the critic step has just changed
+    the shared encoder when the actor runs)."""
+    ops, r = self.ops, self._roll
+    imgs, st = r["imgs"], b["st"]
+    ops.gather_rows_bf16(r["state"], True, idx, st, B, self.S, self.S, self.plan_pf.Sp)
+    # ---- critic
+    self.plan_vf.pack(self.vf_flat)
+    self.plan_vf.forward(self.vf_flat, imgs, idx, st, B, b["values"])
+    ops.vf_loss(b["values"], r["rets"], r["values"], idx, b["d_values"], B, inv_global, inv_local,
+                self.clipped_value_loss, self.clip_para, self._info, self._slot)
+    self.plan_vf.backward(self.g_vf, b["d_values"])
+    if self.world > 1:
+      self._allreduce(self.g_vf)
+    ops.clip_adam(self.vf_flat, self.g_vf, self.m_vf, self.v_vf, self.n_vf, self.hyper_vf, self._info,
+                  self._slot, INFO_GRAD_NORM_VF)
+    # ---- actor
+    self.plan_pf.pack(self.pf_flat)
+    self.plan_pf.forward(self.pf_flat, imgs, idx, st, B, b["mean"])
+    self.plan_t.forward(self.t_flat, imgs, idx, st, B, b["tmean"])
+    ops.pf_loss(b["mean"], self.logstd, b["tmean"], self.t_logstd, r["acts"], r["advs"], idx, b["stats"],
+                b["d_mean"], self.G_pf["logstd"], B, self.A, inv_global, inv_local, self.clip_para,
+                self.entropy_coeff, self._info, self._slot)
+    self.plan_pf.backward(self.g_pf, b["d_mean"])
     if self.world > 1:
       self._allreduce(self.g_pf)
     ops.clip_adam(self.pf_flat, self.g_pf, self.m_pf, self.v_pf, self.n_pf, self.hyper_pf, self._info,

@@ -161,4 +161,5 @@ __device__ __forceinline__ bool elect_one() {
 // host: cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda
 // dependency, so the library still loads on a box without a GPU driver)
 int v4l_encode_tmap(CUtensorMap* out, const void* gaddr, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box, const char* who);
+                    const uint64_t* strides_bytes, const uint32_t* box, const char* who,
+                    const uint32_t* elem_strides);

@@ -42,6 +42,7 @@ struct TcGemmParams {
   int c_f32;
   const __nv_bfloat16* mask;
   int flags;
+  const int32_t* a_idx;
 };
 
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
@@ -89,13 +90,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         int b0, h0;
         if (p.bb == 1) { b0 = tile / p.h_tiles; h0 = (tile - b0 * p.h_tiles) * p.bh; }
         else           { b0 = tile * p.bb; h0 = 0; }
+        const int ab0 = p.a_idx ? p.a_idx[b0] : b0;          // minibatch row gather (bb == 1 only)
         for (int it = 0; it < k_iters; ++it) {
           const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + A_TILE_BYTES;
           tc::mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
-          tc::tma_load_4d(sa, &p.tmap_a, &full_bar[stage], kc * 64, p.tap_dw[tap], h0 + p.tap_dh[tap], b0);
+          tc::tma_load_4d(sa, &p.tmap_a, &full_bar[stage], kc * 64, p.tap_dw[tap], h0 + p.tap_dh[tap], ab0);
           tc::tma_load_2d(sb, &p.tmap_b, &full_bar[stage], it * 64, n0);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -239,7 +241,8 @@ EncodeTiledFn g_encode = nullptr;
 }  // namespace
 
 int v4l_encode_tmap(CUtensorMap* out, const void* gaddr, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box, const char* who) {
+                    const uint64_t* strides_bytes, const uint32_t* box, const char* who,
+                    const uint32_t* elem_strides) {
   if (!g_encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -253,7 +256,7 @@ int v4l_encode_tmap(CUtensorMap* out, const void* gaddr, int rank, const uint64_
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   cuuint64_t gd[5], gs[5];
   cuuint32_t bx[5];
-  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; if (elem_strides) estr[i] = elem_strides[i]; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(gaddr), gd, gs, bx, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -287,8 +290,9 @@ extern "C" int v4l_tc_gemm(v4l_ctx* ctx, void* stream, const v4l_tc_gemm_args* a
   {
     uint64_t dims[4] = {(uint64_t)a->a_C, (uint64_t)a->a_W, (uint64_t)a->a_H, (uint64_t)a->a_B};
     uint64_t str[3] = {(uint64_t)a->a_C * 2, (uint64_t)a->a_C * a->a_W * 2, (uint64_t)a->a_C * a->a_W * a->a_H * 2};
+    if (a->a_sW) { str[0] = (uint64_t)a->a_sW * 2; str[1] = (uint64_t)a->a_sH * 2; str[2] = (uint64_t)a->a_sB * 2; }
     uint32_t box[4] = {64, (uint32_t)a->bw, (uint32_t)a->bh, (uint32_t)a->bb};
-    if (int r = v4l_encode_tmap(&p.tmap_a, a->a, 4, dims, str, box, "v4l_tc_gemm(A)")) return r;
+    if (int r = v4l_encode_tmap(&p.tmap_a, a->a, 4, dims, str, box, "v4l_tc_gemm(A)", nullptr)) return r;
   }
   const int Ktot = a->n_taps * a->kchunks * 64;
   const int Nchunk = a->N_pad > 256 ? 256 : a->N_pad;
@@ -296,7 +300,7 @@ extern "C" int v4l_tc_gemm(v4l_ctx* ctx, void* stream, const v4l_tc_gemm_args* a
     uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)a->N_pad};
     uint64_t str[1] = {(uint64_t)Ktot * 2};
     uint32_t box[2] = {64, (uint32_t)Nchunk};
-    if (int r = v4l_encode_tmap(&p.tmap_b, a->w, 2, dims, str, box, "v4l_tc_gemm(W)")) return r;
+    if (int r = v4l_encode_tmap(&p.tmap_b, a->w, 2, dims, str, box, "v4l_tc_gemm(W)", nullptr)) return r;
   }
   p.B = a->B; p.Hout = a->Hout; p.Wout = a->Wout;
   p.bw = a->bw; p.bh = a->bh; p.bb = a->bb;
@@ -308,6 +312,8 @@ extern "C" int v4l_tc_gemm(v4l_ctx* ctx, void* stream, const v4l_tc_gemm_args* a
   p.bias = a->bias; p.c = a->c; p.c_map = a->c_map; p.c_f32 = a->c_f32;
   p.mask = reinterpret_cast<const __nv_bfloat16*>(a->mask);
   p.flags = a->flags;
+  p.a_idx = a->a_idx;
+  V4L_REQUIRE(!a->a_idx || a->bb == 1, "v4l_tc_gemm: a_idx needs single-item boxes (bb == 1)");
 
   const size_t smem = (size_t)TC_STAGES * (A_TILE_BYTES + (size_t)Nchunk * 128) + 1024;
   static bool attr_set = false;
@@ -371,6 +377,10 @@ struct TcWgradParams {
   int n_atoms;                 // dY atoms of 64 channels (UMMA N = 64 * n_atoms)
   int stages;
   float* partial;              // [splits][kin_tiles][128][64 * n_atoms]
+  int x_estride;               // traversal stride of X in W and H (1, or 2 for sub-sampled grids)
+  int n_sub;                   // sub-iterations per tile (sub-positions of a space-to-depth cell)
+  int sub_dw[4], sub_dh[4], sub_dyc[4];
+  const int32_t* x_idx;
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ TcWgradParams p) {
@@ -424,15 +434,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
         int b0, h0;
         if (p.bb == 1) { b0 = tile / p.h_tiles; h0 = (tile - b0 * p.h_tiles) * p.bh; }
         else           { b0 = tile * p.bb; h0 = 0; }
-        tc::mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* s = smem + stage * stage_bytes;
-        tc::mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(2 + p.n_atoms) * box_rows * 128u);
-        for (int j = 0; j < 2; ++j)
-          tc::tma_load_4d(s + j * ATOM_BYTES, &p.tmap_x, &full_bar[stage], a_c0[j], p.tap_dw[a_tap[j]],
-                          h0 + p.tap_dh[a_tap[j]], b0);
-        for (int j = 0; j < p.n_atoms; ++j)
-          tc::tma_load_4d(s + (2 + j) * ATOM_BYTES, &p.tmap_dy, &full_bar[stage], j * 64, 0, h0, b0);
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        const int xb0 = p.x_idx ? p.x_idx[b0] : b0;
+        for (int sub = 0; sub < p.n_sub; ++sub) {
+          tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* s = smem + stage * stage_bytes;
+          tc::mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(2 + p.n_atoms) * box_rows * 128u);
+          for (int j = 0; j < 2; ++j)
+            tc::tma_load_4d(s + j * ATOM_BYTES, &p.tmap_x, &full_bar[stage], a_c0[j],
+                            p.sub_dw[sub] + p.tap_dw[a_tap[j]],
+                            h0 * p.x_estride + p.sub_dh[sub] + p.tap_dh[a_tap[j]], xb0);
+          for (int j = 0; j < p.n_atoms; ++j)
+            tc::tma_load_4d(s + (2 + j) * ATOM_BYTES, &p.tmap_dy, &full_bar[stage], p.sub_dyc[sub] + j * 64, 0,
+                            h0, b0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -440,7 +455,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
       const uint32_t idesc = tc::umma_idesc_bf16(128, Nmma, 1, 1);     // both operands MN-major
       int stage = 0; uint32_t phase = 0;
       uint32_t first = 1;
-      for (int tile = tile_lo; tile < tile_hi; ++tile) {
+      for (int it = (tile_hi - tile_lo) * p.n_sub; it > 0; --it) {
         tc::mbar_wait(&full_bar[stage], phase);
         tc::tc_fence_after();
         const uint32_t sa = tc::smem_u32(smem + stage * stage_bytes);
@@ -532,11 +547,13 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
     part[(long long)blockIdx.x * N + n] = s;
   }
 }
-__global__ void colsum_reduce_kernel(const float* __restrict__ part, int nparts, int N, float* __restrict__ out) {
+__global__ void colsum_reduce_kernel(const float* __restrict__ part, int nparts, int N, int fold,
+                                     float* __restrict__ out) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += part[(long long)p * N + n];
+  for (int p = 0; p < nparts; ++p)
+    for (int f = 0; f < fold; ++f) s += part[(long long)p * N * fold + f * N + n];
   out[n] = s;
 }
 
@@ -558,15 +575,21 @@ extern "C" int v4l_tc_wgrad(v4l_ctx* ctx, void* stream, const v4l_tc_wgrad_args*
   {
     uint64_t dims[4] = {(uint64_t)a->x_C, (uint64_t)a->x_W, (uint64_t)a->x_H, (uint64_t)a->x_B};
     uint64_t str[3] = {(uint64_t)a->x_C * 2, (uint64_t)a->x_C * a->x_W * 2, (uint64_t)a->x_C * a->x_W * a->x_H * 2};
+    if (a->x_sW) { str[0] = (uint64_t)a->x_sW * 2; str[1] = (uint64_t)a->x_sH * 2; str[2] = (uint64_t)a->x_sB * 2; }
     uint32_t box[4] = {64, (uint32_t)a->bw, (uint32_t)a->bh, (uint32_t)a->bb};
-    if (int r = v4l_encode_tmap(&p.tmap_x, a->x, 4, dims, str, box, "v4l_tc_wgrad(X)")) return r;
+    const uint32_t es = a->x_estride > 1 ? (uint32_t)a->x_estride : 1u;
+    uint32_t estr[4] = {1, es, es, 1};
+    // with a traversal stride the box extent is given in traversed elements: bw outputs span bw*es inputs
+    box[1] *= es; box[2] *= es;
+    if (int r = v4l_encode_tmap(&p.tmap_x, a->x, 4, dims, str, box, "v4l_tc_wgrad(X)", estr)) return r;
   }
   {
     uint64_t dims[4] = {(uint64_t)a->dy_C, (uint64_t)a->Wout, (uint64_t)a->Hout, (uint64_t)a->B};
     uint64_t str[3] = {(uint64_t)a->dy_C * 2, (uint64_t)a->dy_C * a->Wout * 2,
                        (uint64_t)a->dy_C * a->Wout * a->Hout * 2};
+    if (a->dy_sW) { str[0] = (uint64_t)a->dy_sW * 2; str[1] = (uint64_t)a->dy_sH * 2; str[2] = (uint64_t)a->dy_sB * 2; }
     uint32_t box[4] = {64, (uint32_t)a->bw, (uint32_t)a->bh, (uint32_t)a->bb};
-    if (int r = v4l_encode_tmap(&p.tmap_dy, a->dy, 4, dims, str, box, "v4l_tc_wgrad(dY)")) return r;
+    if (int r = v4l_encode_tmap(&p.tmap_dy, a->dy, 4, dims, str, box, "v4l_tc_wgrad(dY)", nullptr)) return r;
   }
   p.B = a->B; p.Hout = a->Hout; p.Wout = a->Wout;
   p.bw = a->bw; p.bh = a->bh; p.bb = a->bb;
@@ -574,7 +597,17 @@ extern "C" int v4l_tc_wgrad(v4l_ctx* ctx, void* stream, const v4l_tc_wgrad_args*
   p.num_tiles = (a->bb == 1) ? a->B * p.h_tiles : v4l_cdiv(a->B, a->bb);
   p.n_taps = a->n_taps; p.x_C = a->x_C;
   for (int t = 0; t < a->n_taps; ++t) { p.tap_dw[t] = a->tap_dw[t]; p.tap_dh[t] = a->tap_dh[t]; }
-  p.n_atoms = v4l_cdiv(a->dy_C, 64);
+  p.n_atoms = v4l_cdiv(a->N_valid, 64);
+  p.x_estride = a->x_estride > 1 ? a->x_estride : 1;
+  p.n_sub = a->n_sub > 0 ? a->n_sub : 1;
+  V4L_REQUIRE(p.n_sub <= 4, "v4l_tc_wgrad: at most 4 sub-iterations");
+  for (int i = 0; i < p.n_sub; ++i) {
+    p.sub_dw[i] = a->n_sub > 0 ? a->sub_dw[i] : 0;
+    p.sub_dh[i] = a->n_sub > 0 ? a->sub_dh[i] : 0;
+    p.sub_dyc[i] = a->n_sub > 0 ? a->sub_dyc[i] : 0;
+  }
+  p.x_idx = a->x_idx;
+  V4L_REQUIRE(!a->x_idx || a->bb == 1, "v4l_tc_wgrad: x_idx needs single-item boxes (bb == 1)");
   const int Nmma = 64 * p.n_atoms;
   const int Kp = a->n_taps * a->x_C;
   const int kin_tiles = v4l_cdiv(Kp, 128);
@@ -603,9 +636,11 @@ extern "C" int v4l_tc_wgrad(v4l_ctx* ctx, void* stream, const v4l_tc_wgrad_args*
 }
 
 extern "C" int v4l_colsum_bf16(v4l_ctx* ctx, void* stream, const void* dy, const v4l_rowmap* map, int M, int N,
-                               float* out) {
+                               int fold, float* out) {
   V4L_REQUIRE(ctx && dy && map && out && map->P > 0, "v4l_colsum_bf16: bad argument");
-  V4L_REQUIRE(N >= 1 && N <= 256 && M >= 1, "v4l_colsum_bf16: bad shape M=%d N=%d", M, N);
+  V4L_REQUIRE(fold >= 1 && N >= 1 && N * fold <= 256 && M >= 1, "v4l_colsum_bf16: bad shape M=%d N=%d fold=%d", M, N, fold);
+  const int Nout = N;
+  N = N * fold;
   cudaStream_t s = (cudaStream_t)stream;
   int ctas = min(2 * ctx->sm_count, v4l_cdiv(M, 64));
   const int rpc = v4l_cdiv(M, ctas);
@@ -615,7 +650,117 @@ extern "C" int v4l_colsum_bf16(v4l_ctx* ctx, void* stream, const void* dy, const
   V4L_REQUIRE((size_t)ctas * N <= ctx->scratch_elems, "v4l_colsum_bf16: scratch too small");
   colsum_bf16_kernel<<<ctas, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), *map, M, N, rpc, part);
   V4L_CHECK_LAUNCH();
-  colsum_reduce_kernel<<<v4l_cdiv(N, 128), 128, 0, s>>>(part, ctas, N, out);
+  colsum_reduce_kernel<<<v4l_cdiv(Nout, 128), 128, 0, s>>>(part, ctas, Nout, fold, out);
+  V4L_CHECK_LAUNCH();
+  return 0;
+}
+
+// =================================================================================================
+// Layout helpers of the tensor-core tier
+// =================================================================================================
+namespace {
+
+// fp32 CHW [4,64,64] observation image -> bf16 4x4 space-to-depth NHWC [16,16,64],
+// channel = (py*4 + px)*4 + c for source pixel (4Y+py, 4X+px): the 8x8/4 conv becomes a 2x2/1
+// conv with 64-channel (128-byte) rows — exactly one TMA/UMMA swizzle atom per tap.
+__global__ void ingest_img_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, long long n_img) {
+  const long long total = n_img * 16 * 4 * 16;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int X = (int)(t & 15);
+    const int py = (int)((t >> 4) & 3);
+    const int Y = (int)((t >> 6) & 15);
+    const long long n = t >> 10;
+    const float* src = img + n * 16384 + (4 * Y + py) * 64 + 4 * X;
+    float4 v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = *reinterpret_cast<const float4*>(src + c * 4096);
+    uint32_t w[8];
+    const float* f0 = reinterpret_cast<const float*>(&v[0]);
+    // out order: px (4) x c (4); v[c] holds px = 0..3 for channel c
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      const float a0 = reinterpret_cast<const float*>(&v[0])[px], a1 = reinterpret_cast<const float*>(&v[1])[px];
+      const float a2 = reinterpret_cast<const float*>(&v[2])[px], a3 = reinterpret_cast<const float*>(&v[3])[px];
+      w[2 * px] = pack_bf16(a0, a1);
+      w[2 * px + 1] = pack_bf16(a2, a3);
+    }
+    (void)f0;
+    uint4* dst = reinterpret_cast<uint4*>(out + ((n * 16 + Y) * 16 + X) * 64 + py * 16);
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+// dst[i, :] = src[idx ? idx[i] : i, :] with fp32 or bf16 source, bf16 destination, zero padded to dcols
+template <typename S>
+__global__ void gather_rows_kernel(const S* __restrict__ src, const int32_t* __restrict__ idx,
+                                   __nv_bfloat16* __restrict__ dst, int rows, int scols, long long sstride,
+                                   int dcols) {
+  const long long total = (long long)rows * dcols;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(e / dcols), c = (int)(e - (long long)r * dcols);
+    float v = 0.f;
+    if (c < scols) {
+      const long long sr = idx ? (long long)idx[r] : (long long)r;
+      v = static_cast<float>(src[sr * sstride + c]);
+    }
+    dst[e] = __float2bfloat16(v);
+  }
+}
+
+__global__ void relu_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const v4l_rowmap dy_map,
+                                     const __nv_bfloat16* __restrict__ act, const v4l_rowmap act_map,
+                                     __nv_bfloat16* __restrict__ out, const v4l_rowmap out_map, int M, int N) {
+  const long long total = (long long)M * N;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(e / N), n = (int)(e - (long long)m * N);
+    const __nv_bfloat16 g = dy[v4l_row_addr(dy_map, m) + n];
+    const float a = __bfloat162float(act[v4l_row_addr(act_map, m) + n]);
+    out[v4l_row_addr(out_map, m) + n] = a > 0.f ? g : __float2bfloat16(0.f);
+  }
+}
+
+}  // namespace
+
+extern "C" int v4l_ingest_img(v4l_ctx* ctx, void* stream, const float* img, void* out_s2d, int64_t n_img) {
+  V4L_REQUIRE(ctx && img && out_s2d && n_img >= 0, "v4l_ingest_img: bad argument");
+  if (n_img == 0) return 0;
+  const long long total = n_img * 1024;
+  const int blocks = (int)min((long long)16 * ctx->sm_count, (total + 255) / 256);
+  ingest_img_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(img, reinterpret_cast<__nv_bfloat16*>(out_s2d), n_img);
+  V4L_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int v4l_gather_rows_bf16(v4l_ctx* ctx, void* stream, const void* src, int src_is_f32,
+                                    const int32_t* idx, void* dst, int rows, int src_cols, int64_t src_stride,
+                                    int dst_cols) {
+  V4L_REQUIRE(ctx && src && dst && rows >= 0 && src_cols >= 0 && dst_cols >= src_cols, "v4l_gather_rows_bf16: bad argument");
+  const long long total = (long long)rows * dst_cols;
+  if (total == 0) return 0;
+  const int blocks = (int)min((long long)8 * ctx->sm_count, (total + 255) / 256);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (src_is_f32)
+    gather_rows_kernel<float><<<blocks, 256, 0, s>>>((const float*)src, idx, (__nv_bfloat16*)dst, rows, src_cols, src_stride, dst_cols);
+  else
+    gather_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)src, idx, (__nv_bfloat16*)dst, rows, src_cols, src_stride, dst_cols);
+  V4L_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int v4l_relu_bwd_bf16(v4l_ctx* ctx, void* stream, const void* dy, const v4l_rowmap* dy_map,
+                                 const void* act, const v4l_rowmap* act_map, void* out,
+                                 const v4l_rowmap* out_map, int M, int N) {
+  V4L_REQUIRE(ctx && dy && dy_map && act && act_map && out && out_map, "v4l_relu_bwd_bf16: NULL argument");
+  V4L_REQUIRE(dy_map->P > 0 && act_map->P > 0 && out_map->P > 0, "v4l_relu_bwd_bf16: row map with P <= 0");
+  const long long total = (long long)M * N;
+  if (total <= 0) return 0;
+  const int blocks = (int)min((long long)8 * ctx->sm_count, (total + 255) / 256);
+  relu_bwd_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+    (const __nv_bfloat16*)dy, *dy_map, (const __nv_bfloat16*)act, *act_map, (__nv_bfloat16*)out, *out_map, M, N);
   V4L_CHECK_LAUNCH();
   return 0;
 }

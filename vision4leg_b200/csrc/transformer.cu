@@ -1,15 +1,24 @@
 // Per-sample attention core, LayerNorm(+residual) and token pooling of the LocoTransformer
 // block (reference torchrl/networks/nets.py:949-955, 1009-1034; math: SURVEY Appendix A2).
 // fp32 tier: one CTA per sample keeps q/k/v (T<=33 tokens x d<=128) in shared memory.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace {
 
+// IO element type: float (exact tier) or __nv_bfloat16 (tensor-core tier); math is fp32 either way
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+__device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stf(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
 constexpr int ATT_THREADS = 128;
 
 // smem layout (floats): q[T][dp] k[T][dp] v[T][dp] (dp = d+1 to spread banks), p[nh][T][T]
+template <typename T_>
 __global__ void __launch_bounds__(ATT_THREADS)
-attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ o, float* __restrict__ p_out,
+attn_fwd_kernel(const T_* __restrict__ qkv, T_* __restrict__ o, float* __restrict__ p_out,
                 int T, int d, int nh) {
   extern __shared__ float sm[];
   const int dp = d + 1, hd = d / nh;
@@ -18,10 +27,10 @@ attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ o, float* __r
   float* v = k + T * dp;
   float* p = v + T * dp;
   const int b = blockIdx.x, tid = threadIdx.x;
-  const float* src = qkv + (long long)b * T * 3 * d;
+  const T_* src = qkv + (long long)b * T * 3 * d;
   for (int e = tid; e < T * 3 * d; e += ATT_THREADS) {
     const int t = e / (3 * d), c = e - t * 3 * d;
-    const float val = src[e];
+    const float val = ldf(src + e);
     if (c < d) q[t * dp + c] = val;
     else if (c < 2 * d) k[t * dp + c - d] = val;
     else v[t * dp + c - 2 * d] = val;
@@ -49,20 +58,21 @@ attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ o, float* __r
   __syncthreads();
   float* pg = p_out + (long long)b * nh * T * T;
   for (int e = tid; e < nh * T * T; e += ATT_THREADS) pg[e] = p[e];
-  float* og = o + (long long)b * T * d;
+  T_* og = o + (long long)b * T * d;
   for (int e = tid; e < T * d; e += ATT_THREADS) {
     const int i = e / d, c = e - i * d, h = c / hd;
     const float* pr = p + (h * T + i) * T;
     float s = 0.f;
     for (int j = 0; j < T; ++j) s = fmaf(pr[j], v[j * dp + c], s);
-    og[e] = s;
+    stf(og + e, s);
   }
 }
 
 // smem: q,k,v,dO [T][dp] each; p, ds [nh][T][T]
+template <typename T_>
 __global__ void __launch_bounds__(ATT_THREADS)
-attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ p_in,
-                const float* __restrict__ d_o, float* __restrict__ d_qkv, int T, int d, int nh) {
+attn_bwd_kernel(const T_* __restrict__ qkv, const float* __restrict__ p_in,
+                const T_* __restrict__ d_o, T_* __restrict__ d_qkv, int T, int d, int nh) {
   extern __shared__ float sm[];
   const int dp = d + 1, hd = d / nh;
   float* q = sm;
@@ -72,18 +82,18 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ p_in,
   float* p = go + T * dp;
   float* ds = p + nh * T * T;
   const int b = blockIdx.x, tid = threadIdx.x;
-  const float* src = qkv + (long long)b * T * 3 * d;
+  const T_* src = qkv + (long long)b * T * 3 * d;
   for (int e = tid; e < T * 3 * d; e += ATT_THREADS) {
     const int t = e / (3 * d), c = e - t * 3 * d;
-    const float val = src[e];
+    const float val = ldf(src + e);
     if (c < d) q[t * dp + c] = val;
     else if (c < 2 * d) k[t * dp + c - d] = val;
     else v[t * dp + c - 2 * d] = val;
   }
-  const float* gsrc = d_o + (long long)b * T * d;
+  const T_* gsrc = d_o + (long long)b * T * d;
   for (int e = tid; e < T * d; e += ATT_THREADS) {
     const int t = e / d, c = e - t * d;
-    go[t * dp + c] = gsrc[e];
+    go[t * dp + c] = ldf(gsrc + e);
   }
   const float* pg = p_in + (long long)b * nh * T * T;
   for (int e = tid; e < nh * T * T; e += ATT_THREADS) p[e] = pg[e];
@@ -108,7 +118,7 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ p_in,
     for (int j = 0; j < T; ++j) drow[j] = prow[j] * (drow[j] - dot) * scale;
   }
   __syncthreads();
-  float* out = d_qkv + (long long)b * T * 3 * d;
+  T_* out = d_qkv + (long long)b * T * 3 * d;
   for (int e = tid; e < T * d; e += ATT_THREADS) {
     const int t = e / d, c = e - t * d, h = c / hd;
     float dq = 0.f, dk = 0.f, dv = 0.f;
@@ -117,19 +127,20 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ p_in,
       dk = fmaf(ds[(h * T + j) * T + t], q[j * dp + c], dk);   // dK[t] = sum_i dS[i,t] Q[i]
       dv = fmaf(p[(h * T + j) * T + t], go[j * dp + c], dv);   // dV[t] = sum_i P[i,t] dO[i]
     }
-    out[t * 3 * d + c] = dq;
-    out[t * 3 * d + d + c] = dk;
-    out[t * 3 * d + 2 * d + c] = dv;
+    stf(out + t * 3 * d + c, dq);
+    stf(out + t * 3 * d + d + c, dk);
+    stf(out + t * 3 * d + 2 * d + c, dv);
   }
 }
 
 // ---- LayerNorm over the last dim (d <= 256), one warp per row ---------------------------------
 constexpr int LN_MAXPER = 8;
 
+template <typename T_>
 __global__ void __launch_bounds__(256)
-ln_fwd_kernel(const float* __restrict__ a, const float* __restrict__ res,
+ln_fwd_kernel(const T_* __restrict__ a, const T_* __restrict__ res,
               const float* __restrict__ gamma, const float* __restrict__ beta,
-              float* __restrict__ y, float* __restrict__ z, float* __restrict__ stats,
+              T_* __restrict__ y, float* __restrict__ z, float* __restrict__ stats,
               int rows, int d, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
@@ -142,7 +153,7 @@ ln_fwd_kernel(const float* __restrict__ a, const float* __restrict__ res,
     const int c = lane + 32 * i;
     x[i] = 0.f;
     if (c < d) {
-      x[i] = a[off + c] + (res ? res[off + c] : 0.f);
+      x[i] = ldf(a + off + c) + (res ? ldf(res + off + c) : 0.f);
       s += x[i];
     }
   }
@@ -162,7 +173,7 @@ ln_fwd_kernel(const float* __restrict__ a, const float* __restrict__ res,
   for (int i = 0; i < LN_MAXPER; ++i) {
     const int c = lane + 32 * i;
     if (c < d) {
-      y[off + c] = (x[i] - mean) * rstd * gamma[c] + beta[c];
+      stf(y + off + c, (x[i] - mean) * rstd * gamma[c] + beta[c]);
       if (z) z[off + c] = x[i];
     }
   }
@@ -171,10 +182,11 @@ ln_fwd_kernel(const float* __restrict__ a, const float* __restrict__ res,
 
 // dz = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)), dxhat = dy * gamma.
 // Per-CTA partial sums of dgamma/dbeta go to part[cta][2][d] (reduced by ln_bwd_reduce_kernel).
+template <typename T_>
 __global__ void __launch_bounds__(256)
-ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+ln_bwd_kernel(const T_* __restrict__ dy, const float* __restrict__ z,
               const float* __restrict__ stats, const float* __restrict__ gamma,
-              float* __restrict__ dz, float* __restrict__ part, int rows, int d, int rows_per_cta) {
+              T_* __restrict__ dz, float* __restrict__ part, int rows, int d, int rows_per_cta) {
   __shared__ float red[8][2][32 * LN_MAXPER];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
@@ -195,7 +207,7 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
       const int c = lane + 32 * i;
       xh[i] = 0.f; dxh[i] = 0.f;
       if (c < d) {
-        const float g = dy[off + c];
+        const float g = ldf(dy + off + c);
         xh[i] = (z[off + c] - mean) * rstd;
         dxh[i] = g * gm[i];
         dg[i] = fmaf(g, xh[i], dg[i]);
@@ -213,7 +225,7 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
 #pragma unroll
     for (int i = 0; i < LN_MAXPER; ++i) {
       const int c = lane + 32 * i;
-      if (c < d) dz[off + c] = rstd * (dxh[i] - m1 - xh[i] * m2);
+      if (c < d) stf(dz + off + c, rstd * (dxh[i] - m1 - xh[i] * m2));
     }
   }
 #pragma unroll
@@ -241,29 +253,31 @@ __global__ void ln_bwd_reduce_kernel(const float* __restrict__ part, int nparts,
   (which ? dbeta : dgamma)[c] = s;
 }
 
-__global__ void pool_fwd_kernel(const float* __restrict__ tok, float* __restrict__ out, int B, int T,
+template <typename T_>
+__global__ void pool_fwd_kernel(const T_* __restrict__ tok, T_* __restrict__ out, int B, int T,
                                 int d, int mode) {
   const int od = mode == 0 ? 2 * d : d;
   const long long total = (long long)B * od;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(e / od), c = (int)(e - (long long)b * od);
-    const float* t = tok + (long long)b * T * d;
+    const T_* t = tok + (long long)b * T * d;
     float v;
     if (mode == 0 && c < d) {
-      v = t[c];
+      v = ldf(t + c);
     } else {
       const int cc = mode == 0 ? c - d : c;
       const int t0 = mode == 0 ? 1 : 0;
       float s = 0.f;
-      for (int i = t0; i < T; ++i) s += t[i * d + cc];
+      for (int i = t0; i < T; ++i) s += ldf(t + i * d + cc);
       v = s / (float)(T - t0);
     }
-    out[e] = v;
+    stf(out + e, v);
   }
 }
 
-__global__ void pool_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dtok, int B, int T,
+template <typename T_>
+__global__ void pool_bwd_kernel(const T_* __restrict__ dout, T_* __restrict__ dtok, int B, int T,
                                 int d, int mode) {
   const int od = mode == 0 ? 2 * d : d;
   const long long total = (long long)B * T * d;
@@ -272,11 +286,11 @@ __global__ void pool_bwd_kernel(const float* __restrict__ dout, float* __restric
     const int c = (int)(e % d);
     const long long r = e / d;
     const int t = (int)(r % T), b = (int)(r / T);
-    const float* g = dout + (long long)b * od;
+    const T_* g = dout + (long long)b * od;
     float v;
-    if (mode == 0) v = (t == 0) ? g[c] : g[d + c] / (float)(T - 1);
-    else v = g[c] / (float)T;
-    dtok[e] = v;
+    if (mode == 0) v = (t == 0) ? ldf(g + c) : ldf(g + d + c) / (float)(T - 1);
+    else v = ldf(g + c) / (float)T;
+    stf(dtok + e, v);
   }
 }
 
@@ -288,46 +302,51 @@ static int attn_check(const char* who, int B, int T, int d, int nh) {
   return 0;
 }
 
-extern "C" int v4l_attn_fwd(v4l_ctx* ctx, void* stream, const float* qkv, float* o, float* p,
-                            int B, int T, int d, int n_head) {
+typedef __nv_bfloat16 bf16_t;
+
+template <typename T_>
+static int attn_fwd_impl(v4l_ctx* ctx, void* stream, const void* qkv, void* o, float* p, int B, int T, int d,
+                         int n_head) {
   V4L_REQUIRE(ctx && qkv && o && p, "v4l_attn_fwd: NULL argument");
   if (int r = attn_check("v4l_attn_fwd", B, T, d, n_head)) return r;
   if (B == 0) return 0;
   const size_t smem = sizeof(float) * (3 * T * (d + 1) + n_head * T * T);
   if (smem > 48 * 1024)
-    V4L_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attn_fwd_kernel<<<B, ATT_THREADS, smem, (cudaStream_t)stream>>>(qkv, o, p, T, d, n_head);
+    V4L_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attn_fwd_kernel<T_><<<B, ATT_THREADS, smem, (cudaStream_t)stream>>>((const T_*)qkv, (T_*)o, p, T, d, n_head);
   V4L_CHECK_LAUNCH();
   return 0;
 }
 
-extern "C" int v4l_attn_bwd(v4l_ctx* ctx, void* stream, const float* qkv, const float* p,
-                            const float* d_o, float* d_qkv, int B, int T, int d, int n_head) {
+template <typename T_>
+static int attn_bwd_impl(v4l_ctx* ctx, void* stream, const void* qkv, const float* p, const void* d_o,
+                         void* d_qkv, int B, int T, int d, int n_head) {
   V4L_REQUIRE(ctx && qkv && p && d_o && d_qkv, "v4l_attn_bwd: NULL argument");
   if (int r = attn_check("v4l_attn_bwd", B, T, d, n_head)) return r;
   if (B == 0) return 0;
   const size_t smem = sizeof(float) * (4 * T * (d + 1) + 2 * n_head * T * T);
   if (smem > 48 * 1024)
-    V4L_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attn_bwd_kernel<<<B, ATT_THREADS, smem, (cudaStream_t)stream>>>(qkv, p, d_o, d_qkv, T, d, n_head);
+    V4L_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attn_bwd_kernel<T_><<<B, ATT_THREADS, smem, (cudaStream_t)stream>>>((const T_*)qkv, p, (const T_*)d_o, (T_*)d_qkv, T, d, n_head);
   V4L_CHECK_LAUNCH();
   return 0;
 }
 
-extern "C" int v4l_ln_fwd(v4l_ctx* ctx, void* stream, const float* a, const float* res,
-                          const float* gamma, const float* beta, float* y, float* z, float* stats,
-                          int rows, int d, float eps) {
+template <typename T_>
+static int ln_fwd_impl(v4l_ctx* ctx, void* stream, const void* a, const void* res, const float* gamma,
+                       const float* beta, void* y, float* z, float* stats, int rows, int d, float eps) {
   V4L_REQUIRE(ctx && a && gamma && beta && y, "v4l_ln_fwd: NULL argument");
   V4L_REQUIRE(d > 0 && d <= 32 * LN_MAXPER, "v4l_ln_fwd: d=%d unsupported (max %d)", d, 32 * LN_MAXPER);
   if (rows == 0) return 0;
-  ln_fwd_kernel<<<v4l_cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(a, res, gamma, beta, y, z, stats, rows, d, eps);
+  ln_fwd_kernel<T_><<<v4l_cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>((const T_*)a, (const T_*)res, gamma, beta,
+                                                                          (T_*)y, z, stats, rows, d, eps);
   V4L_CHECK_LAUNCH();
   return 0;
 }
 
-extern "C" int v4l_ln_bwd(v4l_ctx* ctx, void* stream, const float* dy, const float* z,
-                          const float* stats, const float* gamma, float* dz, float* dgamma,
-                          float* dbeta, int rows, int d) {
+template <typename T_>
+static int ln_bwd_impl(v4l_ctx* ctx, void* stream, const void* dy, const float* z, const float* stats,
+                       const float* gamma, void* dz, float* dgamma, float* dbeta, int rows, int d) {
   V4L_REQUIRE(ctx && dy && z && stats && gamma && dz && dgamma && dbeta, "v4l_ln_bwd: NULL argument");
   V4L_REQUIRE(d > 0 && d <= 32 * LN_MAXPER, "v4l_ln_bwd: d=%d unsupported", d);
   V4L_REQUIRE(rows > 0, "v4l_ln_bwd: rows must be > 0");
@@ -336,33 +355,77 @@ extern "C" int v4l_ln_bwd(v4l_ctx* ctx, void* stream, const float* dy, const flo
   ctas = v4l_cdiv(rows, rpc);
   V4L_REQUIRE((size_t)ctas * 2 * d <= ctx->scratch_elems, "v4l_ln_bwd: scratch too small");
   cudaStream_t s = (cudaStream_t)stream;
-  ln_bwd_kernel<<<ctas, 256, 0, s>>>(dy, z, stats, gamma, dz, ctx->scratch, rows, d, rpc);
+  ln_bwd_kernel<T_><<<ctas, 256, 0, s>>>((const T_*)dy, z, stats, gamma, (T_*)dz, ctx->scratch, rows, d, rpc);
   V4L_CHECK_LAUNCH();
   ln_bwd_reduce_kernel<<<v4l_cdiv(2 * d, 128), 128, 0, s>>>(ctx->scratch, ctas, d, dgamma, dbeta);
   V4L_CHECK_LAUNCH();
   return 0;
 }
 
-extern "C" int v4l_pool_fwd(v4l_ctx* ctx, void* stream, const float* tok, float* out, int B, int T,
-                            int d, int mode) {
-  V4L_REQUIRE(ctx && tok && out, "v4l_pool_fwd: NULL argument");
-  V4L_REQUIRE((mode == 0 && T >= 2) || (mode == 1 && T >= 1), "v4l_pool_fwd: bad mode/T");
-  const long long total = (long long)B * (mode == 0 ? 2 * d : d);
+template <typename T_>
+static int pool_impl(v4l_ctx* ctx, void* stream, const void* in, void* out, int B, int T, int d, int mode, bool fwd) {
+  V4L_REQUIRE(ctx && in && out, "v4l_pool: NULL argument");
+  V4L_REQUIRE((mode == 0 && T >= 2) || (mode == 1 && T >= 1), "v4l_pool: bad mode/T");
+  const long long total = fwd ? (long long)B * (mode == 0 ? 2 * d : d) : (long long)B * T * d;
   if (total == 0) return 0;
   const int blocks = (int)min((long long)8 * ctx->sm_count, (total + 255) / 256);
-  pool_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(tok, out, B, T, d, mode);
+  if (fwd) pool_fwd_kernel<T_><<<blocks, 256, 0, (cudaStream_t)stream>>>((const T_*)in, (T_*)out, B, T, d, mode);
+  else     pool_bwd_kernel<T_><<<blocks, 256, 0, (cudaStream_t)stream>>>((const T_*)in, (T_*)out, B, T, d, mode);
   V4L_CHECK_LAUNCH();
   return 0;
 }
 
+extern "C" int v4l_attn_fwd(v4l_ctx* ctx, void* stream, const float* qkv, float* o, float* p,
+                            int B, int T, int d, int n_head) {
+  return attn_fwd_impl<float>(ctx, stream, qkv, o, p, B, T, d, n_head);
+}
+extern "C" int v4l_attn_bwd(v4l_ctx* ctx, void* stream, const float* qkv, const float* p,
+                            const float* d_o, float* d_qkv, int B, int T, int d, int n_head) {
+  return attn_bwd_impl<float>(ctx, stream, qkv, p, d_o, d_qkv, B, T, d, n_head);
+}
+extern "C" int v4l_ln_fwd(v4l_ctx* ctx, void* stream, const float* a, const float* res,
+                          const float* gamma, const float* beta, float* y, float* z, float* stats,
+                          int rows, int d, float eps) {
+  return ln_fwd_impl<float>(ctx, stream, a, res, gamma, beta, y, z, stats, rows, d, eps);
+}
+extern "C" int v4l_ln_bwd(v4l_ctx* ctx, void* stream, const float* dy, const float* z,
+                          const float* stats, const float* gamma, float* dz, float* dgamma,
+                          float* dbeta, int rows, int d) {
+  return ln_bwd_impl<float>(ctx, stream, dy, z, stats, gamma, dz, dgamma, dbeta, rows, d);
+}
+extern "C" int v4l_pool_fwd(v4l_ctx* ctx, void* stream, const float* tok, float* out, int B, int T,
+                            int d, int mode) {
+  return pool_impl<float>(ctx, stream, tok, out, B, T, d, mode, true);
+}
 extern "C" int v4l_pool_bwd(v4l_ctx* ctx, void* stream, const float* dout, float* dtok, int B, int T,
                             int d, int mode) {
-  V4L_REQUIRE(ctx && dout && dtok, "v4l_pool_bwd: NULL argument");
-  V4L_REQUIRE((mode == 0 && T >= 2) || (mode == 1 && T >= 1), "v4l_pool_bwd: bad mode/T");
-  const long long total = (long long)B * T * d;
-  if (total == 0) return 0;
-  const int blocks = (int)min((long long)8 * ctx->sm_count, (total + 255) / 256);
-  pool_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dout, dtok, B, T, d, mode);
-  V4L_CHECK_LAUNCH();
-  return 0;
+  return pool_impl<float>(ctx, stream, dout, dtok, B, T, d, mode, false);
+}
+
+// ---- bf16-IO variants used by the tensor-core tier (fp32 math, fp32 softmax/LayerNorm statistics)
+extern "C" int v4l_attn_fwd_bf16(v4l_ctx* ctx, void* stream, const void* qkv, void* o, float* p,
+                                 int B, int T, int d, int n_head) {
+  return attn_fwd_impl<bf16_t>(ctx, stream, qkv, o, p, B, T, d, n_head);
+}
+extern "C" int v4l_attn_bwd_bf16(v4l_ctx* ctx, void* stream, const void* qkv, const float* p,
+                                 const void* d_o, void* d_qkv, int B, int T, int d, int n_head) {
+  return attn_bwd_impl<bf16_t>(ctx, stream, qkv, p, d_o, d_qkv, B, T, d, n_head);
+}
+extern "C" int v4l_ln_fwd_bf16(v4l_ctx* ctx, void* stream, const void* a, const void* res,
+                               const float* gamma, const float* beta, void* y, float* z, float* stats,
+                               int rows, int d, float eps) {
+  return ln_fwd_impl<bf16_t>(ctx, stream, a, res, gamma, beta, y, z, stats, rows, d, eps);
+}
+extern "C" int v4l_ln_bwd_bf16(v4l_ctx* ctx, void* stream, const void* dy, const float* z,
+                               const float* stats, const float* gamma, void* dz, float* dgamma,
+                               float* dbeta, int rows, int d) {
+  return ln_bwd_impl<bf16_t>(ctx, stream, dy, z, stats, gamma, dz, dgamma, dbeta, rows, d);
+}
+extern "C" int v4l_pool_fwd_bf16(v4l_ctx* ctx, void* stream, const void* tok, void* out, int B, int T,
+                                 int d, int mode) {
+  return pool_impl<bf16_t>(ctx, stream, tok, out, B, T, d, mode, true);
+}
+extern "C" int v4l_pool_bwd_bf16(v4l_ctx* ctx, void* stream, const void* dout, void* dtok, int B, int T,
+                                 int d, int mode) {
+  return pool_impl<bf16_t>(ctx, stream, dout, dtok, B, T, d, mode, false);
 }

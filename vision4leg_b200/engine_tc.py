@@ -1,0 +1,312 @@
+"""Tensor-core tier of the PPO networks: bf16 activations, fp32 master weights / gradients,
+every GEMM-shaped layer on tcgen05 (v4l_tc_gemm / v4l_tc_wgrad), fed by TMA.
+
+Layouts (all bf16 unless noted)
+  image      [N,16,16,64]  4x4 space-to-depth of the 4x64x64 depth stack (v4l_ingest_img): conv1
+                           (8x8 stride 4) is a 2x2 stride-1 conv over 64-channel pixels
+  a1 cells   [B,8,8,128]   conv1 output stored directly as the 2x2 space-to-depth "cells" of the
+                           (zero-padded to 16x16) 15x15x32 map: conv2 (4x4 stride 2) is again a
+                           2x2 stride-1 conv; pad cells stay zero (allocated zeroed, never written)
+  a2 / a3    [B,6,6,64] / [B,4,4,64] = [B,16,64]
+  tokens     [B,17,64]     slot 0 = proprio token, 1..16 = depth tokens (reference base.py:602-622)
+Every conv/linear is "sum over taps of a shifted TMA box x packed weight slice"; the data
+gradient is the same kernel with negated shifts and the transposed packing, the weight gradient
+reads the same boxes as MN-major operands.  Weights are re-packed (fp32 -> bf16, tap-major) from
+the flat parameter bucket by ONE gather kernel per optimiser step through a precomputed index
+table; the same table scatters the fp32 weight gradients back into the reference layout.
+
+Reference semantics: torchrl/networks/nets.py:909-1038 + base.py:497-626 (LocoTransformer).
+"""
+import numpy as np
+import torch
+
+from . import engine
+from .engine import RM, RELU, ACCUM
+from ._lib import V4LError
+
+BF16 = torch.bfloat16
+
+
+def _ceil(a, b):
+  return (a + b - 1) // b * b
+
+
+class _Packed:
+  """One packed weight matrix: where it lives in the packed buffer and its gather table."""
+
+  def __init__(self, rows, cols, table):
+    self.rows, self.cols, self.table = rows, cols, table     # table: int64 [rows, cols], -1 = zero
+    self.off = None
+
+
+def _linear_tables(off, N, K):
+  """W[N,K] fp32 at flat offset `off` -> (fwd [N_pad, ceil64(K)], dgrad [Kd_pad, ceil64(N)])"""
+  Np, Kp = _ceil(N, 16), _ceil(K, 64)
+  fwd = -np.ones((Np, Kp), np.int64)
+  n, k = np.meshgrid(np.arange(N), np.arange(K), indexing="ij")
+  fwd[:N, :K] = off + n * K + k
+  Kd = _ceil(K, 16)
+  if Kd > 256:
+    Kd = _ceil(Kd, 256)
+  dg = -np.ones((Kd, _ceil(N, 64)), np.int64)
+  dg[:K, :N] = (off + n * K + k).T
+  return _Packed(Np, Kp, fwd), _Packed(Kd, _ceil(N, 64), dg)
+
+
+def _conv_tables(off, N, C, KH, KW, s):
+  """OIHW conv weight with stride s -> taps of the s x s space-to-depth form.
+  packed k = ((dy*T + dx) * (s*s*C)) + (py*s + px)*C + c, kh = s*dy + py, kw = s*dx + px, T = KH//s."""
+  T = KH // s
+  Cc = s * s * C
+  n, dy, dx, py, px, c = np.meshgrid(np.arange(N), np.arange(T), np.arange(T), np.arange(s), np.arange(s),
+                                     np.arange(C), indexing="ij")
+  src = off + ((n * C + c) * KH + (s * dy + py)) * KW + (s * dx + px)
+  fwd = -np.ones((_ceil(N, 16), T * T * Cc), np.int64)
+  fwd[:N] = src.reshape(N, T * T * Cc)
+  # dgrad: rows = cell channel (py,px,c), cols = (tap, n)
+  dg = -np.ones((_ceil(Cc, 16), T * T * _ceil(N, 64)), np.int64)
+  d = src.transpose(3, 4, 5, 1, 2, 0).reshape(Cc, T * T, N)     # [(py,px,c), tap, n]
+  dgv = dg.reshape(_ceil(Cc, 16), T * T, _ceil(N, 64))
+  dgv[:Cc, :, :N] = d
+  return _Packed(_ceil(N, 16), T * T * Cc, fwd), _Packed(_ceil(Cc, 16), T * T * _ceil(N, 64), dg)
+
+
+class TcWeights:
+  """Packed bf16 copies (forward and data-gradient orientations) of one network's GEMM weights."""
+
+  def __init__(self, ops, layout, with_dgrad=True):
+    """layout: {param name: (flat offset, shape)} relative to the flat fp32 bucket handed to pack()"""
+    self.ops = ops
+    self.layout = layout
+    self.fwd, self.dgr = {}, {}
+    tables = []
+    cursor = 0
+    for name, (off, shape) in layout.items():
+      if not name.endswith("weight") or len(shape) < 2 or ".norm" in name:
+        continue
+      if len(shape) == 4 and shape[2] > 1:
+        stride = {8: 4, 4: 2, 3: 1}[shape[2]]
+        f, d = _conv_tables(off, shape[0], shape[1], shape[2], shape[3], stride)
+      else:
+        f, d = _linear_tables(off, shape[0], int(np.prod(shape[1:])))
+      for store, pk in ((self.fwd, f), (self.dgr, d)):
+        if store is self.dgr and not with_dgrad:
+          continue
+        pk.off = cursor
+        cursor += pk.rows * pk.cols
+        cursor = _ceil(cursor, 64)                # 128-byte alignment of every packed matrix (TMA)
+        tables.append((pk.off, pk.table))
+        store[name] = pk
+    self.size = cursor
+    table = -np.ones(cursor, np.int64)
+    for o, t in tables:
+      table[o:o + t.size] = t.ravel()
+    dev = ops.device
+    self.table = torch.tensor(table.astype(np.int32), device=dev)
+    self.packed = torch.zeros(cursor, device=dev, dtype=BF16)
+    for pk in list(self.fwd.values()) + list(self.dgr.values()):
+      pk.dev_table = self.table[pk.off:pk.off + pk.rows * pk.cols]
+      pk.w = self.packed[pk.off:pk.off + pk.rows * pk.cols]
+
+  def pack(self, flat):
+    self.ops.pack_bf16(flat, self.table, self.packed, self.size)
+
+
+class LocoPlanTC:
+  """LocoTransformer forward/backward on the tensor-core tier for one batch size."""
+  family = "loco"
+
+  def __init__(self, ops, S, out_dim, layout, n_heads=(1, 1), with_backward=True):
+    self.ops, self.device = ops, ops.device
+    self.S, self.Sp = S, _ceil(S, 64)
+    self.out_dim = out_dim
+    self.n_heads = list(n_heads)
+    self.T, self.d = 17, 64
+    self.layout = layout
+    self.W = TcWeights(ops, layout, with_dgrad=with_backward)
+    self._ws = {}
+    self.k_base = [k for k in layout if k.startswith("encoder.base.seq_fcs.") and k.endswith("weight")]
+    self.k_head = sorted((k for k in layout if k.startswith("visual_seq_append_fcs.") and k.endswith("weight")),
+                         key=lambda k: int(k.split(".")[-2]))
+    oh, ow = np.meshgrid(np.arange(15), np.arange(15), indexing="ij")
+    pos = ((oh // 2) * 8 + ow // 2) * 128 + ((oh % 2) * 2 + ow % 2) * 32
+    self.pos_a1 = torch.tensor(pos.ravel().astype(np.int32), device=self.device)
+    self.taps2 = [(dx, dy) for dy in range(2) for dx in range(2)]
+    self.taps3 = [(kw, kh) for kh in range(3) for kw in range(3)]
+
+  # ---- workspace ------------------------------------------------------------------------------
+  def buf(self, name, shape, dtype=BF16, zero=False):
+    key = (name,) + tuple(shape)
+    t = self._ws.get(key)
+    if t is None:
+      t = (torch.zeros if zero else torch.empty)(shape, device=self.device, dtype=dtype)
+      self._ws[key] = t
+    return t
+
+  def pack(self, flat):
+    self.W.pack(flat)
+
+  def _view(self, flat, name):
+    off, shape = self.layout[name]
+    return flat[off:off + int(np.prod(shape))]
+
+  # ---- generic layer helpers ------------------------------------------------------------------
+  def _lin_fwd(self, flat, wname, x, M, K, out, out_map, relu, c_f32=False):
+    pk = self.W.fwd[wname]
+    N = self.layout[wname][1][0]
+    bias = self._view(flat, wname[:-6] + "bias")
+    self.ops.tc_gemm(x, (M, 1, 1, K), (M, 1, 1), (1, 1, 128), [(0, 0)], pk.cols // 64, pk.w, pk.rows, N, bias,
+                     out, out_map, c_f32=c_f32, flags=RELU if relu else 0)
+
+  def _lin_bwd(self, gflat, wname, x, x_cols, dy, dy_cols, M, dx=None, dx_map=None, mask=None, accum=False,
+               need_dx=True):
+    """dW, db from (x [M,x_cols], dy [M,dy_cols]); optionally dx = dy @ W (masked / accumulated)."""
+    pk = self.W.fwd[wname]
+    N, K = self.layout[wname][1][0], int(np.prod(self.layout[wname][1][1:]))
+    self.ops.tc_wgrad(x, (M, 1, 1, x_cols), dy, dy_cols, (M, 1, 1), (1, 1, 128), [(0, 0)], N, pk.dev_table, gflat)
+    self.ops.colsum_bf16(dy, RM.dense(dy_cols), M, N, self._view(gflat, wname[:-6] + "bias"))
+    if need_dx:
+      pd = self.W.dgr[wname]
+      self.ops.tc_gemm(dy, (M, 1, 1, dy_cols), (M, 1, 1), (1, 1, 128), [(0, 0)], pd.cols // 64, pd.w, pd.rows, K,
+                       None, dx, dx_map, mask=mask, flags=ACCUM if accum else 0)
+
+  # ---- forward --------------------------------------------------------------------------------
+  def forward(self, flat, imgs, idx, st, B, out):
+    """imgs [N,16,16,64] bf16 (whole rollout), idx int32 [B] or None, st [B,Sp] bf16 proprio rows,
+    out fp32 [B,out_dim].  `flat` = the fp32 bucket the layout offsets refer to (biases, LN)."""
+    ops, T, d = self.ops, self.T, self.d
+    self._flat, self._B, self._imgs, self._idx, self._st = flat, B, imgs, idx, st
+    L = self.layout
+    Nimg = imgs.shape[0]
+    pre = "encoder.depth_visual_base.layers."
+    # conv1 (s2d 2x2) -> a1 cells
+    a1c = self.buf("a1c", (B, 8, 8, 128), zero=True)
+    pk = self.W.fwd[pre + "0.weight"]
+    ops.tc_gemm(imgs, (Nimg, 16, 16, 64), (B, 15, 15), (15, 8, 1), self.taps2, 1, pk.w, pk.rows, 32,
+                self._view(flat, pre + "0.bias"), a1c, RM(225, 8 * 8 * 128, 0, 0, pos_off=self.pos_a1),
+                flags=RELU, a_idx=idx)
+    # conv2 on cells
+    a2 = self.buf("a2", (B, 6, 6, 64))
+    pk = self.W.fwd[pre + "2.weight"]
+    ops.tc_gemm(a1c, (B, 8, 8, 128), (B, 6, 6), (6, 6, 3), self.taps2, 2, pk.w, pk.rows, 64,
+                self._view(flat, pre + "2.bias"), a2, RM(36, 36 * 64, 64, 0), flags=RELU)
+    # conv3
+    a3 = self.buf("a3", (B, 16, 64))
+    pk = self.W.fwd[pre + "4.weight"]
+    ops.tc_gemm(a2, (B, 6, 6, 64), (B, 4, 4), (4, 4, 8), self.taps3, 1, pk.w, pk.rows, 64,
+                self._view(flat, pre + "4.bias"), a3, RM(16, 16 * 64, 64, 0), flags=RELU)
+    # tokens
+    tok = self.buf("tok0", (B, T, d))
+    self._lin_fwd(flat, "encoder.depth_up_conv.weight", a3, B * 16, 64, tok, RM.slots(16, T, d, 1), False)
+    s1 = self.buf("s1", (B, 256)); s2 = self.buf("s2", (B, 256))
+    self._lin_fwd(flat, self.k_base[0], st, B, self.Sp, s1, RM.dense(256), True)
+    self._lin_fwd(flat, self.k_base[1], s1, B, 256, s2, RM.dense(256), True)
+    self._lin_fwd(flat, "encoder.state_projector.projection.0.weight", s2, B, 256, tok, RM.slots(1, T, d, 0), True)
+    R = B * T
+    x = tok
+    self._layers = []
+    for l, nh in enumerate(self.n_heads):
+      p = "visual_append_layers.%d." % l
+      qkv = self.buf("qkv%d" % l, (R, 3 * d))
+      self._lin_fwd(flat, p + "self_attn.in_proj_weight", x, R, d, qkv, RM.dense(3 * d), False)
+      o = self.buf("o%d" % l, (R, d))
+      pr = self.buf("p%d" % l, (B, nh, T, T), torch.float32)
+      ops.attn_fwd_bf16(qkv, o, pr, B, T, d, nh)
+      proj = self.buf("proj", (R, d))
+      self._lin_fwd(flat, p + "self_attn.out_proj.weight", o, R, d, proj, RM.dense(d), False)
+      h = self.buf("h%d" % l, (R, d))
+      z1 = self.buf("z1_%d" % l, (R, d), torch.float32); st1 = self.buf("st1_%d" % l, (R, 2), torch.float32)
+      ops.ln_fwd_bf16(proj, x, self._view(flat, p + "norm1.weight"), self._view(flat, p + "norm1.bias"), h, z1, st1, R, d)
+      f1 = self.buf("f1_%d" % l, (R, 256))
+      self._lin_fwd(flat, p + "linear1.weight", h, R, d, f1, RM.dense(256), True)
+      f2 = self.buf("f2", (R, d))
+      self._lin_fwd(flat, p + "linear2.weight", f1, R, 256, f2, RM.dense(d), False)
+      y = self.buf("y%d" % l, (R, d))
+      z2 = self.buf("z2_%d" % l, (R, d), torch.float32); st2 = self.buf("st2_%d" % l, (R, 2), torch.float32)
+      ops.ln_fwd_bf16(f2, h, self._view(flat, p + "norm2.weight"), self._view(flat, p + "norm2.bias"), y, z2, st2, R, d)
+      self._layers.append(dict(p=p, nh=nh, x=x, qkv=qkv, o=o, pr=pr, h=h, z1=z1, st1=st1, f1=f1, z2=z2, st2=st2))
+      x = y
+    pooled = self.buf("pooled", (B, 2 * d))
+    ops.pool_fwd_bf16(x, pooled, B, T, d, 0)
+    h1 = self.buf("h1", (B, 256)); h2 = self.buf("h2", (B, 256))
+    self._lin_fwd(flat, self.k_head[0], pooled, B, 2 * d, h1, RM.dense(256), True)
+    self._lin_fwd(flat, self.k_head[1], h1, B, 256, h2, RM.dense(256), True)
+    self._lin_fwd(flat, self.k_head[2], h2, B, 256, out, RM.dense(self.out_dim), False, c_f32=True)
+    return out
+
+  # ---- backward -------------------------------------------------------------------------------
+  def backward(self, gflat, d_out):
+    """d_out fp32 [B,out_dim]; writes every weight/bias/LayerNorm gradient (fp32) into gflat at
+    the layout offsets."""
+    ops, T, d, B, flat = self.ops, self.T, self.d, self._B, self._flat
+    R = B * T
+    A = self.out_dim
+    ws = self._ws
+    g16 = self.buf("dout16", (B, 16))
+    ops.gather_rows_bf16(d_out, True, None, g16, B, A, A, 16)
+    h1, h2, pooled = ws[("h1", B, 256)], ws[("h2", B, 256)], ws[("pooled", B, 2 * d)]
+    dh2 = self.buf("dh2", (B, 256)); dh1 = self.buf("dh1", (B, 256)); dpool = self.buf("dpool", (B, 2 * d))
+    self._lin_bwd(gflat, self.k_head[2], h2, 256, g16, 16, B, dh2, RM.dense(256), mask=h2)
+    self._lin_bwd(gflat, self.k_head[1], h1, 256, dh2, 256, B, dh1, RM.dense(256), mask=h1)
+    self._lin_bwd(gflat, self.k_head[0], pooled, 2 * d, dh1, 256, B, dpool, RM.dense(2 * d))
+    dx = self.buf("dxa", (R, d)); other = self.buf("dxb", (R, d))
+    ops.pool_bwd_bf16(dpool, dx, B, T, d, 0)
+    for Ly in reversed(self._layers):
+      p = Ly["p"]
+      dz2 = self.buf("dz2", (R, d))
+      ops.ln_bwd_bf16(dx, Ly["z2"], Ly["st2"], self._view(flat, p + "norm2.weight"), dz2,
+                      self._view(gflat, p + "norm2.weight"), self._view(gflat, p + "norm2.bias"), R, d)
+      df1 = self.buf("df1", (R, 256))
+      self._lin_bwd(gflat, p + "linear2.weight", Ly["f1"], 256, dz2, d, R, df1, RM.dense(256), mask=Ly["f1"])
+      self._lin_bwd(gflat, p + "linear1.weight", Ly["h"], d, df1, 256, R, dz2, RM.dense(d), accum=True)   # dh
+      dz1 = other
+      ops.ln_bwd_bf16(dz2, Ly["z1"], Ly["st1"], self._view(flat, p + "norm1.weight"), dz1,
+                      self._view(gflat, p + "norm1.weight"), self._view(gflat, p + "norm1.bias"), R, d)
+      do = self.buf("do", (R, d))
+      self._lin_bwd(gflat, p + "self_attn.out_proj.weight", Ly["o"], d, dz1, d, R, do, RM.dense(d))
+      dqkv = self.buf("dqkv", (R, 3 * d))
+      ops.attn_bwd_bf16(Ly["qkv"], Ly["pr"], do, dqkv, B, T, d, Ly["nh"])
+      self._lin_bwd(gflat, p + "self_attn.in_proj_weight", Ly["x"], d, dqkv, 3 * d, R, dz1, RM.dense(d), accum=True)
+      dx, other = dz1, dx
+    tok = ws[("tok0", B, T, d)]
+    # proprio token -> state MLP
+    ds = self.buf("ds", (B, d))
+    smap = RM.slots(1, T, d, 0)
+    ops.relu_bwd_bf16(dx, smap, tok, smap, ds, RM.dense(d), B, d)
+    s1, s2 = ws[("s1", B, 256)], ws[("s2", B, 256)]
+    ds2 = self.buf("ds2", (B, 256)); ds1 = self.buf("ds1", (B, 256))
+    self._lin_bwd(gflat, "encoder.state_projector.projection.0.weight", s2, 256, ds, d, B, ds2, RM.dense(256), mask=s2)
+    self._lin_bwd(gflat, self.k_base[1], s1, 256, ds2, 256, B, ds1, RM.dense(256), mask=s1)
+    self._lin_bwd(gflat, self.k_base[0], self._st, self.Sp, ds1, 256, B, need_dx=False)
+    # depth tokens -> 1x1 up-conv (dY is the strided [B,16,64] window of the token gradient)
+    a3 = ws[("a3", B, 16, 64)]
+    up = "encoder.depth_up_conv.weight"
+    strides = (d, T * d, T * d)
+    ops.tc_wgrad(a3, (B, 1, 16, 64), dx, d, (B, 1, 16), (16, 1, 8), [(0, 0)], 64, self.W.fwd[up].dev_table, gflat,
+                 dy_strides=strides, dy_off=d)
+    ops.colsum_bf16(dx, RM.slots(16, T, d, 1), B * 16, 64, self._view(gflat, "encoder.depth_up_conv.bias"))
+    da3 = self.buf("da3", (B, 16, 64))
+    pd = self.W.dgr[up]
+    ops.tc_gemm(dx, (B, 1, 16, 64), (B, 1, 16), (16, 1, 8), [(0, 0)], 1, pd.w, pd.rows, 64, None, da3,
+                RM(16, 16 * 64, 64, 0), mask=a3, a_strides=strides, a_off=d)
+    # conv3
+    pre = "encoder.depth_visual_base.layers."
+    a2, a1c = ws[("a2", B, 6, 6, 64)], ws[("a1c", B, 8, 8, 128)]
+    ops.tc_wgrad(a2, (B, 6, 6, 64), da3, 64, (B, 4, 4), (4, 4, 4), self.taps3, 64, self.W.fwd[pre + "4.weight"].dev_table, gflat)
+    ops.colsum_bf16(da3, RM.dense(64), B * 16, 64, self._view(gflat, pre + "4.bias"))
+    da2 = self.buf("da2", (B, 6, 6, 64))
+    pd = self.W.dgr[pre + "4.weight"]
+    ops.tc_gemm(da3, (B, 4, 4, 64), (B, 6, 6), (6, 6, 3), [(-kw, -kh) for kw, kh in self.taps3], 1, pd.w, pd.rows, 64,
+                None, da2, RM(36, 36 * 64, 64, 0), mask=a2)
+    # conv2
+    ops.tc_wgrad(a1c, (B, 8, 8, 128), da2, 64, (B, 6, 6), (6, 6, 3), self.taps2, 64, self.W.fwd[pre + "2.weight"].dev_table, gflat)
+    ops.colsum_bf16(da2, RM.dense(64), B * 36, 64, self._view(gflat, pre + "2.bias"))
+    da1c = self.buf("da1c", (B, 8, 8, 128))
+    pd = self.W.dgr[pre + "2.weight"]
+    ops.tc_gemm(da2, (B, 6, 6, 64), (B, 8, 8), (8, 8, 2), [(-dx_, -dy_) for dx_, dy_ in self.taps2], 1, pd.w, pd.rows, 128,
+                None, da1c, RM(64, 64 * 128, 128, 0), mask=a1c)
+    # conv1: per sub-position (py,px) of a cell, X is the stride-2 sub-grid of the s2d image
+    subs = [(px, py, (py * 2 + px) * 32) for py in range(2) for px in range(2)]
+    ops.tc_wgrad(self._imgs, (self._imgs.shape[0], 16, 16, 64), da1c, 128, (B, 8, 8), (8, 8, 1), self.taps2, 32,
+                 self.W.fwd[pre + "0.weight"].dev_table, gflat, x_idx=self._idx, x_estride=2, subs=subs)
+    ops.colsum_bf16(da1c, RM.dense(128), B * 64, 32, self._view(gflat, pre + "0.bias"), fold=4)
