@@ -115,18 +115,19 @@ int v4l_ln_bwd(v4l_ctx* ctx, void* stream, const float* dy, const float* z, cons
 int v4l_pool_fwd(v4l_ctx* ctx, void* stream, const float* tok, float* out, int B, int T, int d, int mode);
 int v4l_pool_bwd(v4l_ctx* ctx, void* stream, const float* dout, float* dtok, int B, int T, int d, int mode);
 
-/* bf16-IO variants of the block pieces for the tensor-core tier (activations and activation
- * gradients bf16; softmax probabilities, LayerNorm inputs z and statistics, dgamma/dbeta fp32) */
-int v4l_attn_fwd_bf16(v4l_ctx* ctx, void* stream, const void* qkv, void* o, float* p,
+/* f16-IO variants of the block pieces for the tensor-core tier (activations and activation
+ * gradients f16; softmax probabilities, LayerNorm inputs z and statistics, dgamma/dbeta fp32) */
+int v4l_attn_fwd_f16(v4l_ctx* ctx, void* stream, const void* qkv, void* o, float* p,
                       int B, int T, int d, int n_head);
-int v4l_attn_bwd_bf16(v4l_ctx* ctx, void* stream, const void* qkv, const float* p, const void* d_o,
+int v4l_attn_bwd_f16(v4l_ctx* ctx, void* stream, const void* qkv, const float* p, const void* d_o,
                       void* d_qkv, int B, int T, int d, int n_head);
-int v4l_ln_fwd_bf16(v4l_ctx* ctx, void* stream, const void* a, const void* res, const float* gamma,
+int v4l_ln_fwd_f16(v4l_ctx* ctx, void* stream, const void* a, const void* res, const float* gamma,
                     const float* beta, void* y, float* z, float* stats, int rows, int d, float eps);
-int v4l_ln_bwd_bf16(v4l_ctx* ctx, void* stream, const void* dy, const float* z, const float* stats,
-                    const float* gamma, void* dz, float* dgamma, float* dbeta, int rows, int d);
-int v4l_pool_fwd_bf16(v4l_ctx* ctx, void* stream, const void* tok, void* out, int B, int T, int d, int mode);
-int v4l_pool_bwd_bf16(v4l_ctx* ctx, void* stream, const void* dout, void* dtok, int B, int T, int d, int mode);
+int v4l_ln_bwd_f16(v4l_ctx* ctx, void* stream, const void* dy, const float* z, const float* stats,
+                   const float* gamma, void* dz, float* dgamma, float* dbeta, int rows, int d,
+                   float out_scale);
+int v4l_pool_fwd_f16(v4l_ctx* ctx, void* stream, const void* tok, void* out, int B, int T, int d, int mode);
+int v4l_pool_bwd_f16(v4l_ctx* ctx, void* stream, const void* dout, void* dtok, int B, int T, int d, int mode);
 
 /* ---- GAE / discounted return: reverse segmented scan over the rollout buffer
  *      (reference torchrl/replay_buffers/on_policy.py:17-71; recurrence: SURVEY Appendix A4).
@@ -180,13 +181,13 @@ int v4l_clip_adam(v4l_ctx* ctx, void* stream, float* param, const float* grad, f
                   float* v, int64_t n, float* hyper, float* info, const int32_t* slot,
                   int norm_slot);
 
-/* ---- tensor-core tier (bf16 operands, fp32 accumulate; tcgen05.mma fed by TMA) ---------------
+/* ---- tensor-core tier (f16 operands, fp32 accumulate; tcgen05.mma fed by TMA) ---------------
  * D[row tile, N] = sum_{tap,kc} A_tap[rows, 64k] * W[N, (tap,kc,64k)]^T  (+bias, ReLU, ReLU-mask,
- * accumulate), see vision4leg_b200/csrc/tc_gemm.cu.  A: bf16 NHWC activation [a_B,a_H,a_W,a_C]
+ * accumulate), see vision4leg_b200/csrc/tc_gemm.cu.  A: f16 NHWC activation [a_B,a_H,a_W,a_C]
  * (plain matrices: a_H = a_W = 1); a row tile is the TMA box {64, bw, bh, bb} shifted per tap by
- * (tap_dw, tap_dh) with hardware zero fill outside the tensor.  W: packed bf16
+ * (tap_dw, tap_dh) with hardware zero fill outside the tensor.  W: packed f16
  * [N_pad, n_taps*kchunks*64].  Output rows are the logical positions (b, h, w) of a
- * [B, Hout, Wout] grid addressed through c_map (+ column n); c is bf16 unless c_f32.
+ * [B, Hout, Wout] grid addressed through c_map (+ column n); c is f16 unless c_f32.
  * Same reference layers as v4l_gemm_rows.                                                    */
 typedef struct {
   const void* a;  int32_t a_B, a_H, a_W, a_C;
@@ -204,7 +205,7 @@ typedef struct {
 } v4l_tc_gemm_args;
 int v4l_tc_gemm(v4l_ctx* ctx, void* stream, const v4l_tc_gemm_args* args);
 /* dw[index[n*Kp + kp]] = sum_rows X_tap[row, kp] * dY[row, n], Kp = n_taps * x_C, through
- * tcgen05 with MN-major operands (no transposed copies); x: bf16 [x_B,x_H,x_W,x_C], dy: bf16
+ * tcgen05 with MN-major operands (no transposed copies); x: f16 [x_B,x_H,x_W,x_C], dy: f16
  * [B,Hout,Wout,dy_C]; the row tiles are the same boxes as the forward pass.  index = the
  * weight-packing table (or NULL for dw[n*Kp + kp]).  Deterministic (fixed split order).       */
 typedef struct {
@@ -224,26 +225,27 @@ typedef struct {
   int32_t N_valid;
   const int32_t* index;
   float* dw;
+  float out_scale;               /* fp32 results are multiplied by this (1/loss-scale); 0 = 1    */
 } v4l_tc_wgrad_args;
 int v4l_tc_wgrad(v4l_ctx* ctx, void* stream, const v4l_tc_wgrad_args* args);
-/* out[n] = sum_m sum_f dy(m, f*N + n) for a row-mapped bf16 [M, N*fold <= 256] view (bias
+/* out[n] = sum_m sum_f dy(m, f*N + n) for a row-mapped f16 [M, N*fold <= 256] view (bias
  * gradients; fold > 1 sums the sub-positions of a space-to-depth cell)                         */
-int v4l_colsum_bf16(v4l_ctx* ctx, void* stream, const void* dy, const v4l_rowmap* map, int M, int N,
-                    int fold, float* out);
-/* dst_bf16[i] = index ? (index[i] >= 0 ? src[index[i]] : 0) : src[i]  — weight packing /
- * fp32 -> bf16 conversion for the tensor-core tier                                            */
-int v4l_pack_bf16(v4l_ctx* ctx, void* stream, const float* src, const int32_t* index, void* dst,
+int v4l_colsum_f16(v4l_ctx* ctx, void* stream, const void* dy, const v4l_rowmap* map, int M, int N,
+                   int fold, float out_scale, float* out);
+/* dst_f16[i] = index ? (index[i] >= 0 ? src[index[i]] : 0) : src[i]  — weight packing /
+ * fp32 -> f16 conversion for the tensor-core tier                                            */
+int v4l_pack_f16(v4l_ctx* ctx, void* stream, const float* src, const int32_t* index, void* dst,
                   int64_t n);
 
-/* fp32 CHW [n,4,64,64] depth stack -> bf16 4x4 space-to-depth NHWC [n,16,16,64]
+/* fp32 CHW [n,4,64,64] depth stack -> f16 4x4 space-to-depth NHWC [n,16,16,64]
  * (channel = (py*4+px)*4+c): the layout the tensor-core conv1 reads (one swizzle atom per tap) */
 int v4l_ingest_img(v4l_ctx* ctx, void* stream, const float* img, void* out_s2d, int64_t n_img);
-/* dst_bf16[i, 0:dst_cols] = src[idx ? idx[i] : i, 0:src_cols] zero padded (proprio rows -> K-padded
- * bf16 operand; also fp32 -> bf16 conversion of loss gradients)                                */
-int v4l_gather_rows_bf16(v4l_ctx* ctx, void* stream, const void* src, int src_is_f32,
-                         const int32_t* idx, void* dst, int rows, int src_cols, int64_t src_stride,
-                         int dst_cols);
-int v4l_relu_bwd_bf16(v4l_ctx* ctx, void* stream, const void* dy, const v4l_rowmap* dy_map,
+/* dst_f16[i, 0:dst_cols] = src[idx ? idx[i] : i, 0:src_cols] zero padded (proprio rows -> K-padded
+ * f16 operand; also fp32 -> f16 conversion of loss gradients)                                */
+int v4l_gather_rows_f16(v4l_ctx* ctx, void* stream, const void* src, int src_is_f32,
+                        const int32_t* idx, void* dst, int rows, int src_cols, int64_t src_stride,
+                        int dst_cols, float scale);
+int v4l_relu_bwd_f16(v4l_ctx* ctx, void* stream, const void* dy, const v4l_rowmap* dy_map,
                       const void* act, const v4l_rowmap* act_map, void* out,
                       const v4l_rowmap* out_map, int M, int N);
 

@@ -1,6 +1,6 @@
-"""Tensor-core tier (tcgen05 + TMA) kernel parity against torch on bf16-rounded operands.
+"""Tensor-core tier (tcgen05 + TMA) kernel parity against torch on fp16-rounded operands.
 The GEMM itself is exact up to fp32 accumulation order, so errors are ~1e-6 relative except for
-the final bf16 rounding of the stored output (2^-9 relative) — tolerance 1e-2 is the bf16 tier's
+the final fp16 rounding of the stored output (2^-9 relative) — tolerance 1e-2 is the fp16 tier's
 north-star bound; we assert the much tighter 5e-3 on outputs of O(1)."""
 import math
 
@@ -24,7 +24,7 @@ def rel(a, b):
 
 
 def bf(x):
-  return x.to(torch.bfloat16)
+  return x.to(torch.float16)
 
 
 def _linear_case(M, N, K, relu, f32_out, N_valid=None):
@@ -38,7 +38,7 @@ def _linear_case(M, N, K, relu, f32_out, N_valid=None):
   w[:N_valid, :K] = torch.randn(N_valid, K, device=DEV) / math.sqrt(K)
   w = bf(w)
   bias = torch.randn(N_valid, device=DEV)
-  out = torch.full((M, N_valid), float("nan"), device=DEV, dtype=torch.float32 if f32_out else torch.bfloat16)
+  out = torch.full((M, N_valid), float("nan"), device=DEV, dtype=torch.float32 if f32_out else torch.float16)
   ops.tc_gemm(x, (M, 1, 1, K), (M, 1, 1), (1, 1, 128), [(0, 0)], kch, w, N, N_valid, bias, out,
               RM.dense(N_valid), c_f32=f32_out, flags=engine.RELU if relu else 0)
   torch.cuda.synchronize()
@@ -87,7 +87,7 @@ def test_tc_conv3_taps_and_dgrad():
   bias = torch.randn(64, device=DEV)
   taps = [(kw, kh) for kh in range(3) for kw in range(3)]
   wp = w.permute(0, 2, 3, 1).reshape(64, 9 * 64).contiguous()  # [n][(kh,kw),c]
-  out = torch.zeros(B, 4, 4, 64, device=DEV, dtype=torch.bfloat16)
+  out = torch.zeros(B, 4, 4, 64, device=DEV, dtype=torch.float16)
   ops.tc_gemm(x, (B, 6, 6, 64), (B, 4, 4), (4, 4, 8), taps, 1, wp, 64, 64, bias, out, RM(16, 16 * 64, 64, 0),
               flags=engine.RELU)
   ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias)).permute(0, 2, 3, 1)
@@ -96,7 +96,7 @@ def test_tc_conv3_taps_and_dgrad():
   dy = bf(torch.randn(B, 4, 4, 64, device=DEV))
   wd = w.permute(1, 2, 3, 0).reshape(64, 9 * 64).contiguous()  # [c][(kh,kw),n]
   dtaps = [(-kw, -kh) for kh in range(3) for kw in range(3)]
-  dx = torch.zeros(B, 6, 6, 64, device=DEV, dtype=torch.bfloat16)
+  dx = torch.zeros(B, 6, 6, 64, device=DEV, dtype=torch.float16)
   ops.tc_gemm(dy, (B, 4, 4, 64), (B, 6, 6), (6, 6, 3), dtaps, 1, wd, 64, 64, None, dx, RM(36, 36 * 64, 64, 0),
               mask=x)
   xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
@@ -119,7 +119,7 @@ def test_tc_conv1_space_to_depth():
   # w[n, c, 4dy+py, 4dx+px] -> wp[n][(dy,dx)][(py,px,c)]
   wp = w.reshape(32, 4, 2, 4, 2, 4).permute(0, 2, 4, 3, 5, 1).reshape(32, 4 * 64).contiguous()
   taps = [(dx, dy) for dy in range(2) for dx in range(2)]
-  out = torch.zeros(B, 15, 15, 32, device=DEV, dtype=torch.bfloat16)
+  out = torch.zeros(B, 15, 15, 32, device=DEV, dtype=torch.float16)
   ops.tc_gemm(s2d, (B, 16, 16, 64), (B, 15, 15), (15, 8, 1), taps, 1, wp, 32, 32, bias, out,
               RM(225, 225 * 32, 32, 0), flags=engine.RELU)
   ref = F.relu(F.conv2d(img.float(), w.float(), bias, stride=4)).permute(0, 2, 3, 1)
@@ -141,7 +141,7 @@ def test_tc_wgrad_linear(M, N, K):
   ref = dy.float()[:, :N_valid].t() @ x.float()
   assert rel(dw, ref) < 1e-4
   db = torch.empty(N_valid, device=DEV)
-  ops.colsum_bf16(dy, RM.dense(N), M, N_valid, db)
+  ops.colsum_f16(dy, RM.dense(N), M, N_valid, db)
   assert rel(db, dy.float()[:, :N_valid].sum(0)) < 1e-4
 
 
@@ -179,7 +179,7 @@ def test_tc_wgrad_conv3_and_conv1():
 
 
 # =================================================================================================
-# whole-network parity of the tensor-core tier (bf16 tier tolerance of the north star: 1e-2)
+# whole-network parity of the tensor-core tier (fp16 tier tolerance of the north star: 1e-2)
 # =================================================================================================
 def _tc_agent(B=32, graph=False):
   from oracle import ppo_oracle as po, synth
@@ -191,7 +191,7 @@ def _tc_agent(B=32, graph=False):
   load_np_sd(pf, pf_np); load_np_sd(vf, vf_np)
   pf, vf = pf.to(DEV), vf.to(DEV)
   agent, logger = make_ppo(pf, vf, None, A, B, B, 1, device=DEV)
-  agent.precision = "bf16"
+  agent.precision = "f16"
   agent.use_cuda_graph = graph
   agent.current_epoch = 0
   opf, ovf = po.sd_to_torch(pf_np, vf_np)
@@ -220,12 +220,12 @@ def test_tc_tier_update_matches_oracle(B):
   m_err = rel(eng._bufs(B)["mean"], orc._last["mean"])
   print("B=%d value err %.3e mean err %.3e" % (B, v_err, m_err))
   assert v_err < 1e-2
-  assert m_err < 3e-2   # the actor forward runs on an encoder already stepped by (bf16) critic grads
+  assert m_err < 3e-2   # the actor forward runs on an encoder already stepped by (fp16) critic grads
   for k in ("Training/vf_loss", "logprob/mean", "advs/mean", "advs/std", "log_std/mean"):
     assert abs(info[k] - ref[k]) <= 1e-2 * abs(ref[k]) + 1e-4, (k, info[k], ref[k])
   assert abs(info["grad_norm/vf"] - ref["grad_norm/vf"]) <= 3e-2 * ref["grad_norm/vf"]
   assert abs(info["grad_norm/pf"] - ref["grad_norm/pf"]) <= 5e-2 * ref["grad_norm/pf"]
-  # gradients, tensor by tensor (norm-wise): bf16 activations/gradients, fp32 accumulation
+  # gradients, tensor by tensor (norm-wise): fp16 activations/gradients, fp32 accumulation
   worst = 0.0
   for k, gr in orc._last["vgrads"].items():
     e = nrm_err(eng.G_vf[k], gr)
@@ -248,7 +248,7 @@ def test_tc_tier_graph_replay_is_bit_identical():
     roll = synth.make_rollout(5, 16, 4, S, A, p_term=0.1)
     buf = fill_buffer(roll, 16, 4)
     agent, logger = make_ppo(pf, vf, buf, A, 16, 64, 2, device=DEV)
-    agent.precision = "bf16"
+    agent.precision = "f16"
     agent.use_cuda_graph = graph
     agent.current_epoch = 3
     np.random.seed(9)

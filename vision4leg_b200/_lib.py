@@ -72,7 +72,7 @@ class TcWgradArgs(C.Structure):
               ("B", C.c_int32), ("Hout", C.c_int32), ("Wout", C.c_int32),
               ("bw", C.c_int32), ("bh", C.c_int32), ("bb", C.c_int32),
               ("n_taps", C.c_int32), ("tap_dw", C.c_int32 * 16), ("tap_dh", C.c_int32 * 16),
-              ("N_valid", C.c_int32), ("index", C.c_void_p), ("dw", C.c_void_p)]
+              ("N_valid", C.c_int32), ("index", C.c_void_p), ("dw", C.c_void_p), ("out_scale", C.c_float)]
 
 
 _vp, _i, _i64, _f, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
@@ -95,12 +95,12 @@ SIGNATURES = {
   "v4l_ln_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i],
   "v4l_pool_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
   "v4l_pool_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
-  "v4l_attn_fwd_bf16": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i],
-  "v4l_attn_bwd_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i],
-  "v4l_ln_fwd_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f],
-  "v4l_ln_bwd_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i],
-  "v4l_pool_fwd_bf16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
-  "v4l_pool_bwd_bf16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
+  "v4l_attn_fwd_f16": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i],
+  "v4l_attn_bwd_f16": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i],
+  "v4l_ln_fwd_f16": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f],
+  "v4l_ln_bwd_f16": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f],
+  "v4l_pool_fwd_f16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
+  "v4l_pool_bwd_f16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
   "v4l_gae": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i, _i, _d, _d, _i, _i],
   "v4l_select_rows": [_vp, _vp, _vp, _vp, _vp, _i],
   "v4l_slot_advance": [_vp, _vp, _vp, C.c_int32],
@@ -111,12 +111,12 @@ SIGNATURES = {
   "v4l_clip_adam": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i],
   "v4l_tc_gemm": [_vp, _vp, C.POINTER(TcGemmArgs)],
   "v4l_tc_wgrad": [_vp, _vp, C.POINTER(TcWgradArgs)],
-  "v4l_colsum_bf16": [_vp, _vp, _vp, C.POINTER(RowMap), _i, _i, _i, _vp],
+  "v4l_colsum_f16": [_vp, _vp, _vp, C.POINTER(RowMap), _i, _i, _i, _f, _vp],
   "v4l_ingest_img": [_vp, _vp, _vp, _vp, _i64],
-  "v4l_gather_rows_bf16": [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i64, _i],
-  "v4l_relu_bwd_bf16": [_vp, _vp, _vp, C.POINTER(RowMap), _vp, C.POINTER(RowMap), _vp, C.POINTER(RowMap),
+  "v4l_gather_rows_f16": [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i64, _i, _f],
+  "v4l_relu_bwd_f16": [_vp, _vp, _vp, C.POINTER(RowMap), _vp, C.POINTER(RowMap), _vp, C.POINTER(RowMap),
                         _i, _i],
-  "v4l_pack_bf16": [_vp, _vp, _vp, _vp, _vp, _i64],
+  "v4l_pack_f16": [_vp, _vp, _vp, _vp, _vp, _i64],
   "v4l_h2d_2d": [_vp, _vp, _sz, _vp, _sz, _sz, _sz],
 }
 _RESTYPE = {"v4l_last_error": C.c_char_p}

@@ -28,7 +28,7 @@ class PPO(A2C):
     self.sample_key = ["obs", "acts", "advs", "estimate_returns", "values"]
     self.process_group = None       # set to a torch.distributed group for data-parallel updates
     self.use_cuda_graph = True
-    self.precision = "fp32"         # "fp32": exact CUDA-core tier; "bf16": tcgen05 tensor-core tier
+    self.precision = "fp32"         # "fp32": exact CUDA-core tier; "fp16": tcgen05 tensor-core tier
     self._engine = None
 
   @property

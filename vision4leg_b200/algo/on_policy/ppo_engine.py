@@ -88,10 +88,10 @@ class PPOUpdateEngine:
       self.world = dist.get_world_size(process_group)
     self._build_buckets()
     kw = getattr(pf, "_plan_kwargs", {})
-    if precision not in ("fp32", "bf16"):
-      raise ValueError("precision must be 'fp32' (exact CUDA-core tier) or 'bf16' (tcgen05 tier)")
+    if precision not in ("fp32", "f16"):
+      raise ValueError("precision must be 'fp32' (exact CUDA-core tier) or 'f16' (tcgen05 tier)")
     self.precision = precision
-    if precision == "bf16":
+    if precision == "f16":
       if self.family != "loco":
         raise NotImplementedError("the tensor-core tier currently covers the LocoTransformer family; "
                                   "use precision='fp32' for %s" % self.family)
@@ -172,8 +172,8 @@ class PPOUpdateEngine:
              terminals=f(N), advs=f(N), rets=f(N), last_value=f(E))
     if self.has_img:
       r["img"] = f(N, engine.IMG_ELEMS)
-      if self.precision == "bf16":
-        r["imgs"] = torch.empty((N, 16, 16, 64), device=dev, dtype=torch.bfloat16)
+      if self.precision == "f16":
+        r["imgs"] = torch.empty((N, 16, 16, 64), device=dev, dtype=torch.float16)
     self._roll = r
     self._graphs.clear()            # captured graphs hold the old planes' addresses
     return r
@@ -195,8 +195,8 @@ class PPOUpdateEngine:
       self.ops.h2d_2d(r["img"], engine.IMG_ELEMS * 4, obs.data_ptr() + self.S * 4, D * 4,
                       engine.IMG_ELEMS * 4, T * E)
     self.h2d_bytes = T * E * D * 4
-    if self.precision == "bf16":
-      self.ops.ingest_img(r["img"], r["imgs"], T * E)       # fp32 CHW -> bf16 space-to-depth NHWC
+    if self.precision == "f16":
+      self.ops.ingest_img(r["img"], r["imgs"], T * E)       # fp32 CHW -> fp16 space-to-depth NHWC
     for key in ("acts", "values", "rewards", "terminals"):
       src = host[key].reshape(T * E, -1)
       r[key].view(T * E, -1).copy_(src, non_blocking=True)
@@ -229,11 +229,11 @@ class PPOUpdateEngine:
     x = torch.as_tensor(np.ascontiguousarray(last_obs, dtype=np.float32)).to(self.device).reshape(E, -1)
     v = torch.empty((E, 1), device=self.device, dtype=torch.float32)
     plan = self._aux_plan(E)
-    if self.precision == "bf16":
-      imgs = torch.empty((E, 16, 16, 64), device=self.device, dtype=torch.bfloat16)
+    if self.precision == "f16":
+      imgs = torch.empty((E, 16, 16, 64), device=self.device, dtype=torch.float16)
       self.ops.ingest_img(x[:, self.S:].contiguous(), imgs, E)
-      st = torch.empty((E, plan.Sp), device=self.device, dtype=torch.bfloat16)
-      self.ops.gather_rows_bf16(x, True, None, st, E, self.S, x.shape[1], plan.Sp)
+      st = torch.empty((E, plan.Sp), device=self.device, dtype=torch.float16)
+      self.ops.gather_rows_f16(x, True, None, st, E, self.S, x.shape[1], plan.Sp)
       plan.pack(self.vf_flat)
       plan.forward(self.vf_flat, imgs, None, st, E, v)
     else:
@@ -252,7 +252,7 @@ class PPOUpdateEngine:
     p = self._mb_bufs.get(key)
     if p is None:
       kw = getattr(self.pf, "_plan_kwargs", {})
-      if self.precision == "bf16":
+      if self.precision == "f16":
         p = engine_tc.LocoPlanTC(self.ops, self.S, 1, self.vf_layout, kw.get("n_heads", (1, 1)), with_backward=False)
       else:
         p = engine.make_plan(self.family, self.ops, self.S, 1, **kw)
@@ -269,7 +269,7 @@ class PPOUpdateEngine:
   def sync_target(self):
     """copy_model_params_from_to(pf, target_pf) as one D2D copy (reference utils.py:23-25)."""
     self.t_flat.copy_(self.pf_flat)
-    if self.precision == "bf16":
+    if self.precision == "f16":
       self.plan_t.pack(self.t_flat)
 
   def _bufs(self, B):
@@ -282,8 +282,8 @@ class PPOUpdateEngine:
                stats=torch.zeros(8, device=dev, dtype=torch.float64))
       if self.world > 1:
         b["stats_all"] = torch.zeros((self.world, 8), device=dev, dtype=torch.float64)
-      if self.precision == "bf16":
-        b["st"] = torch.zeros((B, self.plan_pf.Sp), device=dev, dtype=torch.bfloat16)
+      if self.precision == "f16":
+        b["st"] = torch.zeros((B, self.plan_pf.Sp), device=dev, dtype=torch.float16)
       self._mb_bufs[B] = b
     return b
 
@@ -304,7 +304,7 @@ class PPOUpdateEngine:
     ops.adv_stats(r["advs"], idx, B, b["stats"])
     if self.world > 1:
       self._allreduce_stats(b)
-    if self.precision == "bf16":
+    if self.precision == "f16":
       return self._minibatch_tc(B, b, idx, inv_local, inv_global)
     inp = self._input(B, idx)
     # ---- critic
@@ -330,12 +330,12 @@ class PPOUpdateEngine:
     ops.slot_advance(self._slot, 0)
 
   def _minibatch_tc(self, B, b, idx, inv_local, inv_global):
-    """Same sequence on the tensor-core tier: bf16 activations, tcgen05 GEMMs; weights are
-    re-packed to bf16 right before each network's forward (the critic step has just changed
+    """Same sequence on the tensor-core tier: fp16 activations, tcgen05 GEMMs; weights are
+    re-packed to fp16 right before each network's forward (the critic step has just changed
     the shared encoder when the actor runs)."""
     ops, r = self.ops, self._roll
     imgs, st = r["imgs"], b["st"]
-    ops.gather_rows_bf16(r["state"], True, idx, st, B, self.S, self.S, self.plan_pf.Sp)
+    ops.gather_rows_f16(r["state"], True, idx, st, B, self.S, self.S, self.plan_pf.Sp)
     # ---- critic
     self.plan_vf.pack(self.vf_flat)
     self.plan_vf.forward(self.vf_flat, imgs, idx, st, B, b["values"])

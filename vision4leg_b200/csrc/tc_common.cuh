@@ -5,7 +5,7 @@
 // cute/arch/mma_sm100_desc.hpp of the vendored CUTLASS headers).
 #pragma once
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace tc {
@@ -137,11 +137,11 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
-// Instruction descriptor for kind::f16 with BF16 inputs and FP32 accumulator:
-//   [4,6) D format: 1 = F32   [7,10) A format: 1 = BF16   [10,13) B format: 1 = BF16
+// Instruction descriptor for kind::f16 with FP16 inputs and FP32 accumulator:
+//   [4,6) D format: 1 = F32   [7,10) A format: 0 = F16 (1 = BF16)   [10,13) B format: 0 = F16
 //   [15] A major (0 = K, 1 = MN)   [16] B major   [17,23) N >> 3   [24,29) M >> 4
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }

@@ -1,14 +1,14 @@
-// Tensor-core tier: tap-shifted TMA + tcgen05 GEMM (bf16 operands, fp32 accumulators in TMEM).
+// Tensor-core tier: tap-shifted TMA + tcgen05 GEMM (f16 operands, fp32 accumulators in TMEM).
 //
 //   D[128-row tile, N] = sum_{tap, kc} A_tap[rows, 64 k] * W[N, (tap, kc, 64 k)]^T
 //
 // One kernel covers every forward layer and every data-gradient of the PPO networks:
-//   * A is an NHWC bf16 activation viewed as a 4-D TMA tensor {C, W, H, B}; a row tile is a TMA
+//   * A is an NHWC f16 activation viewed as a 4-D TMA tensor {C, W, H, B}; a row tile is a TMA
 //     box {64, bw, bh, bb} (<= 128 rows).  Convolutions are a sum over taps of the SAME box
 //     shifted by (dw, dh) — implicit im2col done by the TMA unit, out-of-range pixels zero-filled
 //     by the hardware (this also gives the "full" correlation of the data-gradient with negative
 //     shifts).  Plain matrices are the degenerate case W = H = 1, B = M.
-//   * W is a packed bf16 weight matrix [N, taps*kchunks*64] (K-major), one TMA box {64, N}.
+//   * W is a packed f16 weight matrix [N, taps*kchunks*64] (K-major), one TMA box {64, N}.
 //   * both land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes.
 // Warp roles (192 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 =
 // TMEM allocator + single-thread MMA issuer, warps 2-5 = epilogue (TMEM -> registers -> bias /
@@ -23,7 +23,7 @@ namespace {
 
 constexpr int TC_THREADS = 192;
 constexpr int TC_STAGES = 4;
-constexpr int A_TILE_BYTES = 128 * 128;          // 128 rows x 64 bf16
+constexpr int A_TILE_BYTES = 128 * 128;          // 128 rows x 64 f16
 constexpr int ACC_COLS = 256;                    // TMEM columns per accumulator stage
 constexpr int MAX_TAPS = 16;
 
@@ -40,15 +40,15 @@ struct TcGemmParams {
   void* c;
   v4l_rowmap c_map;
   int c_f32;
-  const __nv_bfloat16* mask;
+  const __half* mask;
   int flags;
   const int32_t* a_idx;
 };
 
-__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+__device__ __forceinline__ float h16_lo(uint32_t u) { return __half2float(__ushort_as_half(static_cast<unsigned short>(u & 0xffffu))); }
+__device__ __forceinline__ float h16_hi(uint32_t u) { return __half2float(__ushort_as_half(static_cast<unsigned short>(u >> 16))); }
+__device__ __forceinline__ uint32_t pack_h16(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   } else if (warp == 1) {
     // ============================== MMA issuer ================================
     if (lane == 0) {
-      const uint32_t idesc = tc::umma_idesc_bf16(128, N, 0, 0);
+      const uint32_t idesc = tc::umma_idesc_f16(128, N, 0, 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -182,40 +182,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
           const long long addr = row_addr + c0 + j0;
           const bool full8 = (n + 8 <= p.N_valid);
           if (!p.c_f32 && full8 && ((addr & 7) == 0)) {
-            __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.c) + addr;
+            __half* cp = reinterpret_cast<__half*>(p.c) + addr;
             if (p.mask) {
               const uint4 m = *reinterpret_cast<const uint4*>(p.mask + addr);
               const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                if (!(bf16_lo(mw[j]) > 0.f)) f[2 * j] = 0.f;
-                if (!(bf16_hi(mw[j]) > 0.f)) f[2 * j + 1] = 0.f;
+                if (!(h16_lo(mw[j]) > 0.f)) f[2 * j] = 0.f;
+                if (!(h16_hi(mw[j]) > 0.f)) f[2 * j + 1] = 0.f;
               }
             }
             if (accum) {
               const uint4 o = *reinterpret_cast<const uint4*>(cp);
               const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) { f[2 * j] += bf16_lo(ow[j]); f[2 * j + 1] += bf16_hi(ow[j]); }
+              for (int j = 0; j < 4; ++j) { f[2 * j] += h16_lo(ow[j]); f[2 * j + 1] += h16_hi(ow[j]); }
             }
             uint4 o;
-            o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
-            o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+            o.x = pack_h16(f[0], f[1]); o.y = pack_h16(f[2], f[3]);
+            o.z = pack_h16(f[4], f[5]); o.w = pack_h16(f[6], f[7]);
             *reinterpret_cast<uint4*>(cp) = o;
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               if (n + j >= p.N_valid) break;
               float x = f[j];
-              if (p.mask && !(__bfloat162float(p.mask[addr + j]) > 0.f)) x = 0.f;
+              if (p.mask && !(__half2float(p.mask[addr + j]) > 0.f)) x = 0.f;
               if (p.c_f32) {
                 float* cp = reinterpret_cast<float*>(p.c) + addr + j;
                 if (accum) x += *cp;
                 *cp = x;
               } else {
-                __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.c) + addr + j;
-                if (accum) x += __bfloat162float(*cp);
-                *cp = __float2bfloat16(x);
+                __half* cp = reinterpret_cast<__half*>(p.c) + addr + j;
+                if (accum) x += __half2float(*cp);
+                *cp = __float2half(x);
               }
             }
           }
@@ -258,7 +258,7 @@ int v4l_encode_tmap(CUtensorMap* out, const void* gaddr, int rank, const uint64_
   cuuint32_t bx[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; if (elem_strides) estr[i] = elem_strides[i]; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(gaddr), gd, gs, bx, estr,
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(gaddr), gd, gs, bx, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -310,7 +310,7 @@ extern "C" int v4l_tc_gemm(v4l_ctx* ctx, void* stream, const v4l_tc_gemm_args* a
   for (int t = 0; t < a->n_taps; ++t) { p.tap_dw[t] = a->tap_dw[t]; p.tap_dh[t] = a->tap_dh[t]; }
   p.N = Nchunk; p.N_total = a->N_pad; p.N_valid = a->N_valid;
   p.bias = a->bias; p.c = a->c; p.c_map = a->c_map; p.c_f32 = a->c_f32;
-  p.mask = reinterpret_cast<const __nv_bfloat16*>(a->mask);
+  p.mask = reinterpret_cast<const __half*>(a->mask);
   p.flags = a->flags;
   p.a_idx = a->a_idx;
   V4L_REQUIRE(!a->a_idx || a->bb == 1, "v4l_tc_gemm: a_idx needs single-item boxes (bb == 1)");
@@ -330,22 +330,22 @@ extern "C" int v4l_tc_gemm(v4l_ctx* ctx, void* stream, const v4l_tc_gemm_args* a
 
 // ---- helper kernels of the tier: packing / conversion ------------------------------------------
 namespace {
-__global__ void pack_bf16_kernel(const float* __restrict__ src, const int32_t* __restrict__ index,
-                                 __nv_bfloat16* __restrict__ dst, long long n) {
+__global__ void pack_f16_kernel(const float* __restrict__ src, const int32_t* __restrict__ index,
+                                 __half* __restrict__ dst, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const long long s = index ? (long long)index[i] : i;
-    dst[i] = __float2bfloat16(s >= 0 ? src[s] : 0.f);
+    dst[i] = __float2half(s >= 0 ? src[s] : 0.f);
   }
 }
 }  // namespace
 
-extern "C" int v4l_pack_bf16(v4l_ctx* ctx, void* stream, const float* src, const int32_t* index, void* dst,
+extern "C" int v4l_pack_f16(v4l_ctx* ctx, void* stream, const float* src, const int32_t* index, void* dst,
                              int64_t n) {
-  V4L_REQUIRE(ctx && src && dst && n >= 0, "v4l_pack_bf16: bad argument");
+  V4L_REQUIRE(ctx && src && dst && n >= 0, "v4l_pack_f16: bad argument");
   if (n == 0) return 0;
   const int blocks = (int)min((long long)8 * ctx->sm_count, (long long)((n + 255) / 256));
-  pack_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, index, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  pack_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, index, reinterpret_cast<__half*>(dst), n);
   V4L_CHECK_LAUNCH();
   return 0;
 }
@@ -364,7 +364,7 @@ extern "C" int v4l_pack_bf16(v4l_ctx* ctx, void* stream, const float* src, const
 namespace {
 
 constexpr int WG_THREADS = 192;
-constexpr int ATOM_BYTES = 128 * 128;           // [<=128 reduction rows][64 channels] bf16
+constexpr int ATOM_BYTES = 128 * 128;           // [<=128 reduction rows][64 channels] f16
 
 struct TcWgradParams {
   CUtensorMap tmap_x;
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = tc::umma_idesc_bf16(128, Nmma, 1, 1);     // both operands MN-major
+      const uint32_t idesc = tc::umma_idesc_f16(128, Nmma, 1, 1);     // both operands MN-major
       int stage = 0; uint32_t phase = 0;
       uint32_t first = 1;
       for (int it = (tile_hi - tile_lo) * p.n_sub; it > 0; --it) {
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
 // dw[index[n*Kp + kp]] = sum_split partial[split][kp/128][kp%128][n]
 __global__ void tc_wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int kin_tiles, int Nmma,
                                        int N_valid, int Kp, const int32_t* __restrict__ index,
-                                       float* __restrict__ dw) {
+                                       float* __restrict__ dw, float out_scale) {
   const long long total = (long long)N_valid * Kp;
   const long long split_stride = (long long)kin_tiles * 128 * Nmma;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
@@ -515,12 +515,12 @@ __global__ void tc_wgrad_reduce_kernel(const float* __restrict__ partial, int sp
     const float* src = partial + (long long)kp * Nmma + n;
     float s = 0.f;
     for (int z = 0; z < splits; ++z) s += src[z * split_stride];
-    dw[dst] = s;
+    dw[dst] = s * out_scale;
   }
 }
 
-// column sums of a row-mapped bf16 [M, N] matrix (bias gradients), two deterministic stages
-__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy,
+// column sums of a row-mapped f16 [M, N] matrix (bias gradients), two deterministic stages
+__global__ void __launch_bounds__(256) colsum_f16_kernel(const __half* __restrict__ dy,
                                                           const v4l_rowmap map, int M, int N,
                                                           int rows_per_cta, float* __restrict__ part) {
   __shared__ float red[8][256];
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int n = c + 32 * i;
-      if (n < N) acc[i] += __bfloat162float(dy[a + n]);
+      if (n < N) acc[i] += __half2float(dy[a + n]);
     }
   }
 #pragma unroll
@@ -548,13 +548,13 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
   }
 }
 __global__ void colsum_reduce_kernel(const float* __restrict__ part, int nparts, int N, int fold,
-                                     float* __restrict__ out) {
+                                     float* __restrict__ out, float out_scale) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float s = 0.f;
   for (int p = 0; p < nparts; ++p)
     for (int f = 0; f < fold; ++f) s += part[(long long)p * N * fold + f * N + n];
-  out[n] = s;
+  out[n] = s * out_scale;
 }
 
 }  // namespace
@@ -630,15 +630,16 @@ extern "C" int v4l_tc_wgrad(v4l_ctx* ctx, void* stream, const v4l_tc_wgrad_args*
   V4L_CHECK_LAUNCH();
   const long long total = (long long)a->N_valid * Kp;
   const int rblocks = (int)min((long long)4 * ctx->sm_count, (total + 255) / 256);
-  tc_wgrad_reduce_kernel<<<rblocks, 256, 0, s>>>(ctx->scratch, splits, kin_tiles, Nmma, a->N_valid, Kp, a->index, a->dw);
+  tc_wgrad_reduce_kernel<<<rblocks, 256, 0, s>>>(ctx->scratch, splits, kin_tiles, Nmma, a->N_valid, Kp, a->index, a->dw,
+                                                 a->out_scale != 0.f ? a->out_scale : 1.f);
   V4L_CHECK_LAUNCH();
   return 0;
 }
 
-extern "C" int v4l_colsum_bf16(v4l_ctx* ctx, void* stream, const void* dy, const v4l_rowmap* map, int M, int N,
-                               int fold, float* out) {
-  V4L_REQUIRE(ctx && dy && map && out && map->P > 0, "v4l_colsum_bf16: bad argument");
-  V4L_REQUIRE(fold >= 1 && N >= 1 && N * fold <= 256 && M >= 1, "v4l_colsum_bf16: bad shape M=%d N=%d fold=%d", M, N, fold);
+extern "C" int v4l_colsum_f16(v4l_ctx* ctx, void* stream, const void* dy, const v4l_rowmap* map, int M, int N,
+                              int fold, float out_scale, float* out) {
+  V4L_REQUIRE(ctx && dy && map && out && map->P > 0, "v4l_colsum_f16: bad argument");
+  V4L_REQUIRE(fold >= 1 && N >= 1 && N * fold <= 256 && M >= 1, "v4l_colsum_f16: bad shape M=%d N=%d fold=%d", M, N, fold);
   const int Nout = N;
   N = N * fold;
   cudaStream_t s = (cudaStream_t)stream;
@@ -647,10 +648,10 @@ extern "C" int v4l_colsum_bf16(v4l_ctx* ctx, void* stream, const void* dy, const
   ctas = v4l_cdiv(M, rpc);
   // partials live past the region v4l_tc_wgrad uses? no: separate calls are stream-ordered
   float* part = ctx->scratch;
-  V4L_REQUIRE((size_t)ctas * N <= ctx->scratch_elems, "v4l_colsum_bf16: scratch too small");
-  colsum_bf16_kernel<<<ctas, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), *map, M, N, rpc, part);
+  V4L_REQUIRE((size_t)ctas * N <= ctx->scratch_elems, "v4l_colsum_f16: scratch too small");
+  colsum_f16_kernel<<<ctas, 256, 0, s>>>(reinterpret_cast<const __half*>(dy), *map, M, N, rpc, part);
   V4L_CHECK_LAUNCH();
-  colsum_reduce_kernel<<<v4l_cdiv(Nout, 128), 128, 0, s>>>(part, ctas, Nout, fold, out);
+  colsum_reduce_kernel<<<v4l_cdiv(Nout, 128), 128, 0, s>>>(part, ctas, Nout, fold, out, out_scale);
   V4L_CHECK_LAUNCH();
   return 0;
 }
@@ -660,10 +661,10 @@ extern "C" int v4l_colsum_bf16(v4l_ctx* ctx, void* stream, const void* dy, const
 // =================================================================================================
 namespace {
 
-// fp32 CHW [4,64,64] observation image -> bf16 4x4 space-to-depth NHWC [16,16,64],
+// fp32 CHW [4,64,64] observation image -> f16 4x4 space-to-depth NHWC [16,16,64],
 // channel = (py*4 + px)*4 + c for source pixel (4Y+py, 4X+px): the 8x8/4 conv becomes a 2x2/1
 // conv with 64-channel (128-byte) rows — exactly one TMA/UMMA swizzle atom per tap.
-__global__ void ingest_img_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, long long n_img) {
+__global__ void ingest_img_kernel(const float* __restrict__ img, __half* __restrict__ out, long long n_img) {
   const long long total = n_img * 16 * 4 * 16;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
@@ -682,8 +683,8 @@ __global__ void ingest_img_kernel(const float* __restrict__ img, __nv_bfloat16* 
     for (int px = 0; px < 4; ++px) {
       const float a0 = reinterpret_cast<const float*>(&v[0])[px], a1 = reinterpret_cast<const float*>(&v[1])[px];
       const float a2 = reinterpret_cast<const float*>(&v[2])[px], a3 = reinterpret_cast<const float*>(&v[3])[px];
-      w[2 * px] = pack_bf16(a0, a1);
-      w[2 * px + 1] = pack_bf16(a2, a3);
+      w[2 * px] = pack_h16(a0, a1);
+      w[2 * px + 1] = pack_h16(a2, a3);
     }
     (void)f0;
     uint4* dst = reinterpret_cast<uint4*>(out + ((n * 16 + Y) * 16 + X) * 64 + py * 16);
@@ -692,11 +693,11 @@ __global__ void ingest_img_kernel(const float* __restrict__ img, __nv_bfloat16* 
   }
 }
 
-// dst[i, :] = src[idx ? idx[i] : i, :] with fp32 or bf16 source, bf16 destination, zero padded to dcols
+// dst[i, :] = src[idx ? idx[i] : i, :] with fp32 or f16 source, f16 destination, zero padded to dcols
 template <typename S>
 __global__ void gather_rows_kernel(const S* __restrict__ src, const int32_t* __restrict__ idx,
-                                   __nv_bfloat16* __restrict__ dst, int rows, int scols, long long sstride,
-                                   int dcols) {
+                                   __half* __restrict__ dst, int rows, int scols, long long sstride,
+                                   int dcols, float scale) {
   const long long total = (long long)rows * dcols;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
@@ -704,22 +705,22 @@ __global__ void gather_rows_kernel(const S* __restrict__ src, const int32_t* __r
     float v = 0.f;
     if (c < scols) {
       const long long sr = idx ? (long long)idx[r] : (long long)r;
-      v = static_cast<float>(src[sr * sstride + c]);
+      v = static_cast<float>(src[sr * sstride + c]) * scale;
     }
-    dst[e] = __float2bfloat16(v);
+    dst[e] = __float2half(v);
   }
 }
 
-__global__ void relu_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const v4l_rowmap dy_map,
-                                     const __nv_bfloat16* __restrict__ act, const v4l_rowmap act_map,
-                                     __nv_bfloat16* __restrict__ out, const v4l_rowmap out_map, int M, int N) {
+__global__ void relu_bwd_f16_kernel(const __half* __restrict__ dy, const v4l_rowmap dy_map,
+                                     const __half* __restrict__ act, const v4l_rowmap act_map,
+                                     __half* __restrict__ out, const v4l_rowmap out_map, int M, int N) {
   const long long total = (long long)M * N;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
     const int m = (int)(e / N), n = (int)(e - (long long)m * N);
-    const __nv_bfloat16 g = dy[v4l_row_addr(dy_map, m) + n];
-    const float a = __bfloat162float(act[v4l_row_addr(act_map, m) + n]);
-    out[v4l_row_addr(out_map, m) + n] = a > 0.f ? g : __float2bfloat16(0.f);
+    const __half g = dy[v4l_row_addr(dy_map, m) + n];
+    const float a = __half2float(act[v4l_row_addr(act_map, m) + n]);
+    out[v4l_row_addr(out_map, m) + n] = a > 0.f ? g : __float2half(0.f);
   }
 }
 
@@ -730,37 +731,37 @@ extern "C" int v4l_ingest_img(v4l_ctx* ctx, void* stream, const float* img, void
   if (n_img == 0) return 0;
   const long long total = n_img * 1024;
   const int blocks = (int)min((long long)16 * ctx->sm_count, (total + 255) / 256);
-  ingest_img_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(img, reinterpret_cast<__nv_bfloat16*>(out_s2d), n_img);
+  ingest_img_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(img, reinterpret_cast<__half*>(out_s2d), n_img);
   V4L_CHECK_LAUNCH();
   return 0;
 }
 
-extern "C" int v4l_gather_rows_bf16(v4l_ctx* ctx, void* stream, const void* src, int src_is_f32,
-                                    const int32_t* idx, void* dst, int rows, int src_cols, int64_t src_stride,
-                                    int dst_cols) {
-  V4L_REQUIRE(ctx && src && dst && rows >= 0 && src_cols >= 0 && dst_cols >= src_cols, "v4l_gather_rows_bf16: bad argument");
+extern "C" int v4l_gather_rows_f16(v4l_ctx* ctx, void* stream, const void* src, int src_is_f32,
+                                   const int32_t* idx, void* dst, int rows, int src_cols, int64_t src_stride,
+                                   int dst_cols, float scale) {
+  V4L_REQUIRE(ctx && src && dst && rows >= 0 && src_cols >= 0 && dst_cols >= src_cols, "v4l_gather_rows_f16: bad argument");
   const long long total = (long long)rows * dst_cols;
   if (total == 0) return 0;
   const int blocks = (int)min((long long)8 * ctx->sm_count, (total + 255) / 256);
   cudaStream_t s = (cudaStream_t)stream;
   if (src_is_f32)
-    gather_rows_kernel<float><<<blocks, 256, 0, s>>>((const float*)src, idx, (__nv_bfloat16*)dst, rows, src_cols, src_stride, dst_cols);
+    gather_rows_kernel<float><<<blocks, 256, 0, s>>>((const float*)src, idx, (__half*)dst, rows, src_cols, src_stride, dst_cols, scale);
   else
-    gather_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)src, idx, (__nv_bfloat16*)dst, rows, src_cols, src_stride, dst_cols);
+    gather_rows_kernel<__half><<<blocks, 256, 0, s>>>((const __half*)src, idx, (__half*)dst, rows, src_cols, src_stride, dst_cols, scale);
   V4L_CHECK_LAUNCH();
   return 0;
 }
 
-extern "C" int v4l_relu_bwd_bf16(v4l_ctx* ctx, void* stream, const void* dy, const v4l_rowmap* dy_map,
+extern "C" int v4l_relu_bwd_f16(v4l_ctx* ctx, void* stream, const void* dy, const v4l_rowmap* dy_map,
                                  const void* act, const v4l_rowmap* act_map, void* out,
                                  const v4l_rowmap* out_map, int M, int N) {
-  V4L_REQUIRE(ctx && dy && dy_map && act && act_map && out && out_map, "v4l_relu_bwd_bf16: NULL argument");
-  V4L_REQUIRE(dy_map->P > 0 && act_map->P > 0 && out_map->P > 0, "v4l_relu_bwd_bf16: row map with P <= 0");
+  V4L_REQUIRE(ctx && dy && dy_map && act && act_map && out && out_map, "v4l_relu_bwd_f16: NULL argument");
+  V4L_REQUIRE(dy_map->P > 0 && act_map->P > 0 && out_map->P > 0, "v4l_relu_bwd_f16: row map with P <= 0");
   const long long total = (long long)M * N;
   if (total <= 0) return 0;
   const int blocks = (int)min((long long)8 * ctx->sm_count, (total + 255) / 256);
-  relu_bwd_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
-    (const __nv_bfloat16*)dy, *dy_map, (const __nv_bfloat16*)act, *act_map, (__nv_bfloat16*)out, *out_map, M, N);
+  relu_bwd_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+    (const __half*)dy, *dy_map, (const __half*)act, *act_map, (__half*)out, *out_map, M, N);
   V4L_CHECK_LAUNCH();
   return 0;
 }

@@ -1,17 +1,17 @@
 // Per-sample attention core, LayerNorm(+residual) and token pooling of the LocoTransformer
 // block (reference torchrl/networks/nets.py:949-955, 1009-1034; math: SURVEY Appendix A2).
 // fp32 tier: one CTA per sample keeps q/k/v (T<=33 tokens x d<=128) in shared memory.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
 namespace {
 
-// IO element type: float (exact tier) or __nv_bfloat16 (tensor-core tier); math is fp32 either way
+// IO element type: float (exact tier) or __half (tensor-core tier); math is fp32 either way
 __device__ __forceinline__ float ldf(const float* p) { return *p; }
-__device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float ldf(const __half* p) { return __half2float(*p); }
 __device__ __forceinline__ void stf(float* p, float v) { *p = v; }
-__device__ __forceinline__ void stf(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+__device__ __forceinline__ void stf(__half* p, float v) { *p = __float2half(v); }
 
 constexpr int ATT_THREADS = 128;
 
@@ -244,13 +244,13 @@ ln_bwd_kernel(const T_* __restrict__ dy, const float* __restrict__ z,
 }
 
 __global__ void ln_bwd_reduce_kernel(const float* __restrict__ part, int nparts, int d,
-                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta, float out_scale) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= 2 * d) return;
   const int which = e / d, c = e - which * d;
   float s = 0.f;
   for (int p = 0; p < nparts; ++p) s += part[((long long)p * 2 + which) * d + c];
-  (which ? dbeta : dgamma)[c] = s;
+  (which ? dbeta : dgamma)[c] = s * out_scale;
 }
 
 template <typename T_>
@@ -302,7 +302,7 @@ static int attn_check(const char* who, int B, int T, int d, int nh) {
   return 0;
 }
 
-typedef __nv_bfloat16 bf16_t;
+typedef __half f16_t;
 
 template <typename T_>
 static int attn_fwd_impl(v4l_ctx* ctx, void* stream, const void* qkv, void* o, float* p, int B, int T, int d,
@@ -346,7 +346,8 @@ static int ln_fwd_impl(v4l_ctx* ctx, void* stream, const void* a, const void* re
 
 template <typename T_>
 static int ln_bwd_impl(v4l_ctx* ctx, void* stream, const void* dy, const float* z, const float* stats,
-                       const float* gamma, void* dz, float* dgamma, float* dbeta, int rows, int d) {
+                       const float* gamma, void* dz, float* dgamma, float* dbeta, int rows, int d,
+                       float out_scale) {
   V4L_REQUIRE(ctx && dy && z && stats && gamma && dz && dgamma && dbeta, "v4l_ln_bwd: NULL argument");
   V4L_REQUIRE(d > 0 && d <= 32 * LN_MAXPER, "v4l_ln_bwd: d=%d unsupported", d);
   V4L_REQUIRE(rows > 0, "v4l_ln_bwd: rows must be > 0");
@@ -357,7 +358,7 @@ static int ln_bwd_impl(v4l_ctx* ctx, void* stream, const void* dy, const float* 
   cudaStream_t s = (cudaStream_t)stream;
   ln_bwd_kernel<T_><<<ctas, 256, 0, s>>>((const T_*)dy, z, stats, gamma, (T_*)dz, ctx->scratch, rows, d, rpc);
   V4L_CHECK_LAUNCH();
-  ln_bwd_reduce_kernel<<<v4l_cdiv(2 * d, 128), 128, 0, s>>>(ctx->scratch, ctas, d, dgamma, dbeta);
+  ln_bwd_reduce_kernel<<<v4l_cdiv(2 * d, 128), 128, 0, s>>>(ctx->scratch, ctas, d, dgamma, dbeta, out_scale);
   V4L_CHECK_LAUNCH();
   return 0;
 }
@@ -391,7 +392,7 @@ extern "C" int v4l_ln_fwd(v4l_ctx* ctx, void* stream, const float* a, const floa
 extern "C" int v4l_ln_bwd(v4l_ctx* ctx, void* stream, const float* dy, const float* z,
                           const float* stats, const float* gamma, float* dz, float* dgamma,
                           float* dbeta, int rows, int d) {
-  return ln_bwd_impl<float>(ctx, stream, dy, z, stats, gamma, dz, dgamma, dbeta, rows, d);
+  return ln_bwd_impl<float>(ctx, stream, dy, z, stats, gamma, dz, dgamma, dbeta, rows, d, 1.f);
 }
 extern "C" int v4l_pool_fwd(v4l_ctx* ctx, void* stream, const float* tok, float* out, int B, int T,
                             int d, int mode) {
@@ -402,30 +403,30 @@ extern "C" int v4l_pool_bwd(v4l_ctx* ctx, void* stream, const float* dout, float
   return pool_impl<float>(ctx, stream, dout, dtok, B, T, d, mode, false);
 }
 
-// ---- bf16-IO variants used by the tensor-core tier (fp32 math, fp32 softmax/LayerNorm statistics)
-extern "C" int v4l_attn_fwd_bf16(v4l_ctx* ctx, void* stream, const void* qkv, void* o, float* p,
+// ---- f16-IO variants used by the tensor-core tier (fp32 math, fp32 softmax/LayerNorm statistics)
+extern "C" int v4l_attn_fwd_f16(v4l_ctx* ctx, void* stream, const void* qkv, void* o, float* p,
                                  int B, int T, int d, int n_head) {
-  return attn_fwd_impl<bf16_t>(ctx, stream, qkv, o, p, B, T, d, n_head);
+  return attn_fwd_impl<f16_t>(ctx, stream, qkv, o, p, B, T, d, n_head);
 }
-extern "C" int v4l_attn_bwd_bf16(v4l_ctx* ctx, void* stream, const void* qkv, const float* p,
+extern "C" int v4l_attn_bwd_f16(v4l_ctx* ctx, void* stream, const void* qkv, const float* p,
                                  const void* d_o, void* d_qkv, int B, int T, int d, int n_head) {
-  return attn_bwd_impl<bf16_t>(ctx, stream, qkv, p, d_o, d_qkv, B, T, d, n_head);
+  return attn_bwd_impl<f16_t>(ctx, stream, qkv, p, d_o, d_qkv, B, T, d, n_head);
 }
-extern "C" int v4l_ln_fwd_bf16(v4l_ctx* ctx, void* stream, const void* a, const void* res,
+extern "C" int v4l_ln_fwd_f16(v4l_ctx* ctx, void* stream, const void* a, const void* res,
                                const float* gamma, const float* beta, void* y, float* z, float* stats,
                                int rows, int d, float eps) {
-  return ln_fwd_impl<bf16_t>(ctx, stream, a, res, gamma, beta, y, z, stats, rows, d, eps);
+  return ln_fwd_impl<f16_t>(ctx, stream, a, res, gamma, beta, y, z, stats, rows, d, eps);
 }
-extern "C" int v4l_ln_bwd_bf16(v4l_ctx* ctx, void* stream, const void* dy, const float* z,
+extern "C" int v4l_ln_bwd_f16(v4l_ctx* ctx, void* stream, const void* dy, const float* z,
                                const float* stats, const float* gamma, void* dz, float* dgamma,
-                               float* dbeta, int rows, int d) {
-  return ln_bwd_impl<bf16_t>(ctx, stream, dy, z, stats, gamma, dz, dgamma, dbeta, rows, d);
+                               float* dbeta, int rows, int d, float out_scale) {
+  return ln_bwd_impl<f16_t>(ctx, stream, dy, z, stats, gamma, dz, dgamma, dbeta, rows, d, out_scale);
 }
-extern "C" int v4l_pool_fwd_bf16(v4l_ctx* ctx, void* stream, const void* tok, void* out, int B, int T,
+extern "C" int v4l_pool_fwd_f16(v4l_ctx* ctx, void* stream, const void* tok, void* out, int B, int T,
                                  int d, int mode) {
-  return pool_impl<bf16_t>(ctx, stream, tok, out, B, T, d, mode, true);
+  return pool_impl<f16_t>(ctx, stream, tok, out, B, T, d, mode, true);
 }
-extern "C" int v4l_pool_bwd_bf16(v4l_ctx* ctx, void* stream, const void* dout, void* dtok, int B, int T,
+extern "C" int v4l_pool_bwd_f16(v4l_ctx* ctx, void* stream, const void* dout, void* dtok, int B, int T,
                                  int d, int mode) {
-  return pool_impl<bf16_t>(ctx, stream, dout, dtok, B, T, d, mode, false);
+  return pool_impl<f16_t>(ctx, stream, dout, dtok, B, T, d, mode, false);
 }

@@ -115,7 +115,7 @@ class Ops:
   # ---- tensor-core tier
   def tc_gemm(self, a, a_shape, out_grid, box, taps, kchunks, w, N_pad, N_valid, bias, c, c_map,
               c_f32=False, mask=None, flags=0, a_strides=None, a_idx=None, a_off=0):
-    """a: bf16 [a_B, a_H, a_W, a_C]; out_grid (B, Hout, Wout); box (bw, bh, bb); taps [(dw, dh)];
+    """a: fp16 [a_B, a_H, a_W, a_C]; out_grid (B, Hout, Wout); box (bw, bh, bb); taps [(dw, dh)];
     a_strides: element strides (sW, sH, sB) of a non-packed view; a_off: element offset"""
     g = TcGemmArgs()
     g.a = ptr(a) + 2 * a_off
@@ -135,7 +135,7 @@ class Ops:
     self.launches += 1
 
   def tc_wgrad(self, x, x_shape, dy, dy_C, out_grid, box, taps, N_valid, index, dw, x_idx=None,
-               x_estride=1, subs=None, dy_strides=None, dy_off=0, x_strides=None):
+               x_estride=1, subs=None, dy_strides=None, dy_off=0, x_strides=None, out_scale=1.0):
     """subs: [(sub_dw, sub_dh, dy_channel_offset)] sub-iterations per tile (space-to-depth cells)"""
     g = TcWgradArgs()
     g.x = ptr(x)
@@ -156,58 +156,60 @@ class Ops:
     for i, (dw_, dh_) in enumerate(taps):
       g.tap_dw[i], g.tap_dh[i] = dw_, dh_
     g.N_valid, g.index, g.dw = N_valid, ptr(index), ptr(dw)
+    g.out_scale = out_scale
     check(self.lib.v4l_tc_wgrad(self.h, self.ctx.stream(), C.byref(g)))
     self.launches += 2
 
-  def colsum_bf16(self, dy, dy_map, M, N, out, fold=1):
+  def colsum_f16(self, dy, dy_map, M, N, out, fold=1, out_scale=1.0):
     m = dy_map.c()
-    check(self.lib.v4l_colsum_bf16(self.h, self.ctx.stream(), ptr(dy), C.byref(m), M, N, fold, ptr(out)))
+    check(self.lib.v4l_colsum_f16(self.h, self.ctx.stream(), ptr(dy), C.byref(m), M, N, fold, out_scale,
+                                  ptr(out)))
     self.launches += 2
 
   def ingest_img(self, img_f32, out_s2d, n):
     check(self.lib.v4l_ingest_img(self.h, self.ctx.stream(), ptr(img_f32), ptr(out_s2d), n))
     self.launches += 1
 
-  def gather_rows_bf16(self, src, src_is_f32, idx, dst, rows, src_cols, src_stride, dst_cols):
-    check(self.lib.v4l_gather_rows_bf16(self.h, self.ctx.stream(), ptr(src), 1 if src_is_f32 else 0, ptr(idx),
-                                        ptr(dst), rows, src_cols, src_stride, dst_cols))
+  def gather_rows_f16(self, src, src_is_f32, idx, dst, rows, src_cols, src_stride, dst_cols, scale=1.0):
+    check(self.lib.v4l_gather_rows_f16(self.h, self.ctx.stream(), ptr(src), 1 if src_is_f32 else 0, ptr(idx),
+                                       ptr(dst), rows, src_cols, src_stride, dst_cols, scale))
     self.launches += 1
 
-  def relu_bwd_bf16(self, dy, dy_map, act, act_map, out, out_map, M, N):
+  def relu_bwd_f16(self, dy, dy_map, act, act_map, out, out_map, M, N):
     a, b, c = dy_map.c(), act_map.c(), out_map.c()
-    check(self.lib.v4l_relu_bwd_bf16(self.h, self.ctx.stream(), ptr(dy), C.byref(a), ptr(act), C.byref(b),
+    check(self.lib.v4l_relu_bwd_f16(self.h, self.ctx.stream(), ptr(dy), C.byref(a), ptr(act), C.byref(b),
                                      ptr(out), C.byref(c), M, N))
     self.launches += 1
 
-  def attn_fwd_bf16(self, qkv, o, p, B, T, d, nh):
-    check(self.lib.v4l_attn_fwd_bf16(self.h, self.ctx.stream(), ptr(qkv), ptr(o), ptr(p), B, T, d, nh))
+  def attn_fwd_f16(self, qkv, o, p, B, T, d, nh):
+    check(self.lib.v4l_attn_fwd_f16(self.h, self.ctx.stream(), ptr(qkv), ptr(o), ptr(p), B, T, d, nh))
     self.launches += 1
 
-  def attn_bwd_bf16(self, qkv, p, d_o, d_qkv, B, T, d, nh):
-    check(self.lib.v4l_attn_bwd_bf16(self.h, self.ctx.stream(), ptr(qkv), ptr(p), ptr(d_o), ptr(d_qkv),
+  def attn_bwd_f16(self, qkv, p, d_o, d_qkv, B, T, d, nh):
+    check(self.lib.v4l_attn_bwd_f16(self.h, self.ctx.stream(), ptr(qkv), ptr(p), ptr(d_o), ptr(d_qkv),
                                      B, T, d, nh))
     self.launches += 1
 
-  def ln_fwd_bf16(self, a, res, gamma, beta, y, z, stats, rows, d, eps=1e-5):
-    check(self.lib.v4l_ln_fwd_bf16(self.h, self.ctx.stream(), ptr(a), ptr(res), ptr(gamma), ptr(beta),
+  def ln_fwd_f16(self, a, res, gamma, beta, y, z, stats, rows, d, eps=1e-5):
+    check(self.lib.v4l_ln_fwd_f16(self.h, self.ctx.stream(), ptr(a), ptr(res), ptr(gamma), ptr(beta),
                                    ptr(y), ptr(z), ptr(stats), rows, d, eps))
     self.launches += 1
 
-  def ln_bwd_bf16(self, dy, z, stats, gamma, dz, dgamma, dbeta, rows, d):
-    check(self.lib.v4l_ln_bwd_bf16(self.h, self.ctx.stream(), ptr(dy), ptr(z), ptr(stats), ptr(gamma),
-                                   ptr(dz), ptr(dgamma), ptr(dbeta), rows, d))
+  def ln_bwd_f16(self, dy, z, stats, gamma, dz, dgamma, dbeta, rows, d, out_scale=1.0):
+    check(self.lib.v4l_ln_bwd_f16(self.h, self.ctx.stream(), ptr(dy), ptr(z), ptr(stats), ptr(gamma),
+                                  ptr(dz), ptr(dgamma), ptr(dbeta), rows, d, out_scale))
     self.launches += 2
 
-  def pool_fwd_bf16(self, tok, out, B, T, d, mode):
-    check(self.lib.v4l_pool_fwd_bf16(self.h, self.ctx.stream(), ptr(tok), ptr(out), B, T, d, mode))
+  def pool_fwd_f16(self, tok, out, B, T, d, mode):
+    check(self.lib.v4l_pool_fwd_f16(self.h, self.ctx.stream(), ptr(tok), ptr(out), B, T, d, mode))
     self.launches += 1
 
-  def pool_bwd_bf16(self, dout, dtok, B, T, d, mode):
-    check(self.lib.v4l_pool_bwd_bf16(self.h, self.ctx.stream(), ptr(dout), ptr(dtok), B, T, d, mode))
+  def pool_bwd_f16(self, dout, dtok, B, T, d, mode):
+    check(self.lib.v4l_pool_bwd_f16(self.h, self.ctx.stream(), ptr(dout), ptr(dtok), B, T, d, mode))
     self.launches += 1
 
-  def pack_bf16(self, src, index, dst, n):
-    check(self.lib.v4l_pack_bf16(self.h, self.ctx.stream(), ptr(src), ptr(index), ptr(dst), n))
+  def pack_f16(self, src, index, dst, n):
+    check(self.lib.v4l_pack_f16(self.h, self.ctx.stream(), ptr(src), ptr(index), ptr(dst), n))
     self.launches += 1
 
   # ---- transformer pieces

@@ -1,7 +1,7 @@
-"""Tensor-core tier of the PPO networks: bf16 activations, fp32 master weights / gradients,
+"""Tensor-core tier of the PPO networks: fp16 activations, fp32 master weights / gradients,
 every GEMM-shaped layer on tcgen05 (v4l_tc_gemm / v4l_tc_wgrad), fed by TMA.
 
-Layouts (all bf16 unless noted)
+Layouts (all fp16 unless noted)
   image      [N,16,16,64]  4x4 space-to-depth of the 4x64x64 depth stack (v4l_ingest_img): conv1
                            (8x8 stride 4) is a 2x2 stride-1 conv over 64-channel pixels
   a1 cells   [B,8,8,128]   conv1 output stored directly as the 2x2 space-to-depth "cells" of the
@@ -11,7 +11,7 @@ Layouts (all bf16 unless noted)
   tokens     [B,17,64]     slot 0 = proprio token, 1..16 = depth tokens (reference base.py:602-622)
 Every conv/linear is "sum over taps of a shifted TMA box x packed weight slice"; the data
 gradient is the same kernel with negated shifts and the transposed packing, the weight gradient
-reads the same boxes as MN-major operands.  Weights are re-packed (fp32 -> bf16, tap-major) from
+reads the same boxes as MN-major operands.  Weights are re-packed (fp32 -> fp16, tap-major) from
 the flat parameter bucket by ONE gather kernel per optimiser step through a precomputed index
 table; the same table scatters the fp32 weight gradients back into the reference layout.
 
@@ -24,7 +24,7 @@ from . import engine
 from .engine import RM, RELU, ACCUM
 from ._lib import V4LError
 
-BF16 = torch.bfloat16
+F16 = torch.float16
 
 
 def _ceil(a, b):
@@ -72,7 +72,7 @@ def _conv_tables(off, N, C, KH, KW, s):
 
 
 class TcWeights:
-  """Packed bf16 copies (forward and data-gradient orientations) of one network's GEMM weights."""
+  """Packed fp16 copies (forward and data-gradient orientations) of one network's GEMM weights."""
 
   def __init__(self, ops, layout, with_dgrad=True):
     """layout: {param name: (flat offset, shape)} relative to the flat fp32 bucket handed to pack()"""
@@ -103,13 +103,13 @@ class TcWeights:
       table[o:o + t.size] = t.ravel()
     dev = ops.device
     self.table = torch.tensor(table.astype(np.int32), device=dev)
-    self.packed = torch.zeros(cursor, device=dev, dtype=BF16)
+    self.packed = torch.zeros(cursor, device=dev, dtype=F16)
     for pk in list(self.fwd.values()) + list(self.dgr.values()):
       pk.dev_table = self.table[pk.off:pk.off + pk.rows * pk.cols]
       pk.w = self.packed[pk.off:pk.off + pk.rows * pk.cols]
 
   def pack(self, flat):
-    self.ops.pack_bf16(flat, self.table, self.packed, self.size)
+    self.ops.pack_f16(flat, self.table, self.packed, self.size)
 
 
 class LocoPlanTC:
@@ -135,7 +135,7 @@ class LocoPlanTC:
     self.taps3 = [(kw, kh) for kh in range(3) for kw in range(3)]
 
   # ---- workspace ------------------------------------------------------------------------------
-  def buf(self, name, shape, dtype=BF16, zero=False):
+  def buf(self, name, shape, dtype=F16, zero=False):
     key = (name,) + tuple(shape)
     t = self._ws.get(key)
     if t is None:
@@ -163,8 +163,10 @@ class LocoPlanTC:
     """dW, db from (x [M,x_cols], dy [M,dy_cols]); optionally dx = dy @ W (masked / accumulated)."""
     pk = self.W.fwd[wname]
     N, K = self.layout[wname][1][0], int(np.prod(self.layout[wname][1][1:]))
-    self.ops.tc_wgrad(x, (M, 1, 1, x_cols), dy, dy_cols, (M, 1, 1), (1, 1, 128), [(0, 0)], N, pk.dev_table, gflat)
-    self.ops.colsum_bf16(dy, RM.dense(dy_cols), M, N, self._view(gflat, wname[:-6] + "bias"))
+    inv = self._inv_scale
+    self.ops.tc_wgrad(x, (M, 1, 1, x_cols), dy, dy_cols, (M, 1, 1), (1, 1, 128), [(0, 0)], N, pk.dev_table, gflat,
+                      out_scale=inv)
+    self.ops.colsum_f16(dy, RM.dense(dy_cols), M, N, self._view(gflat, wname[:-6] + "bias"), out_scale=inv)
     if need_dx:
       pd = self.W.dgr[wname]
       self.ops.tc_gemm(dy, (M, 1, 1, dy_cols), (M, 1, 1), (1, 1, 128), [(0, 0)], pd.cols // 64, pd.w, pd.rows, K,
@@ -172,7 +174,7 @@ class LocoPlanTC:
 
   # ---- forward --------------------------------------------------------------------------------
   def forward(self, flat, imgs, idx, st, B, out):
-    """imgs [N,16,16,64] bf16 (whole rollout), idx int32 [B] or None, st [B,Sp] bf16 proprio rows,
+    """imgs [N,16,16,64] fp16 (whole rollout), idx int32 [B] or None, st [B,Sp] fp16 proprio rows,
     out fp32 [B,out_dim].  `flat` = the fp32 bucket the layout offsets refer to (biases, LN)."""
     ops, T, d = self.ops, self.T, self.d
     self._flat, self._B, self._imgs, self._idx, self._st = flat, B, imgs, idx, st
@@ -211,23 +213,23 @@ class LocoPlanTC:
       self._lin_fwd(flat, p + "self_attn.in_proj_weight", x, R, d, qkv, RM.dense(3 * d), False)
       o = self.buf("o%d" % l, (R, d))
       pr = self.buf("p%d" % l, (B, nh, T, T), torch.float32)
-      ops.attn_fwd_bf16(qkv, o, pr, B, T, d, nh)
+      ops.attn_fwd_f16(qkv, o, pr, B, T, d, nh)
       proj = self.buf("proj", (R, d))
       self._lin_fwd(flat, p + "self_attn.out_proj.weight", o, R, d, proj, RM.dense(d), False)
       h = self.buf("h%d" % l, (R, d))
       z1 = self.buf("z1_%d" % l, (R, d), torch.float32); st1 = self.buf("st1_%d" % l, (R, 2), torch.float32)
-      ops.ln_fwd_bf16(proj, x, self._view(flat, p + "norm1.weight"), self._view(flat, p + "norm1.bias"), h, z1, st1, R, d)
+      ops.ln_fwd_f16(proj, x, self._view(flat, p + "norm1.weight"), self._view(flat, p + "norm1.bias"), h, z1, st1, R, d)
       f1 = self.buf("f1_%d" % l, (R, 256))
       self._lin_fwd(flat, p + "linear1.weight", h, R, d, f1, RM.dense(256), True)
       f2 = self.buf("f2", (R, d))
       self._lin_fwd(flat, p + "linear2.weight", f1, R, 256, f2, RM.dense(d), False)
       y = self.buf("y%d" % l, (R, d))
       z2 = self.buf("z2_%d" % l, (R, d), torch.float32); st2 = self.buf("st2_%d" % l, (R, 2), torch.float32)
-      ops.ln_fwd_bf16(f2, h, self._view(flat, p + "norm2.weight"), self._view(flat, p + "norm2.bias"), y, z2, st2, R, d)
+      ops.ln_fwd_f16(f2, h, self._view(flat, p + "norm2.weight"), self._view(flat, p + "norm2.bias"), y, z2, st2, R, d)
       self._layers.append(dict(p=p, nh=nh, x=x, qkv=qkv, o=o, pr=pr, h=h, z1=z1, st1=st1, f1=f1, z2=z2, st2=st2))
       x = y
     pooled = self.buf("pooled", (B, 2 * d))
-    ops.pool_fwd_bf16(x, pooled, B, T, d, 0)
+    ops.pool_fwd_f16(x, pooled, B, T, d, 0)
     h1 = self.buf("h1", (B, 256)); h2 = self.buf("h2", (B, 256))
     self._lin_fwd(flat, self.k_head[0], pooled, B, 2 * d, h1, RM.dense(256), True)
     self._lin_fwd(flat, self.k_head[1], h1, B, 256, h2, RM.dense(256), True)
@@ -242,37 +244,41 @@ class LocoPlanTC:
     R = B * T
     A = self.out_dim
     ws = self._ws
+    # static loss scale (fp16 gradients): d_out ~ 1/B, so scale ~ 4B keeps them O(1e2); every fp32
+    # result (dW, db, dgamma, dbeta) is multiplied by 1/scale where it is produced
+    scale = float(min(4096, max(64, 1 << int(np.floor(np.log2(4 * B))))))
+    self._inv_scale = inv = 1.0 / scale
     g16 = self.buf("dout16", (B, 16))
-    ops.gather_rows_bf16(d_out, True, None, g16, B, A, A, 16)
+    ops.gather_rows_f16(d_out, True, None, g16, B, A, A, 16, scale=scale)
     h1, h2, pooled = ws[("h1", B, 256)], ws[("h2", B, 256)], ws[("pooled", B, 2 * d)]
     dh2 = self.buf("dh2", (B, 256)); dh1 = self.buf("dh1", (B, 256)); dpool = self.buf("dpool", (B, 2 * d))
     self._lin_bwd(gflat, self.k_head[2], h2, 256, g16, 16, B, dh2, RM.dense(256), mask=h2)
     self._lin_bwd(gflat, self.k_head[1], h1, 256, dh2, 256, B, dh1, RM.dense(256), mask=h1)
     self._lin_bwd(gflat, self.k_head[0], pooled, 2 * d, dh1, 256, B, dpool, RM.dense(2 * d))
     dx = self.buf("dxa", (R, d)); other = self.buf("dxb", (R, d))
-    ops.pool_bwd_bf16(dpool, dx, B, T, d, 0)
+    ops.pool_bwd_f16(dpool, dx, B, T, d, 0)
     for Ly in reversed(self._layers):
       p = Ly["p"]
       dz2 = self.buf("dz2", (R, d))
-      ops.ln_bwd_bf16(dx, Ly["z2"], Ly["st2"], self._view(flat, p + "norm2.weight"), dz2,
-                      self._view(gflat, p + "norm2.weight"), self._view(gflat, p + "norm2.bias"), R, d)
+      ops.ln_bwd_f16(dx, Ly["z2"], Ly["st2"], self._view(flat, p + "norm2.weight"), dz2,
+                      self._view(gflat, p + "norm2.weight"), self._view(gflat, p + "norm2.bias"), R, d, out_scale=inv)
       df1 = self.buf("df1", (R, 256))
       self._lin_bwd(gflat, p + "linear2.weight", Ly["f1"], 256, dz2, d, R, df1, RM.dense(256), mask=Ly["f1"])
       self._lin_bwd(gflat, p + "linear1.weight", Ly["h"], d, df1, 256, R, dz2, RM.dense(d), accum=True)   # dh
       dz1 = other
-      ops.ln_bwd_bf16(dz2, Ly["z1"], Ly["st1"], self._view(flat, p + "norm1.weight"), dz1,
-                      self._view(gflat, p + "norm1.weight"), self._view(gflat, p + "norm1.bias"), R, d)
+      ops.ln_bwd_f16(dz2, Ly["z1"], Ly["st1"], self._view(flat, p + "norm1.weight"), dz1,
+                      self._view(gflat, p + "norm1.weight"), self._view(gflat, p + "norm1.bias"), R, d, out_scale=inv)
       do = self.buf("do", (R, d))
       self._lin_bwd(gflat, p + "self_attn.out_proj.weight", Ly["o"], d, dz1, d, R, do, RM.dense(d))
       dqkv = self.buf("dqkv", (R, 3 * d))
-      ops.attn_bwd_bf16(Ly["qkv"], Ly["pr"], do, dqkv, B, T, d, Ly["nh"])
+      ops.attn_bwd_f16(Ly["qkv"], Ly["pr"], do, dqkv, B, T, d, Ly["nh"])
       self._lin_bwd(gflat, p + "self_attn.in_proj_weight", Ly["x"], d, dqkv, 3 * d, R, dz1, RM.dense(d), accum=True)
       dx, other = dz1, dx
     tok = ws[("tok0", B, T, d)]
     # proprio token -> state MLP
     ds = self.buf("ds", (B, d))
     smap = RM.slots(1, T, d, 0)
-    ops.relu_bwd_bf16(dx, smap, tok, smap, ds, RM.dense(d), B, d)
+    ops.relu_bwd_f16(dx, smap, tok, smap, ds, RM.dense(d), B, d)
     s1, s2 = ws[("s1", B, 256)], ws[("s2", B, 256)]
     ds2 = self.buf("ds2", (B, 256)); ds1 = self.buf("ds1", (B, 256))
     self._lin_bwd(gflat, "encoder.state_projector.projection.0.weight", s2, 256, ds, d, B, ds2, RM.dense(256), mask=s2)
@@ -283,8 +289,8 @@ class LocoPlanTC:
     up = "encoder.depth_up_conv.weight"
     strides = (d, T * d, T * d)
     ops.tc_wgrad(a3, (B, 1, 16, 64), dx, d, (B, 1, 16), (16, 1, 8), [(0, 0)], 64, self.W.fwd[up].dev_table, gflat,
-                 dy_strides=strides, dy_off=d)
-    ops.colsum_bf16(dx, RM.slots(16, T, d, 1), B * 16, 64, self._view(gflat, "encoder.depth_up_conv.bias"))
+                 dy_strides=strides, dy_off=d, out_scale=inv)
+    ops.colsum_f16(dx, RM.slots(16, T, d, 1), B * 16, 64, self._view(gflat, "encoder.depth_up_conv.bias"), out_scale=inv)
     da3 = self.buf("da3", (B, 16, 64))
     pd = self.W.dgr[up]
     ops.tc_gemm(dx, (B, 1, 16, 64), (B, 1, 16), (16, 1, 8), [(0, 0)], 1, pd.w, pd.rows, 64, None, da3,
@@ -292,15 +298,15 @@ class LocoPlanTC:
     # conv3
     pre = "encoder.depth_visual_base.layers."
     a2, a1c = ws[("a2", B, 6, 6, 64)], ws[("a1c", B, 8, 8, 128)]
-    ops.tc_wgrad(a2, (B, 6, 6, 64), da3, 64, (B, 4, 4), (4, 4, 4), self.taps3, 64, self.W.fwd[pre + "4.weight"].dev_table, gflat)
-    ops.colsum_bf16(da3, RM.dense(64), B * 16, 64, self._view(gflat, pre + "4.bias"))
+    ops.tc_wgrad(a2, (B, 6, 6, 64), da3, 64, (B, 4, 4), (4, 4, 4), self.taps3, 64, self.W.fwd[pre + "4.weight"].dev_table, gflat, out_scale=inv)
+    ops.colsum_f16(da3, RM.dense(64), B * 16, 64, self._view(gflat, pre + "4.bias"), out_scale=inv)
     da2 = self.buf("da2", (B, 6, 6, 64))
     pd = self.W.dgr[pre + "4.weight"]
     ops.tc_gemm(da3, (B, 4, 4, 64), (B, 6, 6), (6, 6, 3), [(-kw, -kh) for kw, kh in self.taps3], 1, pd.w, pd.rows, 64,
                 None, da2, RM(36, 36 * 64, 64, 0), mask=a2)
     # conv2
-    ops.tc_wgrad(a1c, (B, 8, 8, 128), da2, 64, (B, 6, 6), (6, 6, 3), self.taps2, 64, self.W.fwd[pre + "2.weight"].dev_table, gflat)
-    ops.colsum_bf16(da2, RM.dense(64), B * 36, 64, self._view(gflat, pre + "2.bias"))
+    ops.tc_wgrad(a1c, (B, 8, 8, 128), da2, 64, (B, 6, 6), (6, 6, 3), self.taps2, 64, self.W.fwd[pre + "2.weight"].dev_table, gflat, out_scale=inv)
+    ops.colsum_f16(da2, RM.dense(64), B * 36, 64, self._view(gflat, pre + "2.bias"), out_scale=inv)
     da1c = self.buf("da1c", (B, 8, 8, 128))
     pd = self.W.dgr[pre + "2.weight"]
     ops.tc_gemm(da2, (B, 6, 6, 64), (B, 8, 8), (8, 8, 2), [(-dx_, -dy_) for dx_, dy_ in self.taps2], 1, pd.w, pd.rows, 128,
@@ -308,5 +314,5 @@ class LocoPlanTC:
     # conv1: per sub-position (py,px) of a cell, X is the stride-2 sub-grid of the s2d image
     subs = [(px, py, (py * 2 + px) * 32) for py in range(2) for px in range(2)]
     ops.tc_wgrad(self._imgs, (self._imgs.shape[0], 16, 16, 64), da1c, 128, (B, 8, 8), (8, 8, 1), self.taps2, 32,
-                 self.W.fwd[pre + "0.weight"].dev_table, gflat, x_idx=self._idx, x_estride=2, subs=subs)
-    ops.colsum_bf16(da1c, RM.dense(128), B * 64, 32, self._view(gflat, pre + "0.bias"), fold=4)
+                 self.W.fwd[pre + "0.weight"].dev_table, gflat, x_idx=self._idx, x_estride=2, subs=subs, out_scale=inv)
+    ops.colsum_f16(da1c, RM.dense(128), B * 64, 32, self._view(gflat, pre + "0.bias"), fold=4, out_scale=inv)
