@@ -226,12 +226,19 @@ def test_tc_tier_update_matches_oracle(B):
   assert abs(info["grad_norm/vf"] - ref["grad_norm/vf"]) <= 3e-2 * ref["grad_norm/vf"]
   assert abs(info["grad_norm/pf"] - ref["grad_norm/pf"]) <= 5e-2 * ref["grad_norm/pf"]
   # gradients, tensor by tensor (norm-wise): fp16 activations/gradients, fp32 accumulation
-  worst = 0.0
-  for k, gr in orc._last["vgrads"].items():
-    e = nrm_err(eng.G_vf[k], gr)
-    worst = max(worst, e)
-    assert e < 6e-2, ("vf", k, e)
-  print("worst vf grad norm-err %.3e" % worst)
+  # the oracle keeps the gradients AFTER clip_grad_norm_ (scaled in place): apply the same factor
+  vc = min(1.0, 0.5 / (ref["grad_norm/vf"] + 1e-6)); pc = min(1.0, 0.5 / (ref["grad_norm/pf"] + 1e-6))
+  errs = {("vf", k): nrm_err(eng.G_vf[k] * vc, gr) for k, gr in orc._last["vgrads"].items()}
+  errs.update({("pf", k): nrm_err(eng.G_pf[k] * pc, gr) for k, gr in orc._last["pgrads"].items()})
+  for k, e in sorted(errs.items(), key=lambda kv: -kv[1])[:12]:
+    print("grad norm-err %-70s %.3e" % (k, e))
+  print("worst vf grad err %.3e, worst pf grad err %.3e" % (
+    max(e for k, e in errs.items() if k[0] == "vf"), max(e for k, e in errs.items() if k[0] == "pf")))
+  # critic: direct check of every backward kernel of the tier.  actor: its loss gradient goes
+  # through ratio = exp(lp - lp'), which amplifies the 2e-3 deviation of the action means by
+  # (a-mu)/sigma^2 ~ 64x (SURVEY §7 hard part 3) -> a UNIFORM few-percent deviation on all tensors
+  bad = {k: e for k, e in errs.items() if not e < (6e-2 if k[0] == "vf" else 0.15)}
+  assert not bad, bad
 
 
 def test_tc_tier_graph_replay_is_bit_identical():
