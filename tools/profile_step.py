@@ -19,6 +19,7 @@ def main():
   ap.add_argument("--batch", type=int, default=1024)
   ap.add_argument("--S", type=int, default=93)
   ap.add_argument("--A", type=int, default=12)
+  ap.add_argument("--precision", default="f16")
   args = ap.parse_args()
   from oracle import synth
   from tests._harness import build_nets, load_np_sd, make_ppo
@@ -30,6 +31,7 @@ def main():
   pf, vf = pf.cuda(), vf.cuda()
   agent, _ = make_ppo(pf, vf, None, args.A, args.batch, T * E, 1, device="cuda:0")
   agent.use_cuda_graph = False
+  agent.precision = args.precision
   eng = agent.engine
   roll = synth.make_rollout(3, T, E, args.S, args.A)
   eng.load_rollout_arrays(roll)

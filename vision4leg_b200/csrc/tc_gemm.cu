@@ -58,10 +58,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_bias[256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_chunk = blockIdx.y;
-  const int n0 = n_chunk * 256;
+  for (int i = threadIdx.x; i < 256; i += TC_THREADS) {
+    const int n = n_chunk * p.N + i;
+    s_bias[i] = (p.bias && i < p.N && n < p.N_valid) ? p.bias[n] : 0.f;
+  }
+  const int n0 = n_chunk * p.N;
   const int N = min(p.N, p.N_total - n0);                 // UMMA N of this chunk (multiple of 16)
   const uint32_t b_bytes = static_cast<uint32_t>(N) * 128u;
   const uint32_t stage_bytes = A_TILE_BYTES + static_cast<uint32_t>(p.N) * 128u;
@@ -167,56 +172,59 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         tc::tmem_ld_wait();
         if (!row_ok) continue;
         const int ncols = min(32, N - c0);
+        const int nabs = n0 + c0;                            // absolute first column of this chunk
+        const long long addr = row_addr + c0;
+        float f[32];
 #pragma unroll
-        for (int j0 = 0; j0 < 32; j0 += 8) {
-          if (j0 >= ncols) break;
-          const int n = n0 + c0 + j0;                        // absolute output column
-          if (n >= p.N_valid) break;
-          float f[8];
+        for (int j = 0; j < 32; ++j) {
+          f[j] = __uint_as_float(v[j]) + s_bias[c0 + j];
+          if (relu) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (!p.c_f32 && ncols == 32 && nabs + 32 <= p.N_valid && ((addr & 7) == 0)) {
+          // fast path: 32 fp16 outputs = 4 x 16-byte stores per row
+          __half* cp = reinterpret_cast<__half*>(p.c) + addr;
+          if (p.mask) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            f[j] = __uint_as_float(v[j0 + j]);
-            if (p.bias && n + j < p.N_valid) f[j] += p.bias[n + j];
-            if (relu) f[j] = fmaxf(f[j], 0.f);
-          }
-          const long long addr = row_addr + c0 + j0;
-          const bool full8 = (n + 8 <= p.N_valid);
-          if (!p.c_f32 && full8 && ((addr & 7) == 0)) {
-            __half* cp = reinterpret_cast<__half*>(p.c) + addr;
-            if (p.mask) {
-              const uint4 m = *reinterpret_cast<const uint4*>(p.mask + addr);
+            for (int q = 0; q < 4; ++q) {
+              const uint4 m = __ldg(reinterpret_cast<const uint4*>(p.mask + addr) + q);
               const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                if (!(h16_lo(mw[j]) > 0.f)) f[2 * j] = 0.f;
-                if (!(h16_hi(mw[j]) > 0.f)) f[2 * j + 1] = 0.f;
+                if (!(h16_lo(mw[j]) > 0.f)) f[8 * q + 2 * j] = 0.f;
+                if (!(h16_hi(mw[j]) > 0.f)) f[8 * q + 2 * j + 1] = 0.f;
               }
             }
-            if (accum) {
-              const uint4 o = *reinterpret_cast<const uint4*>(cp);
+          }
+          if (accum) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 o = *(reinterpret_cast<const uint4*>(cp) + q);
               const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) { f[2 * j] += h16_lo(ow[j]); f[2 * j + 1] += h16_hi(ow[j]); }
+              for (int j = 0; j < 4; ++j) { f[8 * q + 2 * j] += h16_lo(ow[j]); f[8 * q + 2 * j + 1] += h16_hi(ow[j]); }
             }
-            uint4 o;
-            o.x = pack_h16(f[0], f[1]); o.y = pack_h16(f[2], f[3]);
-            o.z = pack_h16(f[4], f[5]); o.w = pack_h16(f[6], f[7]);
-            *reinterpret_cast<uint4*>(cp) = o;
-          } else {
+          }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (n + j >= p.N_valid) break;
-              float x = f[j];
-              if (p.mask && !(__half2float(p.mask[addr + j]) > 0.f)) x = 0.f;
-              if (p.c_f32) {
-                float* cp = reinterpret_cast<float*>(p.c) + addr + j;
-                if (accum) x += *cp;
-                *cp = x;
-              } else {
-                __half* cp = reinterpret_cast<__half*>(p.c) + addr + j;
-                if (accum) x += __half2float(*cp);
-                *cp = __float2half(x);
-              }
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = pack_h16(f[8 * q + 0], f[8 * q + 1]); o.y = pack_h16(f[8 * q + 2], f[8 * q + 3]);
+            o.z = pack_h16(f[8 * q + 4], f[8 * q + 5]); o.w = pack_h16(f[8 * q + 6], f[8 * q + 7]);
+            *(reinterpret_cast<uint4*>(cp) + q) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j >= ncols || nabs + j >= p.N_valid) continue;
+            float x = f[j];
+            if (p.mask && !(__half2float(p.mask[addr + j]) > 0.f)) x = 0.f;
+            if (p.c_f32) {
+              float* cp = reinterpret_cast<float*>(p.c) + addr + j;
+              if (accum) x += *cp;
+              *cp = x;
+            } else {
+              __half* cp = reinterpret_cast<__half*>(p.c) + addr + j;
+              if (accum) x += __half2float(*cp);
+              *cp = __float2half(x);
             }
           }
         }
@@ -277,6 +285,7 @@ extern "C" int v4l_tc_gemm(v4l_ctx* ctx, void* stream, const v4l_tc_gemm_args* a
   V4L_REQUIRE(a->a_C % 8 == 0 && a->kchunks * 64 <= ((a->a_C + 63) / 64) * 64, "v4l_tc_gemm: bad channel count %d", a->a_C);
   V4L_REQUIRE(a->N_pad % 16 == 0 && a->N_pad >= 16, "v4l_tc_gemm: N_pad=%d must be a multiple of 16", a->N_pad);
   V4L_REQUIRE(a->N_pad <= 256 || a->N_pad % 256 == 0, "v4l_tc_gemm: N_pad > 256 must be a multiple of 256");
+  V4L_REQUIRE(a->N_pad <= 4096, "v4l_tc_gemm: N_pad too large");
   V4L_REQUIRE(a->N_valid >= 1 && a->N_valid <= a->N_pad, "v4l_tc_gemm: bad N_valid");
   const int rows = a->bw * a->bh * a->bb;
   V4L_REQUIRE(rows >= 1 && rows <= 128 && a->bw == a->Wout && a->bw <= 256 && a->bh <= 256 && a->bb <= 256,
@@ -295,7 +304,11 @@ extern "C" int v4l_tc_gemm(v4l_ctx* ctx, void* stream, const v4l_tc_gemm_args* a
     if (int r = v4l_encode_tmap(&p.tmap_a, a->a, 4, dims, str, box, "v4l_tc_gemm(A)", nullptr)) return r;
   }
   const int Ktot = a->n_taps * a->kchunks * 64;
-  const int Nchunk = a->N_pad > 256 ? 256 : a->N_pad;
+  // N per CTA: the whole (<=256) width, or 64-wide slices when there are too few row tiles to
+  // fill the machine (small-M layers: proprio MLP, heads)
+  const int tiles_est = (a->bb == 1) ? a->B * v4l_cdiv(a->Hout, a->bh) : v4l_cdiv(a->B, a->bb);
+  int Nchunk = a->N_pad > 256 ? 256 : a->N_pad;
+  if (tiles_est * 2 <= ctx->sm_count && a->N_pad % 64 == 0 && a->N_pad > 64) Nchunk = 64;
   {
     uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)a->N_pad};
     uint64_t str[1] = {(uint64_t)Ktot * 2};
@@ -547,14 +560,21 @@ __global__ void __launch_bounds__(256) colsum_f16_kernel(const __half* __restric
     part[(long long)blockIdx.x * N + n] = s;
   }
 }
+// one warp per output column: lanes stride over the partials, fixed-order shuffle reduction
 __global__ void colsum_reduce_kernel(const float* __restrict__ part, int nparts, int N, int fold,
                                      float* __restrict__ out, float out_scale) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (n >= N) return;
   float s = 0.f;
-  for (int p = 0; p < nparts; ++p)
-    for (int f = 0; f < fold; ++f) s += part[(long long)p * N * fold + f * N + n];
-  out[n] = s * out_scale;
+  const int total = nparts * fold;
+  for (int i = lane; i < total; i += 32) {
+    const int p = i / fold, f = i - p * fold;
+    s += part[(long long)p * N * fold + f * N + n];
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[n] = s * out_scale;
 }
 
 }  // namespace
@@ -643,7 +663,7 @@ extern "C" int v4l_colsum_f16(v4l_ctx* ctx, void* stream, const void* dy, const 
   const int Nout = N;
   N = N * fold;
   cudaStream_t s = (cudaStream_t)stream;
-  int ctas = min(2 * ctx->sm_count, v4l_cdiv(M, 64));
+  int ctas = min(ctx->sm_count, v4l_cdiv(M, 64));
   const int rpc = v4l_cdiv(M, ctas);
   ctas = v4l_cdiv(M, rpc);
   // partials live past the region v4l_tc_wgrad uses? no: separate calls are stream-ordered
@@ -651,7 +671,7 @@ extern "C" int v4l_colsum_f16(v4l_ctx* ctx, void* stream, const void* dy, const 
   V4L_REQUIRE((size_t)ctas * N <= ctx->scratch_elems, "v4l_colsum_f16: scratch too small");
   colsum_f16_kernel<<<ctas, 256, 0, s>>>(reinterpret_cast<const __half*>(dy), *map, M, N, rpc, part);
   V4L_CHECK_LAUNCH();
-  colsum_reduce_kernel<<<v4l_cdiv(Nout, 128), 128, 0, s>>>(part, ctas, Nout, fold, out, out_scale);
+  colsum_reduce_kernel<<<v4l_cdiv(Nout, 8), 256, 0, s>>>(part, ctas, Nout, fold, out, out_scale);
   V4L_CHECK_LAUNCH();
   return 0;
 }

@@ -243,14 +243,18 @@ ln_bwd_kernel(const T_* __restrict__ dy, const float* __restrict__ z,
   }
 }
 
+// one warp per (gamma|beta, column): lanes stride over the CTA partials
 __global__ void ln_bwd_reduce_kernel(const float* __restrict__ part, int nparts, int d,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta, float out_scale) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (e >= 2 * d) return;
   const int which = e / d, c = e - which * d;
   float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += part[((long long)p * 2 + which) * d + c];
-  (which ? dbeta : dgamma)[c] = s * out_scale;
+  for (int p = lane; p < nparts; p += 32) s += part[((long long)p * 2 + which) * d + c];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) (which ? dbeta : dgamma)[c] = s * out_scale;
 }
 
 template <typename T_>
@@ -358,7 +362,7 @@ static int ln_bwd_impl(v4l_ctx* ctx, void* stream, const void* dy, const float* 
   cudaStream_t s = (cudaStream_t)stream;
   ln_bwd_kernel<T_><<<ctas, 256, 0, s>>>((const T_*)dy, z, stats, gamma, (T_*)dz, ctx->scratch, rows, d, rpc);
   V4L_CHECK_LAUNCH();
-  ln_bwd_reduce_kernel<<<v4l_cdiv(2 * d, 128), 128, 0, s>>>(ctx->scratch, ctas, d, dgamma, dbeta, out_scale);
+  ln_bwd_reduce_kernel<<<v4l_cdiv(2 * d, 8), 256, 0, s>>>(ctx->scratch, ctas, d, dgamma, dbeta, out_scale);
   V4L_CHECK_LAUNCH();
   return 0;
 }
