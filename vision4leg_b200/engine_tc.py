@@ -25,6 +25,7 @@ from .engine import RM, RELU, ACCUM
 from ._lib import V4LError
 
 F16 = torch.float16
+LOSS_SCALE_OVERRIDE = None        # tests/experiments: force the static loss scale
 
 
 def _ceil(a, b):
@@ -247,6 +248,8 @@ class LocoPlanTC:
     # static loss scale (fp16 gradients): d_out ~ 1/B, so scale ~ 4B keeps them O(1e2); every fp32
     # result (dW, db, dgamma, dbeta) is multiplied by 1/scale where it is produced
     scale = float(min(4096, max(64, 1 << int(np.floor(np.log2(4 * B))))))
+    if LOSS_SCALE_OVERRIDE:
+      scale = float(LOSS_SCALE_OVERRIDE)
     self._inv_scale = inv = 1.0 / scale
     g16 = self.buf("dout16", (B, 16))
     ops.gather_rows_f16(d_out, True, None, g16, B, A, A, 16, scale=scale)
