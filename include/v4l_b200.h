@@ -226,8 +226,13 @@ typedef struct {
   const int32_t* index;
   float* dw;
   float out_scale;               /* fp32 results are multiplied by this (1/loss-scale); 0 = 1    */
+  float* dbias;                  /* optional: dbias[n] = sum_rows dY[row, n] from the SAME launch
+                                    (an extra K slice whose X operand is the constant 1)         */
+  int32_t defer;                 /* 1: leave the split partials in the context and sum them in
+                                    the next v4l_tc_wgrad_flush (one launch for a whole backward) */
 } v4l_tc_wgrad_args;
 int v4l_tc_wgrad(v4l_ctx* ctx, void* stream, const v4l_tc_wgrad_args* args);
+int v4l_tc_wgrad_flush(v4l_ctx* ctx, void* stream);
 /* out[n] = sum_m sum_f dy(m, f*N + n) for a row-mapped f16 [M, N*fold <= 256] view (bias
  * gradients; fold > 1 sums the sub-positions of a space-to-depth cell)                         */
 int v4l_colsum_f16(v4l_ctx* ctx, void* stream, const void* dy, const v4l_rowmap* map, int M, int N,

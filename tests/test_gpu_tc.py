@@ -145,6 +145,24 @@ def test_tc_wgrad_linear(M, N, K):
   assert rel(db, dy.float()[:, :N_valid].sum(0)) < 1e-4
 
 
+def test_tc_wgrad_bias_and_deferred_reduce():
+  """dbias from the same launch (extra K slice with a constant-1 operand) and several layers
+  reduced by ONE flush."""
+  engine, ops = _ops()
+  torch.manual_seed(4)
+  jobs = []
+  for M, N, K in [(1000, 64, 256), (2000, 192, 64), (333, 16, 128)]:
+    x = bf(torch.randn(M, K, device=DEV)); dy = bf(torch.randn(M, N, device=DEV))
+    dw = torch.full((N, K), float("nan"), device=DEV); db = torch.full((N,), float("nan"), device=DEV)
+    ops.tc_wgrad(x, (M, 1, 1, K), dy, N, (M, 1, 1), (1, 1, 128), [(0, 0)], N, None, dw, out_scale=0.5, dbias=db,
+                 defer=True)
+    jobs.append((x, dy, dw, db))
+  ops.tc_wgrad_flush()
+  for x, dy, dw, db in jobs:
+    assert rel(dw, 0.5 * dy.float().t() @ x.float()) < 1e-4
+    assert rel(db, 0.5 * dy.float().sum(0)) < 1e-4
+
+
 def test_tc_wgrad_conv3_and_conv1():
   engine, ops = _ops()
   torch.manual_seed(11)

@@ -72,7 +72,8 @@ class TcWgradArgs(C.Structure):
               ("B", C.c_int32), ("Hout", C.c_int32), ("Wout", C.c_int32),
               ("bw", C.c_int32), ("bh", C.c_int32), ("bb", C.c_int32),
               ("n_taps", C.c_int32), ("tap_dw", C.c_int32 * 16), ("tap_dh", C.c_int32 * 16),
-              ("N_valid", C.c_int32), ("index", C.c_void_p), ("dw", C.c_void_p), ("out_scale", C.c_float)]
+              ("N_valid", C.c_int32), ("index", C.c_void_p), ("dw", C.c_void_p), ("out_scale", C.c_float),
+              ("dbias", C.c_void_p), ("defer", C.c_int32)]
 
 
 _vp, _i, _i64, _f, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
@@ -111,6 +112,7 @@ SIGNATURES = {
   "v4l_clip_adam": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i],
   "v4l_tc_gemm": [_vp, _vp, C.POINTER(TcGemmArgs)],
   "v4l_tc_wgrad": [_vp, _vp, C.POINTER(TcWgradArgs)],
+  "v4l_tc_wgrad_flush": [_vp, _vp],
   "v4l_colsum_f16": [_vp, _vp, _vp, C.POINTER(RowMap), _i, _i, _i, _f, _vp],
   "v4l_ingest_img": [_vp, _vp, _vp, _vp, _i64],
   "v4l_gather_rows_f16": [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i64, _i, _f],

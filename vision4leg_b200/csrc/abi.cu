@@ -31,13 +31,18 @@ extern "C" int v4l_ctx_create(v4l_ctx** out, int device, size_t scratch_bytes) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   if (scratch_bytes == 0) scratch_bytes = (size_t)256 << 20;
-  c->scratch_elems = scratch_bytes / sizeof(float);
+  const size_t total_elems = scratch_bytes / sizeof(float);
+  c->scratch_elems = total_elems / 2;
+  c->defer_elems = total_elems - c->scratch_elems;
+  c->defer_cursor = 0;
+  c->n_jobs = 0;
   cudaError_t e = cudaMalloc(&c->scratch, scratch_bytes);
   if (e != cudaSuccess) {
     v4l_set_error("v4l_ctx_create: cudaMalloc(%zu) -> %s", scratch_bytes, cudaGetErrorString(e));
     delete c;
     return -2;
   }
+  c->defer_base = c->scratch + c->scratch_elems;
   *out = c;
   return 0;
 }

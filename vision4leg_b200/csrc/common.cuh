@@ -6,11 +6,28 @@
 
 #include "v4l_b200.h"
 
+// one deferred weight-gradient reduction (see tc_gemm.cu: v4l_tc_wgrad with defer = 1)
+struct v4l_reduce_job {
+  const float* partial;      // [splits][kin_tiles + has_bias][128][Nmma]
+  const int32_t* index;      // packing table or NULL
+  float* dw;
+  float* dbias;              // or NULL
+  int splits, kin_tiles, has_bias, Nmma, N_valid, Kp;
+  float scale;
+  int pad_;
+};
+constexpr int V4L_MAX_JOBS = 48;
+
 struct v4l_ctx {
   int device;
   int sm_count;
   float* scratch;        // context-owned scratch (split partials)
-  size_t scratch_elems;
+  size_t scratch_elems;  // elements usable by immediate users = lower half; the upper half holds
+                         // the partials of deferred weight-gradient reductions until the flush
+  float* defer_base;
+  size_t defer_elems, defer_cursor;
+  v4l_reduce_job jobs[V4L_MAX_JOBS];
+  int n_jobs;
 };
 
 void v4l_set_error(const char* fmt, ...);

@@ -394,6 +394,7 @@ struct TcWgradParams {
   int n_sub;                   // sub-iterations per tile (sub-positions of a space-to-depth cell)
   int sub_dw[4], sub_dh[4], sub_dyc[4];
   const int32_t* x_idx;
+  int kin_tiles;               // K slices with real X data; blockIdx.y == kin_tiles is the bias CTA
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ TcWgradParams p) {
@@ -413,10 +414,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
 
   // zero the ring once: rows beyond the TMA box stay zero for the whole kernel, so the padded
   // K-steps (box rows not a multiple of 16) contribute exactly 0
+  const bool bias_cta = (kt == p.kin_tiles);   // extra K slice whose "X" is the constant 1: D = column sums of dY
   {
     uint4* z = reinterpret_cast<uint4*>(smem);
     const int n16 = p.stages * stage_bytes / 16;
     for (int i = threadIdx.x; i < n16; i += WG_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    if (bias_cta) {
+      __syncthreads();
+      const uint32_t one2 = 0x3C003C00u;       // two fp16 1.0
+      for (int st = 0; st < p.stages; ++st) {
+        uint4* a = reinterpret_cast<uint4*>(smem + st * stage_bytes);
+        for (int i = threadIdx.x; i < 2 * ATOM_BYTES / 16; i += WG_THREADS) a[i] = make_uint4(one2, one2, one2, one2);
+      }
+    }
   }
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&p.tmap_x);
@@ -451,8 +461,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
         for (int sub = 0; sub < p.n_sub; ++sub) {
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* s = smem + stage * stage_bytes;
-          tc::mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(2 + p.n_atoms) * box_rows * 128u);
-          for (int j = 0; j < 2; ++j)
+          tc::mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>((bias_cta ? 0 : 2) + p.n_atoms) * box_rows * 128u);
+          for (int j = 0; j < 2 && !bias_cta; ++j)
             tc::tma_load_4d(s + j * ATOM_BYTES, &p.tmap_x, &full_bar[stage], a_c0[j],
                             p.sub_dw[sub] + p.tap_dw[a_tap[j]],
                             h0 * p.x_estride + p.sub_dh[sub] + p.tap_dh[a_tap[j]], xb0);
@@ -514,21 +524,33 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
   }
 }
 
-// dw[index[n*Kp + kp]] = sum_split partial[split][kp/128][kp%128][n]
-__global__ void tc_wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int kin_tiles, int Nmma,
-                                       int N_valid, int Kp, const int32_t* __restrict__ index,
-                                       float* __restrict__ dw, float out_scale) {
-  const long long total = (long long)N_valid * Kp;
-  const long long split_stride = (long long)kin_tiles * 128 * Nmma;
+// All pending reductions in ONE launch (blockIdx.y = job): dw[index[n*Kp + kp]] = scale * sum_split
+// partial[split][kp/128][kp%128][n]; dbias[n] = scale * sum_split partial[split][kin_tiles][0][n]
+struct ReduceJobs { v4l_reduce_job j[V4L_MAX_JOBS]; };
+
+__global__ void tc_wgrad_reduce_kernel(const __grid_constant__ ReduceJobs jobs) {
+  const v4l_reduce_job& J = jobs.j[blockIdx.y];
+  const long long nw = (long long)J.N_valid * J.Kp;
+  const long long total = nw + (J.has_bias ? J.N_valid : 0);
+  const long long split_stride = (long long)(J.kin_tiles + J.has_bias) * 128 * J.Nmma;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
-    const int kp = (int)(e % Kp), n = (int)(e / Kp);        // consecutive threads: consecutive kp
-    const long long dst = index ? (long long)index[(long long)n * Kp + kp] : e;
-    if (dst < 0) continue;
-    const float* src = partial + (long long)kp * Nmma + n;
+    const float* src;
+    float* dst;
+    if (e < nw) {
+      const int kp = (int)(e % J.Kp), n = (int)(e / J.Kp);        // consecutive threads: consecutive kp
+      const long long d = J.index ? (long long)J.index[(long long)n * J.Kp + kp] : e;
+      if (d < 0) continue;
+      dst = J.dw + d;
+      src = J.partial + (long long)kp * J.Nmma + n;
+    } else {
+      const int n = (int)(e - nw);
+      dst = J.dbias + n;
+      src = J.partial + (long long)J.kin_tiles * 128 * J.Nmma + n;
+    }
     float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += src[z * split_stride];
-    dw[dst] = s * out_scale;
+    for (int z = 0; z < J.splits; ++z) s += src[z * split_stride];
+    *dst = s * J.scale;
   }
 }
 
@@ -578,6 +600,8 @@ __global__ void colsum_reduce_kernel(const float* __restrict__ part, int nparts,
 }
 
 }  // namespace
+
+extern "C" int v4l_tc_wgrad_flush(v4l_ctx* ctx, void* stream);
 
 extern "C" int v4l_tc_wgrad(v4l_ctx* ctx, void* stream, const v4l_tc_wgrad_args* a) {
   V4L_REQUIRE(ctx && a && a->x && a->dy && a->dw, "v4l_tc_wgrad: NULL argument");
@@ -633,12 +657,22 @@ extern "C" int v4l_tc_wgrad(v4l_ctx* ctx, void* stream, const v4l_tc_wgrad_args*
   const int kin_tiles = v4l_cdiv(Kp, 128);
   const size_t stage_bytes = (size_t)(2 + p.n_atoms) * ATOM_BYTES;
   p.stages = (int)min((size_t)4, (size_t)(200 * 1024 - 1024) / stage_bytes);
-  int splits = max(1, min(p.num_tiles, ctx->sm_count / kin_tiles));
-  splits = (int)min((size_t)splits, ctx->scratch_elems / ((size_t)kin_tiles * 128 * Nmma));
-  V4L_REQUIRE(splits >= 1, "v4l_tc_wgrad: scratch too small");
+  const int has_bias = a->dbias ? 1 : 0;
+  const int ytiles = kin_tiles + has_bias;
+  p.kin_tiles = kin_tiles;
+  // deferred reductions keep their partials in the upper half of the scratch until the flush
+  if (a->defer && (ctx->n_jobs == V4L_MAX_JOBS ||
+                   ctx->defer_elems - ctx->defer_cursor < (size_t)ytiles * 128 * Nmma)) {
+    if (int r = v4l_tc_wgrad_flush(ctx, stream)) return r;
+  }
+  float* region = a->defer ? ctx->defer_base + ctx->defer_cursor : ctx->scratch;
+  const size_t avail = a->defer ? ctx->defer_elems - ctx->defer_cursor : ctx->scratch_elems;
+  int splits = max(1, min(p.num_tiles, min(32, ctx->sm_count / ytiles)));
+  splits = (int)min((size_t)splits, avail / ((size_t)ytiles * 128 * Nmma));
+  V4L_REQUIRE(splits >= 1, "v4l_tc_wgrad: scratch too small (flush deferred reductions more often)");
   p.tiles_per_split = v4l_cdiv(p.num_tiles, splits);
   splits = v4l_cdiv(p.num_tiles, p.tiles_per_split);
-  p.partial = ctx->scratch;
+  p.partial = region;
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -646,12 +680,35 @@ extern "C" int v4l_tc_wgrad(v4l_ctx* ctx, void* stream, const v4l_tc_wgrad_args*
     attr_set = true;
   }
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
-  tc_wgrad_kernel<<<dim3(splits, kin_tiles), WG_THREADS, smem, s>>>(p);
+  tc_wgrad_kernel<<<dim3(splits, ytiles), WG_THREADS, smem, s>>>(p);
   V4L_CHECK_LAUNCH();
-  const long long total = (long long)a->N_valid * Kp;
-  const int rblocks = (int)min((long long)4 * ctx->sm_count, (total + 255) / 256);
-  tc_wgrad_reduce_kernel<<<rblocks, 256, 0, s>>>(ctx->scratch, splits, kin_tiles, Nmma, a->N_valid, Kp, a->index, a->dw,
-                                                 a->out_scale != 0.f ? a->out_scale : 1.f);
+  v4l_reduce_job job;
+  job.partial = region; job.index = a->index; job.dw = a->dw; job.dbias = a->dbias;
+  job.splits = splits; job.kin_tiles = kin_tiles; job.has_bias = has_bias; job.Nmma = Nmma;
+  job.N_valid = a->N_valid; job.Kp = Kp; job.scale = a->out_scale != 0.f ? a->out_scale : 1.f; job.pad_ = 0;
+  if (a->defer) {
+    ctx->jobs[ctx->n_jobs++] = job;
+    ctx->defer_cursor += (((size_t)splits * ytiles * 128 * Nmma) + 63) / 64 * 64;
+    return 0;
+  }
+  ReduceJobs one;
+  one.j[0] = job;
+  const long long total = (long long)a->N_valid * (Kp + has_bias);
+  const int rblocks = (int)min((long long)2 * ctx->sm_count, (total + 255) / 256);
+  tc_wgrad_reduce_kernel<<<dim3(rblocks, 1), 256, 0, s>>>(one);
+  V4L_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int v4l_tc_wgrad_flush(v4l_ctx* ctx, void* stream) {
+  V4L_REQUIRE(ctx, "v4l_tc_wgrad_flush: NULL ctx");
+  if (ctx->n_jobs == 0) return 0;
+  ReduceJobs all;
+  memset(&all, 0, sizeof(all));
+  for (int i = 0; i < ctx->n_jobs; ++i) all.j[i] = ctx->jobs[i];
+  tc_wgrad_reduce_kernel<<<dim3(16, ctx->n_jobs), 256, 0, (cudaStream_t)stream>>>(all);
+  ctx->n_jobs = 0;
+  ctx->defer_cursor = 0;
   V4L_CHECK_LAUNCH();
   return 0;
 }

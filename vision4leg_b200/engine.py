@@ -135,7 +135,8 @@ class Ops:
     self.launches += 1
 
   def tc_wgrad(self, x, x_shape, dy, dy_C, out_grid, box, taps, N_valid, index, dw, x_idx=None,
-               x_estride=1, subs=None, dy_strides=None, dy_off=0, x_strides=None, out_scale=1.0):
+               x_estride=1, subs=None, dy_strides=None, dy_off=0, x_strides=None, out_scale=1.0,
+               dbias=None, defer=False):
     """subs: [(sub_dw, sub_dh, dy_channel_offset)] sub-iterations per tile (space-to-depth cells)"""
     g = TcWgradArgs()
     g.x = ptr(x)
@@ -157,8 +158,13 @@ class Ops:
       g.tap_dw[i], g.tap_dh[i] = dw_, dh_
     g.N_valid, g.index, g.dw = N_valid, ptr(index), ptr(dw)
     g.out_scale = out_scale
+    g.dbias, g.defer = ptr(dbias), 1 if defer else 0
     check(self.lib.v4l_tc_wgrad(self.h, self.ctx.stream(), C.byref(g)))
-    self.launches += 2
+    self.launches += 1 if defer else 2
+
+  def tc_wgrad_flush(self):
+    check(self.lib.v4l_tc_wgrad_flush(self.h, self.ctx.stream()))
+    self.launches += 1
 
   def colsum_f16(self, dy, dy_map, M, N, out, fold=1, out_scale=1.0):
     m = dy_map.c()

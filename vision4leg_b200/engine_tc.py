@@ -166,8 +166,7 @@ class LocoPlanTC:
     N, K = self.layout[wname][1][0], int(np.prod(self.layout[wname][1][1:]))
     inv = self._inv_scale
     self.ops.tc_wgrad(x, (M, 1, 1, x_cols), dy, dy_cols, (M, 1, 1), (1, 1, 128), [(0, 0)], N, pk.dev_table, gflat,
-                      out_scale=inv)
-    self.ops.colsum_f16(dy, RM.dense(dy_cols), M, N, self._view(gflat, wname[:-6] + "bias"), out_scale=inv)
+                      out_scale=inv, dbias=self._view(gflat, wname[:-6] + "bias"), defer=True)
     if need_dx:
       pd = self.W.dgr[wname]
       self.ops.tc_gemm(dy, (M, 1, 1, dy_cols), (M, 1, 1), (1, 1, 128), [(0, 0)], pd.cols // 64, pd.w, pd.rows, K,
@@ -292,8 +291,8 @@ class LocoPlanTC:
     up = "encoder.depth_up_conv.weight"
     strides = (d, T * d, T * d)
     ops.tc_wgrad(a3, (B, 1, 16, 64), dx, d, (B, 1, 16), (16, 1, 8), [(0, 0)], 64, self.W.fwd[up].dev_table, gflat,
-                 dy_strides=strides, dy_off=d, out_scale=inv)
-    ops.colsum_f16(dx, RM.slots(16, T, d, 1), B * 16, 64, self._view(gflat, "encoder.depth_up_conv.bias"), out_scale=inv)
+                 dy_strides=strides, dy_off=d, out_scale=inv, dbias=self._view(gflat, "encoder.depth_up_conv.bias"),
+                 defer=True)
     da3 = self.buf("da3", (B, 16, 64))
     pd = self.W.dgr[up]
     ops.tc_gemm(dx, (B, 1, 16, 64), (B, 1, 16), (16, 1, 8), [(0, 0)], 1, pd.w, pd.rows, 64, None, da3,
@@ -301,15 +300,15 @@ class LocoPlanTC:
     # conv3
     pre = "encoder.depth_visual_base.layers."
     a2, a1c = ws[("a2", B, 6, 6, 64)], ws[("a1c", B, 8, 8, 128)]
-    ops.tc_wgrad(a2, (B, 6, 6, 64), da3, 64, (B, 4, 4), (4, 4, 4), self.taps3, 64, self.W.fwd[pre + "4.weight"].dev_table, gflat, out_scale=inv)
-    ops.colsum_f16(da3, RM.dense(64), B * 16, 64, self._view(gflat, pre + "4.bias"), out_scale=inv)
+    ops.tc_wgrad(a2, (B, 6, 6, 64), da3, 64, (B, 4, 4), (4, 4, 4), self.taps3, 64, self.W.fwd[pre + "4.weight"].dev_table, gflat, out_scale=inv,
+                 dbias=self._view(gflat, pre + "4.bias"), defer=True)
     da2 = self.buf("da2", (B, 6, 6, 64))
     pd = self.W.dgr[pre + "4.weight"]
     ops.tc_gemm(da3, (B, 4, 4, 64), (B, 6, 6), (6, 6, 3), [(-kw, -kh) for kw, kh in self.taps3], 1, pd.w, pd.rows, 64,
                 None, da2, RM(36, 36 * 64, 64, 0), mask=a2)
     # conv2
-    ops.tc_wgrad(a1c, (B, 8, 8, 128), da2, 64, (B, 6, 6), (6, 6, 3), self.taps2, 64, self.W.fwd[pre + "2.weight"].dev_table, gflat, out_scale=inv)
-    ops.colsum_f16(da2, RM.dense(64), B * 36, 64, self._view(gflat, pre + "2.bias"), out_scale=inv)
+    ops.tc_wgrad(a1c, (B, 8, 8, 128), da2, 64, (B, 6, 6), (6, 6, 3), self.taps2, 64, self.W.fwd[pre + "2.weight"].dev_table, gflat, out_scale=inv,
+                 dbias=self._view(gflat, pre + "2.bias"), defer=True)
     da1c = self.buf("da1c", (B, 8, 8, 128))
     pd = self.W.dgr[pre + "2.weight"]
     ops.tc_gemm(da2, (B, 6, 6, 64), (B, 8, 8), (8, 8, 2), [(-dx_, -dy_) for dx_, dy_ in self.taps2], 1, pd.w, pd.rows, 128,
@@ -317,5 +316,6 @@ class LocoPlanTC:
     # conv1: per sub-position (py,px) of a cell, X is the stride-2 sub-grid of the s2d image
     subs = [(px, py, (py * 2 + px) * 32) for py in range(2) for px in range(2)]
     ops.tc_wgrad(self._imgs, (self._imgs.shape[0], 16, 16, 64), da1c, 128, (B, 8, 8), (8, 8, 1), self.taps2, 32,
-                 self.W.fwd[pre + "0.weight"].dev_table, gflat, x_idx=self._idx, x_estride=2, subs=subs, out_scale=inv)
-    ops.colsum_f16(da1c, RM.dense(128), B * 64, 32, self._view(gflat, pre + "0.bias"), fold=4, out_scale=inv)
+                 self.W.fwd[pre + "0.weight"].dev_table, gflat, x_idx=self._idx, x_estride=2, subs=subs, out_scale=inv,
+                 dbias=self._view(gflat, pre + "0.bias"), defer=True)
+    ops.tc_wgrad_flush()
