@@ -202,6 +202,7 @@ typedef struct {
   void* c;  v4l_rowmap c_map;  int32_t c_f32;
   const void* mask;
   int32_t flags;
+  const void* res;               /* optional fp16 residual added after the mask (addressed like c) */
 } v4l_tc_gemm_args;
 int v4l_tc_gemm(v4l_ctx* ctx, void* stream, const v4l_tc_gemm_args* args);
 /* dw[index[n*Kp + kp]] = sum_rows X_tap[row, kp] * dY[row, n], Kp = n_taps * x_C, through

@@ -58,7 +58,7 @@ class TcGemmArgs(C.Structure):
               ("w", C.c_void_p), ("N_pad", C.c_int32), ("N_valid", C.c_int32),
               ("bias", C.c_void_p),
               ("c", C.c_void_p), ("c_map", RowMap), ("c_f32", C.c_int32),
-              ("mask", C.c_void_p), ("flags", C.c_int32)]
+              ("mask", C.c_void_p), ("flags", C.c_int32), ("res", C.c_void_p)]
 
 
 class TcWgradArgs(C.Structure):

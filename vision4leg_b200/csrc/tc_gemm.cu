@@ -43,6 +43,7 @@ struct TcGemmParams {
   const __half* mask;
   int flags;
   const int32_t* a_idx;
+  const __half* res;              // optional residual added to the result (same addressing as c)
 };
 
 __device__ __forceinline__ float h16_lo(uint32_t u) { return __half2float(__ushort_as_half(static_cast<unsigned short>(u & 0xffffu))); }
@@ -195,6 +196,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
               }
             }
           }
+          if (p.res) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 o = __ldg(reinterpret_cast<const uint4*>(p.res + addr) + q);
+              const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { f[8 * q + 2 * j] += h16_lo(ow[j]); f[8 * q + 2 * j + 1] += h16_hi(ow[j]); }
+            }
+          }
           if (accum) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -217,6 +227,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
             if (j >= ncols || nabs + j >= p.N_valid) continue;
             float x = f[j];
             if (p.mask && !(__half2float(p.mask[addr + j]) > 0.f)) x = 0.f;
+            if (p.res) x += __half2float(p.res[addr + j]);
             if (p.c_f32) {
               float* cp = reinterpret_cast<float*>(p.c) + addr + j;
               if (accum) x += *cp;
@@ -326,6 +337,7 @@ extern "C" int v4l_tc_gemm(v4l_ctx* ctx, void* stream, const v4l_tc_gemm_args* a
   p.mask = reinterpret_cast<const __half*>(a->mask);
   p.flags = a->flags;
   p.a_idx = a->a_idx;
+  p.res = reinterpret_cast<const __half*>(a->res);
   V4L_REQUIRE(!a->a_idx || a->bb == 1, "v4l_tc_gemm: a_idx needs single-item boxes (bb == 1)");
 
   const size_t smem = (size_t)TC_STAGES * (A_TILE_BYTES + (size_t)Nchunk * 128) + 1024;

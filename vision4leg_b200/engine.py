@@ -78,6 +78,20 @@ class Ops:
     self.device = self.ctx.device
     self.launches = 0     # kernel launches issued through this object (bench `gpu_launches`)
 
+  # ---- side stream: independent work (weight gradients, frozen-target forward) leaves the
+  #      critical path; under CUDA-graph capture this becomes a parallel branch of the graph
+  def fork(self):
+    side = getattr(self, "_side", None)
+    if side is None:
+      side = self._side = torch.cuda.Stream(device=self.device)
+    side.wait_stream(torch.cuda.current_stream(self.device))
+    return torch.cuda.stream(side)
+
+  def join(self):
+    side = getattr(self, "_side", None)
+    if side is not None:
+      torch.cuda.current_stream(self.device).wait_stream(side)
+
   # ---- GEMMs
   def gemm(self, a, a_map, koff, b, b_sk, b_sn, bias, c, c_map, M, N, K, flags=0, mask=None,
            mask_map=None, c_koff=None):
@@ -114,7 +128,7 @@ class Ops:
 
   # ---- tensor-core tier
   def tc_gemm(self, a, a_shape, out_grid, box, taps, kchunks, w, N_pad, N_valid, bias, c, c_map,
-              c_f32=False, mask=None, flags=0, a_strides=None, a_idx=None, a_off=0):
+              c_f32=False, mask=None, flags=0, a_strides=None, a_idx=None, a_off=0, res=None):
     """a: fp16 [a_B, a_H, a_W, a_C]; out_grid (B, Hout, Wout); box (bw, bh, bb); taps [(dw, dh)];
     a_strides: element strides (sW, sH, sB) of a non-packed view; a_off: element offset"""
     g = TcGemmArgs()
@@ -130,7 +144,7 @@ class Ops:
       g.tap_dw[i], g.tap_dh[i] = dw, dh
     g.w, g.N_pad, g.N_valid = ptr(w), N_pad, N_valid
     g.bias, g.c, g.c_map, g.c_f32 = ptr(bias), ptr(c), c_map.c(), 1 if c_f32 else 0
-    g.mask, g.flags = ptr(mask), flags
+    g.mask, g.flags, g.res = ptr(mask), flags, ptr(res)
     check(self.lib.v4l_tc_gemm(self.h, self.ctx.stream(), C.byref(g)))
     self.launches += 1
 

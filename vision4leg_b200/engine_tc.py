@@ -159,18 +159,26 @@ class LocoPlanTC:
     self.ops.tc_gemm(x, (M, 1, 1, K), (M, 1, 1), (1, 1, 128), [(0, 0)], pk.cols // 64, pk.w, pk.rows, N, bias,
                      out, out_map, c_f32=c_f32, flags=RELU if relu else 0)
 
-  def _lin_bwd(self, gflat, wname, x, x_cols, dy, dy_cols, M, dx=None, dx_map=None, mask=None, accum=False,
+  def _side(self, fn):
+    """Run `fn` (weight-gradient launches) on the side stream: they only READ activations and
+    gradients that are never overwritten during this backward, so they leave the critical path."""
+    with self.ops.fork():
+      fn()
+
+  def _lin_bwd(self, gflat, wname, x, x_cols, dy, dy_cols, M, dx=None, dx_map=None, mask=None, res=None,
                need_dx=True):
-    """dW, db from (x [M,x_cols], dy [M,dy_cols]); optionally dx = dy @ W (masked / accumulated)."""
+    """dW, db from (x [M,x_cols], dy [M,dy_cols]) on the side stream; optionally
+    dx = (dy @ W) * (mask > 0) + res on the main stream."""
     pk = self.W.fwd[wname]
     N, K = self.layout[wname][1][0], int(np.prod(self.layout[wname][1][1:]))
     inv = self._inv_scale
-    self.ops.tc_wgrad(x, (M, 1, 1, x_cols), dy, dy_cols, (M, 1, 1), (1, 1, 128), [(0, 0)], N, pk.dev_table, gflat,
-                      out_scale=inv, dbias=self._view(gflat, wname[:-6] + "bias"), defer=True)
+    self._side(lambda: self.ops.tc_wgrad(
+      x, (M, 1, 1, x_cols), dy, dy_cols, (M, 1, 1), (1, 1, 128), [(0, 0)], N, pk.dev_table, gflat,
+      out_scale=inv, dbias=self._view(gflat, wname[:-6] + "bias"), defer=True))
     if need_dx:
       pd = self.W.dgr[wname]
       self.ops.tc_gemm(dy, (M, 1, 1, dy_cols), (M, 1, 1), (1, 1, 128), [(0, 0)], pd.cols // 64, pd.w, pd.rows, K,
-                       None, dx, dx_map, mask=mask, flags=ACCUM if accum else 0)
+                       None, dx, dx_map, mask=mask, res=res)
 
   # ---- forward --------------------------------------------------------------------------------
   def forward(self, flat, imgs, idx, st, B, out):
@@ -257,25 +265,30 @@ class LocoPlanTC:
     self._lin_bwd(gflat, self.k_head[2], h2, 256, g16, 16, B, dh2, RM.dense(256), mask=h2)
     self._lin_bwd(gflat, self.k_head[1], h1, 256, dh2, 256, B, dh1, RM.dense(256), mask=h1)
     self._lin_bwd(gflat, self.k_head[0], pooled, 2 * d, dh1, 256, B, dpool, RM.dense(2 * d))
-    dx = self.buf("dxa", (R, d)); other = self.buf("dxb", (R, d))
+    dx = self.buf("dx_top", (R, d))
     ops.pool_bwd_f16(dpool, dx, B, T, d, 0)
-    for Ly in reversed(self._layers):
+    # every gradient tensor below is written once and then only read (no in-place accumulation,
+    # per-layer buffers): the weight-gradient launches on the side stream can lag behind safely
+    for l in reversed(range(len(self._layers))):
+      Ly = self._layers[l]
       p = Ly["p"]
-      dz2 = self.buf("dz2", (R, d))
+      dz2 = self.buf("dz2_%d" % l, (R, d))
       ops.ln_bwd_f16(dx, Ly["z2"], Ly["st2"], self._view(flat, p + "norm2.weight"), dz2,
-                      self._view(gflat, p + "norm2.weight"), self._view(gflat, p + "norm2.bias"), R, d, out_scale=inv)
-      df1 = self.buf("df1", (R, 256))
+                     self._view(gflat, p + "norm2.weight"), self._view(gflat, p + "norm2.bias"), R, d, out_scale=inv)
+      df1 = self.buf("df1_%d" % l, (R, 256))
       self._lin_bwd(gflat, p + "linear2.weight", Ly["f1"], 256, dz2, d, R, df1, RM.dense(256), mask=Ly["f1"])
-      self._lin_bwd(gflat, p + "linear1.weight", Ly["h"], d, df1, 256, R, dz2, RM.dense(d), accum=True)   # dh
-      dz1 = other
-      ops.ln_bwd_f16(dz2, Ly["z1"], Ly["st1"], self._view(flat, p + "norm1.weight"), dz1,
-                      self._view(gflat, p + "norm1.weight"), self._view(gflat, p + "norm1.bias"), R, d, out_scale=inv)
+      dh = self.buf("dh_%d" % l, (R, d))
+      self._lin_bwd(gflat, p + "linear1.weight", Ly["h"], d, df1, 256, R, dh, RM.dense(d), res=dz2)
+      dz1 = self.buf("dz1_%d" % l, (R, d))
+      ops.ln_bwd_f16(dh, Ly["z1"], Ly["st1"], self._view(flat, p + "norm1.weight"), dz1,
+                     self._view(gflat, p + "norm1.weight"), self._view(gflat, p + "norm1.bias"), R, d, out_scale=inv)
       do = self.buf("do", (R, d))
       self._lin_bwd(gflat, p + "self_attn.out_proj.weight", Ly["o"], d, dz1, d, R, do, RM.dense(d))
-      dqkv = self.buf("dqkv", (R, 3 * d))
+      dqkv = self.buf("dqkv_%d" % l, (R, 3 * d))
       ops.attn_bwd_f16(Ly["qkv"], Ly["pr"], do, dqkv, B, T, d, Ly["nh"])
-      self._lin_bwd(gflat, p + "self_attn.in_proj_weight", Ly["x"], d, dqkv, 3 * d, R, dz1, RM.dense(d), accum=True)
-      dx, other = dz1, dx
+      dxn = self.buf("dx_%d" % l, (R, d))
+      self._lin_bwd(gflat, p + "self_attn.in_proj_weight", Ly["x"], d, dqkv, 3 * d, R, dxn, RM.dense(d), res=dz1)
+      dx = dxn
     tok = ws[("tok0", B, T, d)]
     # proprio token -> state MLP
     ds = self.buf("ds", (B, d))
@@ -290,9 +303,9 @@ class LocoPlanTC:
     a3 = ws[("a3", B, 16, 64)]
     up = "encoder.depth_up_conv.weight"
     strides = (d, T * d, T * d)
-    ops.tc_wgrad(a3, (B, 1, 16, 64), dx, d, (B, 1, 16), (16, 1, 8), [(0, 0)], 64, self.W.fwd[up].dev_table, gflat,
-                 dy_strides=strides, dy_off=d, out_scale=inv, dbias=self._view(gflat, "encoder.depth_up_conv.bias"),
-                 defer=True)
+    self._side(lambda: ops.tc_wgrad(
+      a3, (B, 1, 16, 64), dx, d, (B, 1, 16), (16, 1, 8), [(0, 0)], 64, self.W.fwd[up].dev_table, gflat,
+      dy_strides=strides, dy_off=d, out_scale=inv, dbias=self._view(gflat, "encoder.depth_up_conv.bias"), defer=True))
     da3 = self.buf("da3", (B, 16, 64))
     pd = self.W.dgr[up]
     ops.tc_gemm(dx, (B, 1, 16, 64), (B, 1, 16), (16, 1, 8), [(0, 0)], 1, pd.w, pd.rows, 64, None, da3,
@@ -300,22 +313,26 @@ class LocoPlanTC:
     # conv3
     pre = "encoder.depth_visual_base.layers."
     a2, a1c = ws[("a2", B, 6, 6, 64)], ws[("a1c", B, 8, 8, 128)]
-    ops.tc_wgrad(a2, (B, 6, 6, 64), da3, 64, (B, 4, 4), (4, 4, 4), self.taps3, 64, self.W.fwd[pre + "4.weight"].dev_table, gflat, out_scale=inv,
-                 dbias=self._view(gflat, pre + "4.bias"), defer=True)
+    self._side(lambda: ops.tc_wgrad(
+      a2, (B, 6, 6, 64), da3, 64, (B, 4, 4), (4, 4, 4), self.taps3, 64, self.W.fwd[pre + "4.weight"].dev_table, gflat,
+      out_scale=inv, dbias=self._view(gflat, pre + "4.bias"), defer=True))
     da2 = self.buf("da2", (B, 6, 6, 64))
     pd = self.W.dgr[pre + "4.weight"]
     ops.tc_gemm(da3, (B, 4, 4, 64), (B, 6, 6), (6, 6, 3), [(-kw, -kh) for kw, kh in self.taps3], 1, pd.w, pd.rows, 64,
                 None, da2, RM(36, 36 * 64, 64, 0), mask=a2)
     # conv2
-    ops.tc_wgrad(a1c, (B, 8, 8, 128), da2, 64, (B, 6, 6), (6, 6, 3), self.taps2, 64, self.W.fwd[pre + "2.weight"].dev_table, gflat, out_scale=inv,
-                 dbias=self._view(gflat, pre + "2.bias"), defer=True)
+    self._side(lambda: ops.tc_wgrad(
+      a1c, (B, 8, 8, 128), da2, 64, (B, 6, 6), (6, 6, 3), self.taps2, 64, self.W.fwd[pre + "2.weight"].dev_table, gflat,
+      out_scale=inv, dbias=self._view(gflat, pre + "2.bias"), defer=True))
     da1c = self.buf("da1c", (B, 8, 8, 128))
     pd = self.W.dgr[pre + "2.weight"]
     ops.tc_gemm(da2, (B, 6, 6, 64), (B, 8, 8), (8, 8, 2), [(-dx_, -dy_) for dx_, dy_ in self.taps2], 1, pd.w, pd.rows, 128,
                 None, da1c, RM(64, 64 * 128, 128, 0), mask=a1c)
     # conv1: per sub-position (py,px) of a cell, X is the stride-2 sub-grid of the s2d image
     subs = [(px, py, (py * 2 + px) * 32) for py in range(2) for px in range(2)]
-    ops.tc_wgrad(self._imgs, (self._imgs.shape[0], 16, 16, 64), da1c, 128, (B, 8, 8), (8, 8, 1), self.taps2, 32,
-                 self.W.fwd[pre + "0.weight"].dev_table, gflat, x_idx=self._idx, x_estride=2, subs=subs, out_scale=inv,
-                 dbias=self._view(gflat, pre + "0.bias"), defer=True)
+    self._side(lambda: ops.tc_wgrad(
+      self._imgs, (self._imgs.shape[0], 16, 16, 64), da1c, 128, (B, 8, 8), (8, 8, 1), self.taps2, 32,
+      self.W.fwd[pre + "0.weight"].dev_table, gflat, x_idx=self._idx, x_estride=2, subs=subs, out_scale=inv,
+      dbias=self._view(gflat, pre + "0.bias"), defer=True))
+    ops.join()
     ops.tc_wgrad_flush()
