@@ -335,8 +335,12 @@ def main():
   e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3))
   e2e_value = samples_per_step * args.steps / (e2e_ms / 1e3)
 
-  if rank != 0:
-    return
+  if world > 1:
+    import torch.distributed as dist
+    dist.barrier()
+    if rank != 0:
+      dist.destroy_process_group()
+      return
   pk = peaks()
   roof = dominant_kernel_roofline(args, eng, pk)
   line = {
@@ -357,6 +361,9 @@ def main():
   if not args.no_cpu_baseline and world == 1:
     line["cpu_baseline"] = cpu_baseline(args, args.cpu_seconds)
   print(json.dumps(line))
+  if world > 1:
+    import torch.distributed as dist
+    dist.destroy_process_group()
 
 
 def dominant_kernel_roofline(args, eng, pk):

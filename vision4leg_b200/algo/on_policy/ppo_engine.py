@@ -416,7 +416,7 @@ class PPOUpdateEngine:
     return [dict(zip(INFO_KEYS, (float(x) for x in row))) for row in info]
 
   def _launch(self, B):
-    if not self.use_cuda_graph or self.world > 1:
+    if not self.use_cuda_graph:
       self._minibatch(B)
       return
     g = self._graphs.get(B)
