@@ -336,11 +336,14 @@ def main():
   e2e_value = samples_per_step * args.steps / (e2e_ms / 1e3)
 
   if world > 1:
+    # no collective is issued past this point; ranks leave without tearing NCCL down (destroying a
+    # communicator that captured CUDA graphs still reference can block) — hard exit after flushing
     import torch.distributed as dist
     dist.barrier()
+    torch.cuda.synchronize(dev)
     if rank != 0:
-      dist.destroy_process_group()
-      return
+      sys.stdout.flush()
+      os._exit(0)
   pk = peaks()
   roof = dominant_kernel_roofline(args, eng, pk)
   line = {
@@ -361,9 +364,9 @@ def main():
   if not args.no_cpu_baseline and world == 1:
     line["cpu_baseline"] = cpu_baseline(args, args.cpu_seconds)
   print(json.dumps(line))
+  sys.stdout.flush()
   if world > 1:
-    import torch.distributed as dist
-    dist.destroy_process_group()
+    os._exit(0)
 
 
 def dominant_kernel_roofline(args, eng, pk):
