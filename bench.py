@@ -272,7 +272,7 @@ def main():
   agent, logger = make_ppo(pf, vf, buf, A, args.batch, T * E, args.opt_epochs, device=dev)
   agent.process_group = pg
   agent.use_cuda_graph = not args.no_graph
-  agent.precision = args.precision if args.model == "loco" else "fp32"
+  agent.precision = args.precision
   eng = agent.engine
   samples_per_step = args.opt_epochs * T * E * world
 
@@ -415,7 +415,7 @@ def tc_conv1_roofline(args, eng, pk):
   plan, r = eng.plan_pf, eng._roll
   idx = eng._bufs(B)["cur_idx"]
   a1c = plan.buf("a1c", (B, 8, 8, 128), zero=True)
-  pre = "encoder.depth_visual_base.layers."
+  pre = "encoder.depth_visual_base.layers." if args.model == "loco" else "encoder.visual_base.layers."
   pkw = plan.W.fwd[pre + "0.weight"]
   bias = plan._view(eng.pf_flat, pre + "0.bias")
   run = lambda: ops.tc_gemm(r["imgs"], (r["imgs"].shape[0], 16, 16, 64), (B, 15, 15), (15, 8, 1), plan.taps2, 1,

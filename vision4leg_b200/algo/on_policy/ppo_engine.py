@@ -92,13 +92,14 @@ class PPOUpdateEngine:
       raise ValueError("precision must be 'fp32' (exact CUDA-core tier) or 'f16' (tcgen05 tier)")
     self.precision = precision
     if precision == "f16":
-      if self.family != "loco":
-        raise NotImplementedError("the tensor-core tier currently covers the LocoTransformer family; "
-                                  "use precision='fp32' for %s" % self.family)
+      if self.family not in engine_tc.PLANS:
+        raise NotImplementedError("the tensor-core tier covers the LocoTransformer and NatureCNN "
+                                  "families; use precision='fp32' for %s" % self.family)
       nh = kw.get("n_heads", (1, 1))
-      self.plan_pf = engine_tc.LocoPlanTC(self.ops, self.S, self.A, self.pf_layout, nh)
-      self.plan_vf = engine_tc.LocoPlanTC(self.ops, self.S, 1, self.vf_layout, nh)
-      self.plan_t = engine_tc.LocoPlanTC(self.ops, self.S, self.A, self.pf_layout, nh, with_backward=False)
+      Plan = engine_tc.PLANS[self.family]
+      self.plan_pf = Plan(self.ops, self.S, self.A, self.pf_layout, nh)
+      self.plan_vf = Plan(self.ops, self.S, 1, self.vf_layout, nh)
+      self.plan_t = Plan(self.ops, self.S, self.A, self.pf_layout, nh, with_backward=False)
       self.plan_t.pack(self.t_flat)
     else:
       self.plan_pf = engine.make_plan(self.family, self.ops, self.S, self.A, **kw)
@@ -253,7 +254,8 @@ class PPOUpdateEngine:
     if p is None:
       kw = getattr(self.pf, "_plan_kwargs", {})
       if self.precision == "f16":
-        p = engine_tc.LocoPlanTC(self.ops, self.S, 1, self.vf_layout, kw.get("n_heads", (1, 1)), with_backward=False)
+        p = engine_tc.PLANS[self.family](self.ops, self.S, 1, self.vf_layout, kw.get("n_heads", (1, 1)),
+                                         with_backward=False)
       else:
         p = engine.make_plan(self.family, self.ops, self.S, 1, **kw)
       self._mb_bufs[key] = p

@@ -40,11 +40,14 @@ class _Packed:
     self.off = None
 
 
-def _linear_tables(off, N, K):
-  """W[N,K] fp32 at flat offset `off` -> (fwd [N_pad, ceil64(K)], dgrad [Kd_pad, ceil64(N)])"""
+def _linear_tables(off, N, K, kperm=None):
+  """W[N,K] fp32 at flat offset `off` -> (fwd [N_pad, ceil64(K)], dgrad [Kd_pad, ceil64(N)]).
+  kperm[kp] = reference K index held at packed position kp (identity if None)."""
   Np, Kp = _ceil(N, 16), _ceil(K, 64)
   fwd = -np.ones((Np, Kp), np.int64)
   n, k = np.meshgrid(np.arange(N), np.arange(K), indexing="ij")
+  if kperm is not None:
+    k = np.asarray(kperm)[k]
   fwd[:N, :K] = off + n * K + k
   Kd = _ceil(K, 16)
   if Kd > 256:
@@ -88,6 +91,10 @@ class TcWeights:
       if len(shape) == 4 and shape[2] > 1:
         stride = {8: 4, 4: 2, 3: 1}[shape[2]]
         f, d = _conv_tables(off, shape[0], shape[1], shape[2], shape[3], stride)
+      elif name == "encoder.visual_projector.projection.0.weight":
+        # torch flattens [64,4,4] as (c, p); our a3 is [16 positions, 64 channels] = (p, c)
+        pp, cc = np.meshgrid(np.arange(16), np.arange(64), indexing="ij")
+        f, d = _linear_tables(off, shape[0], shape[1], kperm=(cc * 16 + pp).ravel())
       else:
         f, d = _linear_tables(off, shape[0], int(np.prod(shape[1:])))
       for store, pk in ((self.fwd, f), (self.dgr, d)):
@@ -113,21 +120,18 @@ class TcWeights:
     self.ops.pack_f16(flat, self.table, self.packed, self.size)
 
 
-class LocoPlanTC:
-  """LocoTransformer forward/backward on the tensor-core tier for one batch size."""
-  family = "loco"
+class _PlanTC:
+  """Shared machinery: workspace, packed weights, Linear helpers and the NatureCNN trunk."""
 
-  def __init__(self, ops, S, out_dim, layout, n_heads=(1, 1), with_backward=True):
+  def __init__(self, ops, S, out_dim, layout, with_backward, head_prefix):
     self.ops, self.device = ops, ops.device
     self.S, self.Sp = S, _ceil(S, 64)
     self.out_dim = out_dim
-    self.n_heads = list(n_heads)
-    self.T, self.d = 17, 64
     self.layout = layout
     self.W = TcWeights(ops, layout, with_dgrad=with_backward)
     self._ws = {}
     self.k_base = [k for k in layout if k.startswith("encoder.base.seq_fcs.") and k.endswith("weight")]
-    self.k_head = sorted((k for k in layout if k.startswith("visual_seq_append_fcs.") and k.endswith("weight")),
+    self.k_head = sorted((k for k in layout if k.startswith(head_prefix) and k.endswith("weight")),
                          key=lambda k: int(k.split(".")[-2]))
     oh, ow = np.meshgrid(np.arange(15), np.arange(15), indexing="ij")
     pos = ((oh // 2) * 8 + ow // 2) * 128 + ((oh % 2) * 2 + ow % 2) * 32
@@ -166,19 +170,88 @@ class LocoPlanTC:
       fn()
 
   def _lin_bwd(self, gflat, wname, x, x_cols, dy, dy_cols, M, dx=None, dx_map=None, mask=None, res=None,
-               need_dx=True):
+               need_dx=True, dy_pitch=0, dy_off=0):
     """dW, db from (x [M,x_cols], dy [M,dy_cols]) on the side stream; optionally
-    dx = (dy @ W) * (mask > 0) + res on the main stream."""
+    dx = (dy @ W) * (mask > 0) + res on the main stream.  dy may be a column window of a wider
+    matrix (row pitch dy_pitch elements, first column dy_off)."""
     pk = self.W.fwd[wname]
     N, K = self.layout[wname][1][0], int(np.prod(self.layout[wname][1][1:]))
     inv = self._inv_scale
+    st = (dy_pitch, dy_pitch, dy_pitch) if dy_pitch else None
     self._side(lambda: self.ops.tc_wgrad(
       x, (M, 1, 1, x_cols), dy, dy_cols, (M, 1, 1), (1, 1, 128), [(0, 0)], N, pk.dev_table, gflat,
-      out_scale=inv, dbias=self._view(gflat, wname[:-6] + "bias"), defer=True))
+      out_scale=inv, dbias=self._view(gflat, wname[:-6] + "bias"), defer=True, dy_strides=st, dy_off=dy_off))
     if need_dx:
       pd = self.W.dgr[wname]
       self.ops.tc_gemm(dy, (M, 1, 1, dy_cols), (M, 1, 1), (1, 1, 128), [(0, 0)], pd.cols // 64, pd.w, pd.rows, K,
-                       None, dx, dx_map, mask=mask, res=res)
+                       None, dx, dx_map, mask=mask, res=res, a_strides=st, a_off=dy_off)
+
+  # ---- NatureCNN trunk (reference base.py:304-342) on tap-shifted TMA boxes -----------------------
+  def _trunk_fwd(self, flat, imgs, idx, B, pre):
+    ops = self.ops
+    Nimg = imgs.shape[0]
+    # conv1 (8x8/4 = 2x2/1 on the s2d image) -> a1 stored as the cells conv2 reads
+    a1c = self.buf("a1c", (B, 8, 8, 128), zero=True)
+    pk = self.W.fwd[pre + "0.weight"]
+    ops.tc_gemm(imgs, (Nimg, 16, 16, 64), (B, 15, 15), (15, 8, 1), self.taps2, 1, pk.w, pk.rows, 32,
+                self._view(flat, pre + "0.bias"), a1c, RM(225, 8 * 8 * 128, 0, 0, pos_off=self.pos_a1),
+                flags=RELU, a_idx=idx)
+    a2 = self.buf("a2", (B, 6, 6, 64))
+    pk = self.W.fwd[pre + "2.weight"]
+    ops.tc_gemm(a1c, (B, 8, 8, 128), (B, 6, 6), (6, 6, 3), self.taps2, 2, pk.w, pk.rows, 64,
+                self._view(flat, pre + "2.bias"), a2, RM(36, 36 * 64, 64, 0), flags=RELU)
+    a3 = self.buf("a3", (B, 16, 64))
+    pk = self.W.fwd[pre + "4.weight"]
+    ops.tc_gemm(a2, (B, 6, 6, 64), (B, 4, 4), (4, 4, 8), self.taps3, 1, pk.w, pk.rows, 64,
+                self._view(flat, pre + "4.bias"), a3, RM(16, 16 * 64, 64, 0), flags=RELU)
+    return a3
+
+  def _trunk_bwd(self, gflat, da3, B, pre):
+    """da3 [B,16,64]: gradient w.r.t. conv3's pre-activation."""
+    ops, ws, inv = self.ops, self._ws, self._inv_scale
+    a2, a1c = ws[("a2", B, 6, 6, 64)], ws[("a1c", B, 8, 8, 128)]
+    self._side(lambda: ops.tc_wgrad(
+      a2, (B, 6, 6, 64), da3, 64, (B, 4, 4), (4, 4, 4), self.taps3, 64, self.W.fwd[pre + "4.weight"].dev_table, gflat,
+      out_scale=inv, dbias=self._view(gflat, pre + "4.bias"), defer=True))
+    da2 = self.buf("da2", (B, 6, 6, 64))
+    pd = self.W.dgr[pre + "4.weight"]
+    ops.tc_gemm(da3, (B, 4, 4, 64), (B, 6, 6), (6, 6, 3), [(-kw, -kh) for kw, kh in self.taps3], 1, pd.w, pd.rows, 64,
+                None, da2, RM(36, 36 * 64, 64, 0), mask=a2)
+    self._side(lambda: ops.tc_wgrad(
+      a1c, (B, 8, 8, 128), da2, 64, (B, 6, 6), (6, 6, 3), self.taps2, 64, self.W.fwd[pre + "2.weight"].dev_table, gflat,
+      out_scale=inv, dbias=self._view(gflat, pre + "2.bias"), defer=True))
+    da1c = self.buf("da1c", (B, 8, 8, 128))
+    pd = self.W.dgr[pre + "2.weight"]
+    ops.tc_gemm(da2, (B, 6, 6, 64), (B, 8, 8), (8, 8, 2), [(-dx_, -dy_) for dx_, dy_ in self.taps2], 1, pd.w, pd.rows, 128,
+                None, da1c, RM(64, 64 * 128, 128, 0), mask=a1c)
+    # conv1: per sub-position (py,px) of a cell, X is the stride-2 sub-grid of the s2d image
+    subs = [(px, py, (py * 2 + px) * 32) for py in range(2) for px in range(2)]
+    self._side(lambda: ops.tc_wgrad(
+      self._imgs, (self._imgs.shape[0], 16, 16, 64), da1c, 128, (B, 8, 8), (8, 8, 1), self.taps2, 32,
+      self.W.fwd[pre + "0.weight"].dev_table, gflat, x_idx=self._idx, x_estride=2, subs=subs, out_scale=inv,
+      dbias=self._view(gflat, pre + "0.bias"), defer=True))
+
+  def _begin_backward(self, d_out, B):
+    """fp32 d_out [B, out_dim] -> loss-scaled fp16 [B,16].  Static loss scale: d_out ~ 1/B, so
+    scale ~ 4B keeps fp16 gradients O(1e2); every fp32 result (dW, db, dgamma, dbeta) is multiplied
+    by 1/scale where it is produced."""
+    scale = float(min(4096, max(64, 1 << int(np.floor(np.log2(4 * B))))))
+    if LOSS_SCALE_OVERRIDE:
+      scale = float(LOSS_SCALE_OVERRIDE)
+    self._inv_scale = 1.0 / scale
+    g16 = self.buf("dout16", (B, 16))
+    self.ops.gather_rows_f16(d_out, True, None, g16, B, self.out_dim, self.out_dim, 16, scale=scale)
+    return g16
+
+
+class LocoPlanTC(_PlanTC):
+  """LocoTransformer forward/backward on the tensor-core tier for one batch size."""
+  family = "loco"
+
+  def __init__(self, ops, S, out_dim, layout, n_heads=(1, 1), with_backward=True):
+    super().__init__(ops, S, out_dim, layout, with_backward, "visual_seq_append_fcs.")
+    self.n_heads = list(n_heads)
+    self.T, self.d = 17, 64
 
   # ---- forward --------------------------------------------------------------------------------
   def forward(self, flat, imgs, idx, st, B, out):
@@ -186,25 +259,7 @@ class LocoPlanTC:
     out fp32 [B,out_dim].  `flat` = the fp32 bucket the layout offsets refer to (biases, LN)."""
     ops, T, d = self.ops, self.T, self.d
     self._flat, self._B, self._imgs, self._idx, self._st = flat, B, imgs, idx, st
-    L = self.layout
-    Nimg = imgs.shape[0]
-    pre = "encoder.depth_visual_base.layers."
-    # conv1 (s2d 2x2) -> a1 cells
-    a1c = self.buf("a1c", (B, 8, 8, 128), zero=True)
-    pk = self.W.fwd[pre + "0.weight"]
-    ops.tc_gemm(imgs, (Nimg, 16, 16, 64), (B, 15, 15), (15, 8, 1), self.taps2, 1, pk.w, pk.rows, 32,
-                self._view(flat, pre + "0.bias"), a1c, RM(225, 8 * 8 * 128, 0, 0, pos_off=self.pos_a1),
-                flags=RELU, a_idx=idx)
-    # conv2 on cells
-    a2 = self.buf("a2", (B, 6, 6, 64))
-    pk = self.W.fwd[pre + "2.weight"]
-    ops.tc_gemm(a1c, (B, 8, 8, 128), (B, 6, 6), (6, 6, 3), self.taps2, 2, pk.w, pk.rows, 64,
-                self._view(flat, pre + "2.bias"), a2, RM(36, 36 * 64, 64, 0), flags=RELU)
-    # conv3
-    a3 = self.buf("a3", (B, 16, 64))
-    pk = self.W.fwd[pre + "4.weight"]
-    ops.tc_gemm(a2, (B, 6, 6, 64), (B, 4, 4), (4, 4, 8), self.taps3, 1, pk.w, pk.rows, 64,
-                self._view(flat, pre + "4.bias"), a3, RM(16, 16 * 64, 64, 0), flags=RELU)
+    a3 = self._trunk_fwd(flat, imgs, idx, B, "encoder.depth_visual_base.layers.")
     # tokens
     tok = self.buf("tok0", (B, T, d))
     self._lin_fwd(flat, "encoder.depth_up_conv.weight", a3, B * 16, 64, tok, RM.slots(16, T, d, 1), False)
@@ -252,14 +307,8 @@ class LocoPlanTC:
     R = B * T
     A = self.out_dim
     ws = self._ws
-    # static loss scale (fp16 gradients): d_out ~ 1/B, so scale ~ 4B keeps them O(1e2); every fp32
-    # result (dW, db, dgamma, dbeta) is multiplied by 1/scale where it is produced
-    scale = float(min(4096, max(64, 1 << int(np.floor(np.log2(4 * B))))))
-    if LOSS_SCALE_OVERRIDE:
-      scale = float(LOSS_SCALE_OVERRIDE)
-    self._inv_scale = inv = 1.0 / scale
-    g16 = self.buf("dout16", (B, 16))
-    ops.gather_rows_f16(d_out, True, None, g16, B, A, A, 16, scale=scale)
+    g16 = self._begin_backward(d_out, B)
+    inv = self._inv_scale
     h1, h2, pooled = ws[("h1", B, 256)], ws[("h2", B, 256)], ws[("pooled", B, 2 * d)]
     dh2 = self.buf("dh2", (B, 256)); dh1 = self.buf("dh1", (B, 256)); dpool = self.buf("dpool", (B, 2 * d))
     self._lin_bwd(gflat, self.k_head[2], h2, 256, g16, 16, B, dh2, RM.dense(256), mask=h2)
@@ -310,29 +359,56 @@ class LocoPlanTC:
     pd = self.W.dgr[up]
     ops.tc_gemm(dx, (B, 1, 16, 64), (B, 1, 16), (16, 1, 8), [(0, 0)], 1, pd.w, pd.rows, 64, None, da3,
                 RM(16, 16 * 64, 64, 0), mask=a3, a_strides=strides, a_off=d)
-    # conv3
-    pre = "encoder.depth_visual_base.layers."
-    a2, a1c = ws[("a2", B, 6, 6, 64)], ws[("a1c", B, 8, 8, 128)]
-    self._side(lambda: ops.tc_wgrad(
-      a2, (B, 6, 6, 64), da3, 64, (B, 4, 4), (4, 4, 4), self.taps3, 64, self.W.fwd[pre + "4.weight"].dev_table, gflat,
-      out_scale=inv, dbias=self._view(gflat, pre + "4.bias"), defer=True))
-    da2 = self.buf("da2", (B, 6, 6, 64))
-    pd = self.W.dgr[pre + "4.weight"]
-    ops.tc_gemm(da3, (B, 4, 4, 64), (B, 6, 6), (6, 6, 3), [(-kw, -kh) for kw, kh in self.taps3], 1, pd.w, pd.rows, 64,
-                None, da2, RM(36, 36 * 64, 64, 0), mask=a2)
-    # conv2
-    self._side(lambda: ops.tc_wgrad(
-      a1c, (B, 8, 8, 128), da2, 64, (B, 6, 6), (6, 6, 3), self.taps2, 64, self.W.fwd[pre + "2.weight"].dev_table, gflat,
-      out_scale=inv, dbias=self._view(gflat, pre + "2.bias"), defer=True))
-    da1c = self.buf("da1c", (B, 8, 8, 128))
-    pd = self.W.dgr[pre + "2.weight"]
-    ops.tc_gemm(da2, (B, 6, 6, 64), (B, 8, 8), (8, 8, 2), [(-dx_, -dy_) for dx_, dy_ in self.taps2], 1, pd.w, pd.rows, 128,
-                None, da1c, RM(64, 64 * 128, 128, 0), mask=a1c)
-    # conv1: per sub-position (py,px) of a cell, X is the stride-2 sub-grid of the s2d image
-    subs = [(px, py, (py * 2 + px) * 32) for py in range(2) for px in range(2)]
-    self._side(lambda: ops.tc_wgrad(
-      self._imgs, (self._imgs.shape[0], 16, 16, 64), da1c, 128, (B, 8, 8), (8, 8, 1), self.taps2, 32,
-      self.W.fwd[pre + "0.weight"].dev_table, gflat, x_idx=self._idx, x_estride=2, subs=subs, out_scale=inv,
-      dbias=self._view(gflat, pre + "0.bias"), defer=True))
+    self._trunk_bwd(gflat, da3, B, "encoder.depth_visual_base.layers.")
     ops.join()
     ops.tc_wgrad_flush()
+
+
+class NaturePlanTC(_PlanTC):
+  """NatureCNN + concat MLP (reference nets.py:194-262, base.py:345-385) on the tensor-core tier."""
+  family = "nature"
+
+  def __init__(self, ops, S, out_dim, layout, n_heads=None, with_backward=True):
+    super().__init__(ops, S, out_dim, layout, with_backward, "seq_append_fcs.")
+    self.k_proj = "encoder.visual_projector.projection.0.weight"
+    self.vd = layout[self.k_proj][1][0]
+    self.sd = layout[self.k_base[-1]][1][0]
+
+  def forward(self, flat, imgs, idx, st, B, out):
+    self._flat, self._B, self._imgs, self._idx, self._st = flat, B, imgs, idx, st
+    W = self.vd + self.sd
+    a3 = self._trunk_fwd(flat, imgs, idx, B, "encoder.visual_base.layers.")
+    cat = self.buf("cat", (B, W))
+    # flatten + Linear(1024, vd) + ReLU: the (c,p) -> (p,c) reorder lives in the packing table
+    self._lin_fwd(flat, self.k_proj, a3, B, 1024, cat, RM(1, W, 0, 0), True)
+    s1 = self.buf("s1", (B, 256))
+    self._lin_fwd(flat, self.k_base[0], st, B, self.Sp, s1, RM.dense(256), True)
+    self._lin_fwd(flat, self.k_base[1], s1, B, 256, cat, RM(1, W, 0, self.vd), True)
+    h1 = self.buf("h1", (B, 256)); h2 = self.buf("h2", (B, 256))
+    self._lin_fwd(flat, self.k_head[0], cat, B, W, h1, RM.dense(256), True)
+    self._lin_fwd(flat, self.k_head[1], h1, B, 256, h2, RM.dense(256), True)
+    self._lin_fwd(flat, self.k_head[2], h2, B, 256, out, RM.dense(self.out_dim), False, c_f32=True)
+    return out
+
+  def backward(self, gflat, d_out):
+    ops, B, ws = self.ops, self._B, self._ws
+    W = self.vd + self.sd
+    g16 = self._begin_backward(d_out, B)
+    cat, h1, h2, s1, a3 = ws[("cat", B, W)], ws[("h1", B, 256)], ws[("h2", B, 256)], ws[("s1", B, 256)], ws[("a3", B, 16, 64)]
+    dh2 = self.buf("dh2", (B, 256)); dh1 = self.buf("dh1", (B, 256)); dcat = self.buf("dcat", (B, W))
+    self._lin_bwd(gflat, self.k_head[2], h2, 256, g16, 16, B, dh2, RM.dense(256), mask=h2)
+    self._lin_bwd(gflat, self.k_head[1], h1, 256, dh2, 256, B, dh1, RM.dense(256), mask=h1)
+    self._lin_bwd(gflat, self.k_head[0], cat, W, dh1, 256, B, dcat, RM.dense(W), mask=cat)
+    # proprio MLP: dy = dcat[:, vd:]
+    ds1 = self.buf("ds1", (B, 256))
+    self._lin_bwd(gflat, self.k_base[1], s1, 256, dcat, self.sd, B, ds1, RM.dense(256), mask=s1, dy_pitch=W, dy_off=self.vd)
+    self._lin_bwd(gflat, self.k_base[0], self._st, self.Sp, ds1, 256, B, need_dx=False)
+    # projector: dy = dcat[:, :vd]; da3 comes out in our (p,c) order through the packing table
+    da3 = self.buf("da3", (B, 16, 64))
+    self._lin_bwd(gflat, self.k_proj, a3, 1024, dcat, self.vd, B, da3, RM.dense(1024), mask=a3, dy_pitch=W, dy_off=0)
+    self._trunk_bwd(gflat, da3, B, "encoder.visual_base.layers.")
+    ops.join()
+    ops.tc_wgrad_flush()
+
+
+PLANS = {"loco": LocoPlanTC, "nature": NaturePlanTC}
