@@ -1,5 +1,6 @@
 // Context, error reporting and copy helpers of libv4l_b200.so.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -11,6 +12,15 @@ void v4l_set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool v4l_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("V4L_NO_PDL");
+    on = (e && e[0] == '1') ? 0 : 1;
+  }
+  return on == 1;
 }
 
 extern "C" int v4l_version(void) { return V4L_ABI_VERSION; }

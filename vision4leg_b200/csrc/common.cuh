@@ -58,6 +58,39 @@ void v4l_set_error(const char* fmt, ...);
     }                                                                                 \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------
+// Every kernel of the library (a) lets its successor start launching right away and (b) blocks
+// until its predecessor has completed and flushed before touching global memory.  Launches go
+// through v4l_launch(), which sets programmaticStreamSerialization, so the successor's launch
+// latency and prologue (barrier init, TMEM allocation, descriptor prefetch) overlap the tail of
+// the predecessor; in a captured CUDA graph these become programmatic dependency edges.
+__device__ __forceinline__ void v4l_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void v4l_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void v4l_pdl_enter() { v4l_pdl_trigger(); v4l_pdl_wait(); }
+
+bool v4l_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t v4l_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                     cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = v4l_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define V4L_LAUNCH(kernel, grid, block, smem, stream, ...)                                   \
+  do {                                                                                       \
+    cudaError_t _le = v4l_launch(kernel, dim3(grid), dim3(block), smem, stream, __VA_ARGS__); \
+    if (_le != cudaSuccess) {                                                                \
+      v4l_set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_le));      \
+      return -3;                                                                             \
+    }                                                                                        \
+  } while (0)
+
 __device__ __forceinline__ long long v4l_row_addr(const v4l_rowmap& rm, int m) {
   int item = m / rm.P;
   int pos = m - item * rm.P;

@@ -18,6 +18,7 @@ constexpr int NT = 256;
 
 template <int BN, bool B_NCONTIG>
 __global__ void __launch_bounds__(NT) gemm_rows_kernel(const v4l_gemm_args g) {
+  v4l_pdl_enter();
   constexpr int TN = BN / 16;
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(NT) gemm_rows_kernel(const v4l_gemm_args g) {
 // ---- weight gradient: partial[z][n][kext] = sum_{m in split z} dY(m,n) * Aext(m,kext) ----------
 __global__ void __launch_bounds__(NT) wgrad_kernel(const v4l_wgrad_args g, float* __restrict__ partial,
                                                    int Kext, int rows_per_split) {
+  v4l_pdl_enter();
   __shared__ __align__(16) float Ys[BK][64 + 4];
   __shared__ __align__(16) float As[BK][64 + 4];
   __shared__ long long rowY[BK], rowA[BK];
@@ -174,6 +176,7 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(const v4l_wgrad_args g, float
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int N, int K,
                                     int Kext, float* __restrict__ dw, long long ldw,
                                     float* __restrict__ dbias) {
+  v4l_pdl_enter();
   const long long total = (long long)N * Kext;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
@@ -188,6 +191,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int split
 __global__ void col2im_kernel(const float* __restrict__ dcol, const float* __restrict__ x,
                               float* __restrict__ dx, int B, int Hin, int Win, int C, int KH, int KW,
                               int stride, int Hout, int Wout) {
+  v4l_pdl_enter();
   const long long total = (long long)B * Hin * Win * C;
   const int K = C * KH * KW;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
@@ -220,6 +224,7 @@ __global__ void col2im_kernel(const float* __restrict__ dcol, const float* __res
 __global__ void relu_bwd_kernel(const float* __restrict__ dy, const v4l_rowmap dy_map,
                                 const float* __restrict__ act, const v4l_rowmap act_map,
                                 float* __restrict__ out, const v4l_rowmap out_map, int M, int N) {
+  v4l_pdl_enter();
   const long long total = (long long)M * N;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
@@ -240,7 +245,7 @@ extern "C" int v4l_relu_bwd(v4l_ctx* ctx, void* stream, const float* dy, const v
   const long long total = (long long)M * N;
   if (total <= 0) return 0;
   const int blocks = (int)min((long long)8 * ctx->sm_count, (total + 255) / 256);
-  relu_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dy, *dy_map, act, *act_map, out, *out_map, M, N);
+  V4L_LAUNCH(relu_bwd_kernel, blocks, 256, 0, (cudaStream_t)stream, dy, *dy_map, act, *act_map, out, *out_map, M, N);
   V4L_CHECK_LAUNCH();
   return 0;
 }
@@ -258,11 +263,11 @@ extern "C" int v4l_gemm_rows(v4l_ctx* ctx, void* stream, const v4l_gemm_args* a)
   dim3 grid(v4l_cdiv(a->M, BM), v4l_cdiv(a->N, bn));
   V4L_REQUIRE(grid.y <= 65535, "v4l_gemm_rows: N too large");
   if (bn == 32) {
-    if (ncontig) gemm_rows_kernel<32, true><<<grid, NT, 0, s>>>(*a);
-    else         gemm_rows_kernel<32, false><<<grid, NT, 0, s>>>(*a);
+    if (ncontig) V4L_LAUNCH((gemm_rows_kernel<32, true>), grid, NT, 0, s, *a);
+    else         V4L_LAUNCH((gemm_rows_kernel<32, false>), grid, NT, 0, s, *a);
   } else {
-    if (ncontig) gemm_rows_kernel<64, true><<<grid, NT, 0, s>>>(*a);
-    else         gemm_rows_kernel<64, false><<<grid, NT, 0, s>>>(*a);
+    if (ncontig) V4L_LAUNCH((gemm_rows_kernel<64, true>), grid, NT, 0, s, *a);
+    else         V4L_LAUNCH((gemm_rows_kernel<64, false>), grid, NT, 0, s, *a);
   }
   V4L_CHECK_LAUNCH();
   return 0;
@@ -286,10 +291,10 @@ extern "C" int v4l_gemm_wgrad(v4l_ctx* ctx, void* stream, const v4l_wgrad_args* 
   splits = v4l_cdiv(a->M, rps);
   V4L_REQUIRE(splits <= 65535, "v4l_gemm_wgrad: too many splits");
   dim3 grid(gx, gy, splits);
-  wgrad_kernel<<<grid, NT, 0, s>>>(*a, ctx->scratch, Kext, rps);
+  V4L_LAUNCH(wgrad_kernel, grid, NT, 0, s, *a, ctx->scratch, Kext, rps);
   V4L_CHECK_LAUNCH();
   const int rblocks = (int)min((long long)4 * ctx->sm_count, (per_split + 255) / 256);
-  wgrad_reduce_kernel<<<rblocks, 256, 0, s>>>(ctx->scratch, splits, a->N, a->K, Kext, a->dw, a->ldw, a->dbias);
+  V4L_LAUNCH(wgrad_reduce_kernel, rblocks, 256, 0, s, ctx->scratch, splits, a->N, a->K, Kext, a->dw, a->ldw, a->dbias);
   V4L_CHECK_LAUNCH();
   return 0;
 }
@@ -302,7 +307,7 @@ extern "C" int v4l_col2im(v4l_ctx* ctx, void* stream, const float* dcol, const f
   const long long total = (long long)B * Hin * Win * C;
   if (total == 0) return 0;
   const int blocks = (int)min((long long)16 * ctx->sm_count, (total + 255) / 256);
-  col2im_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dcol, x, dx, B, Hin, Win, C, KH, KW, stride, Hout, Wout);
+  V4L_LAUNCH(col2im_kernel, blocks, 256, 0, (cudaStream_t)stream, dcol, x, dx, B, Hin, Win, C, KH, KW, stride, Hout, Wout);
   V4L_CHECK_LAUNCH();
   return 0;
 }

@@ -87,6 +87,7 @@ __device__ __forceinline__ AB gae_element(const GaeArgs& g, int t, int e) {
 
 // phase 1: per (column e, chunk c) composite of the chunk -> agg[e * n_chunks + c]
 __global__ void __launch_bounds__(GAE_THREADS) gae_aggregate_kernel(const GaeArgs g, AB* __restrict__ agg) {
+  v4l_pdl_enter();
   __shared__ AB wsum[GAE_THREADS / 32 + 1];
   const int e = blockIdx.y, c = blockIdx.x;
   const int t_lo = c * g.chunk_len, t_hi = min(g.T, t_lo + g.chunk_len);
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(GAE_THREADS) gae_aggregate_kernel(const GaeArg
 
 // phase 2: carry[e][c] = A at the first step AFTER chunk c
 __global__ void gae_carry_kernel(const GaeArgs g, const AB* __restrict__ agg, double* __restrict__ carry) {
+  v4l_pdl_enter();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= g.E) return;
   double A = (g.mode == 0) ? 0.0 : (double)g.last_value[e];
@@ -116,6 +118,7 @@ __global__ void gae_carry_kernel(const GaeArgs g, const AB* __restrict__ agg, do
 
 // phase 3: scan each chunk with its carry-in and write advs / rets
 __global__ void __launch_bounds__(GAE_THREADS) gae_scan_kernel(const GaeArgs g, const double* __restrict__ carry) {
+  v4l_pdl_enter();
   __shared__ AB wsum[GAE_THREADS / 32 + 1];
   __shared__ double s_carry;
   const int e = blockIdx.y, c = blockIdx.x;
@@ -147,12 +150,14 @@ __global__ void __launch_bounds__(GAE_THREADS) gae_scan_kernel(const GaeArgs g, 
 // =============================================================================================
 __global__ void select_rows_kernel(const int32_t* __restrict__ flat_idx, const int32_t* __restrict__ slot,
                                    int32_t* __restrict__ cur, int n) {
+  v4l_pdl_enter();
   const long long base = (long long)(*slot) * n;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     cur[i] = flat_idx[base + i];
 }
 
 __global__ void slot_advance_kernel(int32_t* slot, int32_t wrap) {
+  v4l_pdl_enter();
   int32_t s = *slot + 1;
   if (wrap > 0 && s >= wrap) s = 0;
   *slot = s;
@@ -190,6 +195,7 @@ struct OpMinF { __device__ float operator()(float a, float b) const { return fmi
 __global__ void __launch_bounds__(1024) adv_stats_kernel(const float* __restrict__ adv,
                                                          const int32_t* __restrict__ idx, int n,
                                                          double* __restrict__ stats) {
+  v4l_pdl_enter();
   __shared__ double shd[32];
   __shared__ float shf[32];
   double s = 0.0, s2 = 0.0;
@@ -218,6 +224,7 @@ vf_loss_kernel(const float* __restrict__ values, const float* __restrict__ retur
                const float* __restrict__ old_values, const int32_t* __restrict__ idx,
                float* __restrict__ d_values, int n, float inv_global, int clipped, float clip,
                double* __restrict__ part) {
+  v4l_pdl_enter();
   __shared__ double shd[32];
   double acc = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -249,6 +256,7 @@ vf_loss_kernel(const float* __restrict__ values, const float* __restrict__ retur
 
 __global__ void vf_loss_finalize_kernel(const double* __restrict__ part, int nparts, float inv_local,
                                         float* __restrict__ info, const int32_t* __restrict__ slot) {
+  v4l_pdl_enter();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double s = 0.0;
     for (int i = 0; i < nparts; ++i) s += part[i];
@@ -272,6 +280,7 @@ pf_loss_kernel(const float* __restrict__ mean, const float* __restrict__ logstd,
                const int32_t* __restrict__ idx, const double* __restrict__ adv_stats,
                float* __restrict__ d_mean, int n, int A, float inv_global, float clip,
                double* __restrict__ part) {
+  v4l_pdl_enter();
   __shared__ float s_ls[MAX_A], s_tls[MAX_A], s_ivar[MAX_A], s_tivar[MAX_A];
   __shared__ float s_dls[LOSS_THREADS / 32][MAX_A];
   __shared__ double shd[32];
@@ -362,6 +371,7 @@ __global__ void pf_loss_finalize_kernel(const double* __restrict__ part, int npa
                                         const double* __restrict__ adv_stats, float* __restrict__ d_logstd,
                                         int n, int A, float inv_local, float entropy_coeff,
                                         float* __restrict__ info, const int32_t* __restrict__ slot) {
+  v4l_pdl_enter();
   // one warp; lane a < A reduces d_logstd[a]; lane 0 writes the info row
   const int lane = threadIdx.x;
   float* row = info + (long long)(slot ? *slot : 0) * V4L_INFO_STRIDE;
@@ -419,6 +429,7 @@ constexpr int ADAM_THREADS = 256;
 
 __global__ void __launch_bounds__(ADAM_THREADS)
 sqnorm_kernel(const float* __restrict__ g, long long n, double* __restrict__ part) {
+  v4l_pdl_enter();
   __shared__ double shd[32];
   double s = 0.0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
@@ -434,6 +445,7 @@ __global__ void __launch_bounds__(ADAM_THREADS)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, long long n, const float* __restrict__ hyper,
             const double* __restrict__ part, int nparts) {
+  v4l_pdl_enter();
   __shared__ float s_coef;
   if (threadIdx.x == 0) {
     double s = 0.0;
@@ -461,6 +473,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 
 __global__ void adam_finish_kernel(float* hyper, const double* __restrict__ part, int nparts,
                                    float* info, const int32_t* slot, int norm_slot) {
+  v4l_pdl_enter();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     hyper[5] += 1.f;
     if (info && norm_slot >= 0) {
@@ -498,7 +511,7 @@ extern "C" int v4l_gae(v4l_ctx* ctx, void* stream, const float* rewards, const f
   g.n_chunks = v4l_cdiv(T, chunk);
   dim3 grid(g.n_chunks, E);
   if (g.n_chunks == 1) {
-    gae_scan_kernel<<<grid, GAE_THREADS, 0, s>>>(g, nullptr);
+    V4L_LAUNCH(gae_scan_kernel, grid, GAE_THREADS, 0, s, g, nullptr);
     V4L_CHECK_LAUNCH();
     return 0;
   }
@@ -506,11 +519,11 @@ extern "C" int v4l_gae(v4l_ctx* ctx, void* stream, const float* rewards, const f
   V4L_REQUIRE(need <= ctx->scratch_elems * sizeof(float), "v4l_gae: scratch too small");
   AB* agg = reinterpret_cast<AB*>(ctx->scratch);
   double* carry = reinterpret_cast<double*>(ctx->scratch) + (size_t)E * g.n_chunks * 2;
-  gae_aggregate_kernel<<<grid, GAE_THREADS, 0, s>>>(g, agg);
+  V4L_LAUNCH(gae_aggregate_kernel, grid, GAE_THREADS, 0, s, g, agg);
   V4L_CHECK_LAUNCH();
-  gae_carry_kernel<<<v4l_cdiv(E, 128), 128, 0, s>>>(g, agg, carry);
+  V4L_LAUNCH(gae_carry_kernel, v4l_cdiv(E, 128), 128, 0, s, g, agg, carry);
   V4L_CHECK_LAUNCH();
-  gae_scan_kernel<<<grid, GAE_THREADS, 0, s>>>(g, carry);
+  V4L_LAUNCH(gae_scan_kernel, grid, GAE_THREADS, 0, s, g, carry);
   V4L_CHECK_LAUNCH();
   return 0;
 }
@@ -519,14 +532,14 @@ extern "C" int v4l_select_rows(v4l_ctx* ctx, void* stream, const int32_t* flat_i
                                int32_t* cur_idx, int n) {
   V4L_REQUIRE(ctx && flat_idx && slot && cur_idx && n >= 0, "v4l_select_rows: bad argument");
   if (n == 0) return 0;
-  select_rows_kernel<<<min(v4l_cdiv(n, 256), 4 * ctx->sm_count), 256, 0, (cudaStream_t)stream>>>(flat_idx, slot, cur_idx, n);
+  V4L_LAUNCH(select_rows_kernel, min(v4l_cdiv(n, 256), 4 * ctx->sm_count), 256, 0, (cudaStream_t)stream, flat_idx, slot, cur_idx, n);
   V4L_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int v4l_slot_advance(v4l_ctx* ctx, void* stream, int32_t* slot, int32_t wrap) {
   V4L_REQUIRE(ctx && slot, "v4l_slot_advance: NULL argument");
-  slot_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(slot, wrap);
+  V4L_LAUNCH(slot_advance_kernel, 1, 1, 0, (cudaStream_t)stream, slot, wrap);
   V4L_CHECK_LAUNCH();
   return 0;
 }
@@ -534,7 +547,7 @@ extern "C" int v4l_slot_advance(v4l_ctx* ctx, void* stream, int32_t* slot, int32
 extern "C" int v4l_adv_stats(v4l_ctx* ctx, void* stream, const float* adv, const int32_t* idx, int n,
                              double* stats) {
   V4L_REQUIRE(ctx && adv && stats && n > 0, "v4l_adv_stats: bad argument");
-  adv_stats_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(adv, idx, n, stats);
+  V4L_LAUNCH(adv_stats_kernel, 1, 1024, 0, (cudaStream_t)stream, adv, idx, n, stats);
   V4L_CHECK_LAUNCH();
   return 0;
 }
@@ -548,10 +561,10 @@ extern "C" int v4l_vf_loss(v4l_ctx* ctx, void* stream, const float* values, cons
   cudaStream_t s = (cudaStream_t)stream;
   const int ctas = min(v4l_cdiv(n, LOSS_THREADS), 2 * ctx->sm_count);
   double* part = reinterpret_cast<double*>(ctx->scratch);
-  vf_loss_kernel<<<ctas, LOSS_THREADS, 0, s>>>(values, returns, old_values, idx, d_values, n, inv_global,
+  V4L_LAUNCH(vf_loss_kernel, ctas, LOSS_THREADS, 0, s, values, returns, old_values, idx, d_values, n, inv_global,
                                                clipped, clip_para, part);
   V4L_CHECK_LAUNCH();
-  vf_loss_finalize_kernel<<<1, 32, 0, s>>>(part, ctas, inv_local, info, slot);
+  V4L_LAUNCH(vf_loss_finalize_kernel, 1, 32, 0, s, part, ctas, inv_local, info, slot);
   V4L_CHECK_LAUNCH();
   return 0;
 }
@@ -568,10 +581,10 @@ extern "C" int v4l_pf_loss(v4l_ctx* ctx, void* stream, const float* mean, const 
   cudaStream_t s = (cudaStream_t)stream;
   const int ctas = min(v4l_cdiv(n, LOSS_THREADS), 2 * ctx->sm_count);
   double* part = reinterpret_cast<double*>(ctx->scratch);
-  pf_loss_kernel<<<ctas, LOSS_THREADS, 0, s>>>(mean, logstd, target_mean, target_logstd, acts, adv, idx,
+  V4L_LAUNCH(pf_loss_kernel, ctas, LOSS_THREADS, 0, s, mean, logstd, target_mean, target_logstd, acts, adv, idx,
                                                adv_stats, d_mean, n, A, inv_global, clip_para, part);
   V4L_CHECK_LAUNCH();
-  pf_loss_finalize_kernel<<<1, 32, 0, s>>>(part, ctas, logstd, adv_stats, d_logstd, n, A, inv_local,
+  V4L_LAUNCH(pf_loss_finalize_kernel, 1, 32, 0, s, part, ctas, logstd, adv_stats, d_logstd, n, A, inv_local,
                                            entropy_coeff, info, slot);
   V4L_CHECK_LAUNCH();
   return 0;
@@ -585,11 +598,11 @@ extern "C" int v4l_clip_adam(v4l_ctx* ctx, void* stream, float* param, const flo
   cudaStream_t s = (cudaStream_t)stream;
   const int ctas = (int)min((long long)2 * ctx->sm_count, (long long)((n + ADAM_THREADS - 1) / ADAM_THREADS));
   double* part = reinterpret_cast<double*>(ctx->scratch);
-  sqnorm_kernel<<<ctas, ADAM_THREADS, 0, s>>>(grad, n, part);
+  V4L_LAUNCH(sqnorm_kernel, ctas, ADAM_THREADS, 0, s, grad, n, part);
   V4L_CHECK_LAUNCH();
-  adam_kernel<<<ctas, ADAM_THREADS, 0, s>>>(param, grad, m, v, n, hyper, part, ctas);
+  V4L_LAUNCH(adam_kernel, ctas, ADAM_THREADS, 0, s, param, grad, m, v, n, hyper, part, ctas);
   V4L_CHECK_LAUNCH();
-  adam_finish_kernel<<<1, 32, 0, s>>>(hyper, part, ctas, info, slot, norm_slot);
+  V4L_LAUNCH(adam_finish_kernel, 1, 32, 0, s, hyper, part, ctas, info, slot, norm_slot);
   V4L_CHECK_LAUNCH();
   return 0;
 }

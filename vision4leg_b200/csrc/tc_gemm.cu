@@ -61,12 +61,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_bias[256];
 
+  v4l_pdl_trigger();               // the next kernel may start its prologue now
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_chunk = blockIdx.y;
-  for (int i = threadIdx.x; i < 256; i += TC_THREADS) {
-    const int n = n_chunk * p.N + i;
-    s_bias[i] = (p.bias && i < p.N && n < p.N_valid) ? p.bias[n] : 0.f;
-  }
   const int n0 = n_chunk * p.N;
   const int N = min(p.N, p.N_total - n0);                 // UMMA N of this chunk (multiple of 16)
   const uint32_t b_bytes = static_cast<uint32_t>(N) * 128u;
@@ -83,6 +80,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(&tmem_base_slot, 512);
+  // prologue done without touching global memory: now wait for the predecessor grid
+  v4l_pdl_wait();
+  for (int i = threadIdx.x; i < 256; i += TC_THREADS) {
+    const int n = n_chunk * p.N + i;
+    s_bias[i] = (p.bias && i < p.N && n < p.N_valid) ? p.bias[n] : 0.f;
+  }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -348,7 +351,7 @@ extern "C" int v4l_tc_gemm(v4l_ctx* ctx, void* stream, const v4l_tc_gemm_args* a
   }
   const int n_chunks = a->N_pad / Nchunk;
   dim3 grid(min(p.num_tiles, max(1, ctx->sm_count / n_chunks)), n_chunks);
-  tc_gemm_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
+  V4L_LAUNCH(tc_gemm_kernel, grid, TC_THREADS, smem, (cudaStream_t)stream, p);
   V4L_CHECK_LAUNCH();
   return 0;
 }
@@ -357,6 +360,7 @@ extern "C" int v4l_tc_gemm(v4l_ctx* ctx, void* stream, const v4l_tc_gemm_args* a
 namespace {
 __global__ void pack_f16_kernel(const float* __restrict__ src, const int32_t* __restrict__ index,
                                  __half* __restrict__ dst, long long n) {
+  v4l_pdl_enter();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const long long s = index ? (long long)index[i] : i;
@@ -370,7 +374,7 @@ extern "C" int v4l_pack_f16(v4l_ctx* ctx, void* stream, const float* src, const 
   V4L_REQUIRE(ctx && src && dst && n >= 0, "v4l_pack_f16: bad argument");
   if (n == 0) return 0;
   const int blocks = (int)min((long long)8 * ctx->sm_count, (long long)((n + 255) / 256));
-  pack_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, index, reinterpret_cast<__half*>(dst), n);
+  V4L_LAUNCH(pack_f16_kernel, blocks, 256, 0, (cudaStream_t)stream, src, index, reinterpret_cast<__half*>(dst), n);
   V4L_CHECK_LAUNCH();
   return 0;
 }
@@ -415,6 +419,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
   __shared__ uint64_t full_bar[4], empty_bar[4], tmem_full;
   __shared__ uint32_t tmem_base_slot;
 
+  v4l_pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int split = blockIdx.x, kt = blockIdx.y;
   const int Nmma = 64 * p.n_atoms;
@@ -449,6 +454,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
   }
   if (warp == 1) tc::tmem_alloc(&tmem_base_slot, 256);
   tc::fence_proxy_async();          // generic-proxy zero fill -> visible to the async (TMA/UMMA) proxy
+  v4l_pdl_wait();                   // smem/TMEM prologue overlapped the predecessor's tail
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -541,6 +547,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
 struct ReduceJobs { v4l_reduce_job j[V4L_MAX_JOBS]; };
 
 __global__ void tc_wgrad_reduce_kernel(const __grid_constant__ ReduceJobs jobs) {
+  v4l_pdl_enter();
   const v4l_reduce_job& J = jobs.j[blockIdx.y];
   const long long nw = (long long)J.N_valid * J.Kp;
   const long long total = nw + (J.has_bias ? J.N_valid : 0);
@@ -570,6 +577,7 @@ __global__ void tc_wgrad_reduce_kernel(const __grid_constant__ ReduceJobs jobs) 
 __global__ void __launch_bounds__(256) colsum_f16_kernel(const __half* __restrict__ dy,
                                                           const v4l_rowmap map, int M, int N,
                                                           int rows_per_cta, float* __restrict__ part) {
+  v4l_pdl_enter();
   __shared__ float red[8][256];
   const int r0 = blockIdx.x * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
   const int c = threadIdx.x & 31, w = threadIdx.x >> 5;     // 8 row-lanes x 32 column-lanes
@@ -597,6 +605,7 @@ __global__ void __launch_bounds__(256) colsum_f16_kernel(const __half* __restric
 // one warp per output column: lanes stride over the partials, fixed-order shuffle reduction
 __global__ void colsum_reduce_kernel(const float* __restrict__ part, int nparts, int N, int fold,
                                      float* __restrict__ out, float out_scale) {
+  v4l_pdl_enter();
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -692,7 +701,7 @@ extern "C" int v4l_tc_wgrad(v4l_ctx* ctx, void* stream, const v4l_tc_wgrad_args*
     attr_set = true;
   }
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
-  tc_wgrad_kernel<<<dim3(splits, ytiles), WG_THREADS, smem, s>>>(p);
+  V4L_LAUNCH(tc_wgrad_kernel, dim3(splits, ytiles), WG_THREADS, smem, s, p);
   V4L_CHECK_LAUNCH();
   v4l_reduce_job job;
   job.partial = region; job.index = a->index; job.dw = a->dw; job.dbias = a->dbias;
@@ -707,7 +716,7 @@ extern "C" int v4l_tc_wgrad(v4l_ctx* ctx, void* stream, const v4l_tc_wgrad_args*
   one.j[0] = job;
   const long long total = (long long)a->N_valid * (Kp + has_bias);
   const int rblocks = (int)min((long long)2 * ctx->sm_count, (total + 255) / 256);
-  tc_wgrad_reduce_kernel<<<dim3(rblocks, 1), 256, 0, s>>>(one);
+  V4L_LAUNCH(tc_wgrad_reduce_kernel, dim3(rblocks, 1), 256, 0, s, one);
   V4L_CHECK_LAUNCH();
   return 0;
 }
@@ -718,7 +727,7 @@ extern "C" int v4l_tc_wgrad_flush(v4l_ctx* ctx, void* stream) {
   ReduceJobs all;
   memset(&all, 0, sizeof(all));
   for (int i = 0; i < ctx->n_jobs; ++i) all.j[i] = ctx->jobs[i];
-  tc_wgrad_reduce_kernel<<<dim3(16, ctx->n_jobs), 256, 0, (cudaStream_t)stream>>>(all);
+  V4L_LAUNCH(tc_wgrad_reduce_kernel, dim3(16, ctx->n_jobs), 256, 0, (cudaStream_t)stream, all);
   ctx->n_jobs = 0;
   ctx->defer_cursor = 0;
   V4L_CHECK_LAUNCH();
@@ -738,9 +747,9 @@ extern "C" int v4l_colsum_f16(v4l_ctx* ctx, void* stream, const void* dy, const 
   // partials live past the region v4l_tc_wgrad uses? no: separate calls are stream-ordered
   float* part = ctx->scratch;
   V4L_REQUIRE((size_t)ctas * N <= ctx->scratch_elems, "v4l_colsum_f16: scratch too small");
-  colsum_f16_kernel<<<ctas, 256, 0, s>>>(reinterpret_cast<const __half*>(dy), *map, M, N, rpc, part);
+  V4L_LAUNCH(colsum_f16_kernel, ctas, 256, 0, s, reinterpret_cast<const __half*>(dy), *map, M, N, rpc, part);
   V4L_CHECK_LAUNCH();
-  colsum_reduce_kernel<<<v4l_cdiv(Nout, 8), 256, 0, s>>>(part, ctas, Nout, fold, out, out_scale);
+  V4L_LAUNCH(colsum_reduce_kernel, v4l_cdiv(Nout, 8), 256, 0, s, part, ctas, Nout, fold, out, out_scale);
   V4L_CHECK_LAUNCH();
   return 0;
 }
@@ -754,6 +763,7 @@ namespace {
 // channel = (py*4 + px)*4 + c for source pixel (4Y+py, 4X+px): the 8x8/4 conv becomes a 2x2/1
 // conv with 64-channel (128-byte) rows — exactly one TMA/UMMA swizzle atom per tap.
 __global__ void ingest_img_kernel(const float* __restrict__ img, __half* __restrict__ out, long long n_img) {
+  v4l_pdl_enter();
   const long long total = n_img * 16 * 4 * 16;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
@@ -787,6 +797,7 @@ template <typename S>
 __global__ void gather_rows_kernel(const S* __restrict__ src, const int32_t* __restrict__ idx,
                                    __half* __restrict__ dst, int rows, int scols, long long sstride,
                                    int dcols, float scale) {
+  v4l_pdl_enter();
   const long long total = (long long)rows * dcols;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
@@ -803,6 +814,7 @@ __global__ void gather_rows_kernel(const S* __restrict__ src, const int32_t* __r
 __global__ void relu_bwd_f16_kernel(const __half* __restrict__ dy, const v4l_rowmap dy_map,
                                      const __half* __restrict__ act, const v4l_rowmap act_map,
                                      __half* __restrict__ out, const v4l_rowmap out_map, int M, int N) {
+  v4l_pdl_enter();
   const long long total = (long long)M * N;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
@@ -820,7 +832,7 @@ extern "C" int v4l_ingest_img(v4l_ctx* ctx, void* stream, const float* img, void
   if (n_img == 0) return 0;
   const long long total = n_img * 1024;
   const int blocks = (int)min((long long)16 * ctx->sm_count, (total + 255) / 256);
-  ingest_img_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(img, reinterpret_cast<__half*>(out_s2d), n_img);
+  V4L_LAUNCH(ingest_img_kernel, blocks, 256, 0, (cudaStream_t)stream, img, reinterpret_cast<__half*>(out_s2d), n_img);
   V4L_CHECK_LAUNCH();
   return 0;
 }
@@ -834,9 +846,9 @@ extern "C" int v4l_gather_rows_f16(v4l_ctx* ctx, void* stream, const void* src, 
   const int blocks = (int)min((long long)8 * ctx->sm_count, (total + 255) / 256);
   cudaStream_t s = (cudaStream_t)stream;
   if (src_is_f32)
-    gather_rows_kernel<float><<<blocks, 256, 0, s>>>((const float*)src, idx, (__half*)dst, rows, src_cols, src_stride, dst_cols, scale);
+    V4L_LAUNCH((gather_rows_kernel<float>), blocks, 256, 0, s, (const float*)src, idx, (__half*)dst, rows, src_cols, src_stride, dst_cols, scale);
   else
-    gather_rows_kernel<__half><<<blocks, 256, 0, s>>>((const __half*)src, idx, (__half*)dst, rows, src_cols, src_stride, dst_cols, scale);
+    V4L_LAUNCH((gather_rows_kernel<__half>), blocks, 256, 0, s, (const __half*)src, idx, (__half*)dst, rows, src_cols, src_stride, dst_cols, scale);
   V4L_CHECK_LAUNCH();
   return 0;
 }
@@ -849,7 +861,7 @@ extern "C" int v4l_relu_bwd_f16(v4l_ctx* ctx, void* stream, const void* dy, cons
   const long long total = (long long)M * N;
   if (total <= 0) return 0;
   const int blocks = (int)min((long long)8 * ctx->sm_count, (total + 255) / 256);
-  relu_bwd_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+  V4L_LAUNCH(relu_bwd_f16_kernel, blocks, 256, 0, (cudaStream_t)stream, 
     (const __half*)dy, *dy_map, (const __half*)act, *act_map, (__half*)out, *out_map, M, N);
   V4L_CHECK_LAUNCH();
   return 0;

@@ -20,6 +20,7 @@ template <typename T_>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_fwd_kernel(const T_* __restrict__ qkv, T_* __restrict__ o, float* __restrict__ p_out,
                 int T, int d, int nh) {
+  v4l_pdl_enter();
   extern __shared__ float sm[];
   const int dp = d + 1, hd = d / nh;
   float* q = sm;
@@ -73,6 +74,7 @@ template <typename T_>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_kernel(const T_* __restrict__ qkv, const float* __restrict__ p_in,
                 const T_* __restrict__ d_o, T_* __restrict__ d_qkv, int T, int d, int nh) {
+  v4l_pdl_enter();
   extern __shared__ float sm[];
   const int dp = d + 1, hd = d / nh;
   float* q = sm;
@@ -142,6 +144,7 @@ ln_fwd_kernel(const T_* __restrict__ a, const T_* __restrict__ res,
               const float* __restrict__ gamma, const float* __restrict__ beta,
               T_* __restrict__ y, float* __restrict__ z, float* __restrict__ stats,
               int rows, int d, float eps) {
+  v4l_pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -187,6 +190,7 @@ __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const T_* __restrict__ dy, const float* __restrict__ z,
               const float* __restrict__ stats, const float* __restrict__ gamma,
               T_* __restrict__ dz, float* __restrict__ part, int rows, int d, int rows_per_cta) {
+  v4l_pdl_enter();
   __shared__ float red[8][2][32 * LN_MAXPER];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
@@ -246,6 +250,7 @@ ln_bwd_kernel(const T_* __restrict__ dy, const float* __restrict__ z,
 // one warp per (gamma|beta, column): lanes stride over the CTA partials
 __global__ void ln_bwd_reduce_kernel(const float* __restrict__ part, int nparts, int d,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta, float out_scale) {
+  v4l_pdl_enter();
   const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (e >= 2 * d) return;
@@ -260,6 +265,7 @@ __global__ void ln_bwd_reduce_kernel(const float* __restrict__ part, int nparts,
 template <typename T_>
 __global__ void pool_fwd_kernel(const T_* __restrict__ tok, T_* __restrict__ out, int B, int T,
                                 int d, int mode) {
+  v4l_pdl_enter();
   const int od = mode == 0 ? 2 * d : d;
   const long long total = (long long)B * od;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
@@ -283,6 +289,7 @@ __global__ void pool_fwd_kernel(const T_* __restrict__ tok, T_* __restrict__ out
 template <typename T_>
 __global__ void pool_bwd_kernel(const T_* __restrict__ dout, T_* __restrict__ dtok, int B, int T,
                                 int d, int mode) {
+  v4l_pdl_enter();
   const int od = mode == 0 ? 2 * d : d;
   const long long total = (long long)B * T * d;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
@@ -317,7 +324,7 @@ static int attn_fwd_impl(v4l_ctx* ctx, void* stream, const void* qkv, void* o, f
   const size_t smem = sizeof(float) * (3 * T * (d + 1) + n_head * T * T);
   if (smem > 48 * 1024)
     V4L_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attn_fwd_kernel<T_><<<B, ATT_THREADS, smem, (cudaStream_t)stream>>>((const T_*)qkv, (T_*)o, p, T, d, n_head);
+  V4L_LAUNCH((attn_fwd_kernel<T_>), B, ATT_THREADS, smem, (cudaStream_t)stream, (const T_*)qkv, (T_*)o, p, T, d, n_head);
   V4L_CHECK_LAUNCH();
   return 0;
 }
@@ -331,7 +338,7 @@ static int attn_bwd_impl(v4l_ctx* ctx, void* stream, const void* qkv, const floa
   const size_t smem = sizeof(float) * (4 * T * (d + 1) + 2 * n_head * T * T);
   if (smem > 48 * 1024)
     V4L_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attn_bwd_kernel<T_><<<B, ATT_THREADS, smem, (cudaStream_t)stream>>>((const T_*)qkv, p, (const T_*)d_o, (T_*)d_qkv, T, d, n_head);
+  V4L_LAUNCH((attn_bwd_kernel<T_>), B, ATT_THREADS, smem, (cudaStream_t)stream, (const T_*)qkv, p, (const T_*)d_o, (T_*)d_qkv, T, d, n_head);
   V4L_CHECK_LAUNCH();
   return 0;
 }
@@ -342,7 +349,7 @@ static int ln_fwd_impl(v4l_ctx* ctx, void* stream, const void* a, const void* re
   V4L_REQUIRE(ctx && a && gamma && beta && y, "v4l_ln_fwd: NULL argument");
   V4L_REQUIRE(d > 0 && d <= 32 * LN_MAXPER, "v4l_ln_fwd: d=%d unsupported (max %d)", d, 32 * LN_MAXPER);
   if (rows == 0) return 0;
-  ln_fwd_kernel<T_><<<v4l_cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>((const T_*)a, (const T_*)res, gamma, beta,
+  V4L_LAUNCH((ln_fwd_kernel<T_>), v4l_cdiv(rows, 8), 256, 0, (cudaStream_t)stream, (const T_*)a, (const T_*)res, gamma, beta,
                                                                           (T_*)y, z, stats, rows, d, eps);
   V4L_CHECK_LAUNCH();
   return 0;
@@ -360,9 +367,9 @@ static int ln_bwd_impl(v4l_ctx* ctx, void* stream, const void* dy, const float* 
   ctas = v4l_cdiv(rows, rpc);
   V4L_REQUIRE((size_t)ctas * 2 * d <= ctx->scratch_elems, "v4l_ln_bwd: scratch too small");
   cudaStream_t s = (cudaStream_t)stream;
-  ln_bwd_kernel<T_><<<ctas, 256, 0, s>>>((const T_*)dy, z, stats, gamma, (T_*)dz, ctx->scratch, rows, d, rpc);
+  V4L_LAUNCH((ln_bwd_kernel<T_>), ctas, 256, 0, s, (const T_*)dy, z, stats, gamma, (T_*)dz, ctx->scratch, rows, d, rpc);
   V4L_CHECK_LAUNCH();
-  ln_bwd_reduce_kernel<<<v4l_cdiv(2 * d, 8), 256, 0, s>>>(ctx->scratch, ctas, d, dgamma, dbeta, out_scale);
+  V4L_LAUNCH(ln_bwd_reduce_kernel, v4l_cdiv(2 * d, 8), 256, 0, s, ctx->scratch, ctas, d, dgamma, dbeta, out_scale);
   V4L_CHECK_LAUNCH();
   return 0;
 }
@@ -374,8 +381,8 @@ static int pool_impl(v4l_ctx* ctx, void* stream, const void* in, void* out, int 
   const long long total = fwd ? (long long)B * (mode == 0 ? 2 * d : d) : (long long)B * T * d;
   if (total == 0) return 0;
   const int blocks = (int)min((long long)8 * ctx->sm_count, (total + 255) / 256);
-  if (fwd) pool_fwd_kernel<T_><<<blocks, 256, 0, (cudaStream_t)stream>>>((const T_*)in, (T_*)out, B, T, d, mode);
-  else     pool_bwd_kernel<T_><<<blocks, 256, 0, (cudaStream_t)stream>>>((const T_*)in, (T_*)out, B, T, d, mode);
+  if (fwd) V4L_LAUNCH((pool_fwd_kernel<T_>), blocks, 256, 0, (cudaStream_t)stream, (const T_*)in, (T_*)out, B, T, d, mode);
+  else     V4L_LAUNCH((pool_bwd_kernel<T_>), blocks, 256, 0, (cudaStream_t)stream, (const T_*)in, (T_*)out, B, T, d, mode);
   V4L_CHECK_LAUNCH();
   return 0;
 }
