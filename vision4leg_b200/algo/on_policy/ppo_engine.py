@@ -340,7 +340,7 @@ class PPOUpdateEngine:
     ops.gather_rows_f16(r["state"], True, idx, st, B, self.S, self.S, self.plan_pf.Sp)
     # the frozen target policy only depends on the minibatch rows: its forward runs on the side
     # stream, concurrently with the whole critic phase (a parallel branch of the captured graph)
-    with ops.fork():
+    with ops.fork(1):
       self.plan_t.forward(self.t_flat, imgs, idx, st, B, b["tmean"])
     # ---- critic
     self.plan_vf.pack(self.vf_flat)
@@ -355,7 +355,7 @@ class PPOUpdateEngine:
     # ---- actor
     self.plan_pf.pack(self.pf_flat)
     self.plan_pf.forward(self.pf_flat, imgs, idx, st, B, b["mean"])
-    ops.join()
+    ops.join(1)
     ops.pf_loss(b["mean"], self.logstd, b["tmean"], self.t_logstd, r["acts"], r["advs"], idx, b["stats"],
                 b["d_mean"], self.G_pf["logstd"], B, self.A, inv_global, inv_local, self.clip_para,
                 self.entropy_coeff, self._info, self._slot)

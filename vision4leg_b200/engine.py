@@ -80,17 +80,26 @@ class Ops:
 
   # ---- side stream: independent work (weight gradients, frozen-target forward) leaves the
   #      critical path; under CUDA-graph capture this becomes a parallel branch of the graph
-  def fork(self):
-    side = getattr(self, "_side", None)
-    if side is None:
-      side = self._side = torch.cuda.Stream(device=self.device)
-    side.wait_stream(torch.cuda.current_stream(self.device))
+  def _side_stream(self, which):
+    sides = self.__dict__.setdefault("_sides", {})
+    if which not in sides:
+      sides[which] = torch.cuda.Stream(device=self.device)
+    return sides[which]
+
+  def fork(self, which=0):
+    """Context manager: launches inside go to side stream `which`, ordered after everything
+    issued so far on the current stream."""
+    side = self._side_stream(which)
+    cur = torch.cuda.current_stream(self.device)
+    if cur != side:
+      side.wait_stream(cur)
     return torch.cuda.stream(side)
 
-  def join(self):
-    side = getattr(self, "_side", None)
-    if side is not None:
-      torch.cuda.current_stream(self.device).wait_stream(side)
+  def join(self, which=0):
+    side = self._side_stream(which)
+    cur = torch.cuda.current_stream(self.device)
+    if cur != side:
+      cur.wait_stream(side)
 
   # ---- GEMMs
   def gemm(self, a, a_map, koff, b, b_sk, b_sn, bias, c, c_map, M, N, K, flags=0, mask=None,

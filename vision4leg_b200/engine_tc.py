@@ -259,14 +259,17 @@ class LocoPlanTC(_PlanTC):
     out fp32 [B,out_dim].  `flat` = the fp32 bucket the layout offsets refer to (biases, LN)."""
     ops, T, d = self.ops, self.T, self.d
     self._flat, self._B, self._imgs, self._idx, self._st = flat, B, imgs, idx, st
-    a3 = self._trunk_fwd(flat, imgs, idx, B, "encoder.depth_visual_base.layers.")
-    # tokens
     tok = self.buf("tok0", (B, T, d))
-    self._lin_fwd(flat, "encoder.depth_up_conv.weight", a3, B * 16, 64, tok, RM.slots(16, T, d, 1), False)
     s1 = self.buf("s1", (B, 256)); s2 = self.buf("s2", (B, 256))
-    self._lin_fwd(flat, self.k_base[0], st, B, self.Sp, s1, RM.dense(256), True)
-    self._lin_fwd(flat, self.k_base[1], s1, B, 256, s2, RM.dense(256), True)
-    self._lin_fwd(flat, "encoder.state_projector.projection.0.weight", s2, B, 256, tok, RM.slots(1, T, d, 0), True)
+
+    def state_branch():      # proprio MLP -> token 0: independent of the conv trunk
+      self._lin_fwd(flat, self.k_base[0], st, B, self.Sp, s1, RM.dense(256), True)
+      self._lin_fwd(flat, self.k_base[1], s1, B, 256, s2, RM.dense(256), True)
+      self._lin_fwd(flat, "encoder.state_projector.projection.0.weight", s2, B, 256, tok, RM.slots(1, T, d, 0), True)
+    self._side(state_branch)
+    a3 = self._trunk_fwd(flat, imgs, idx, B, "encoder.depth_visual_base.layers.")
+    self._lin_fwd(flat, "encoder.depth_up_conv.weight", a3, B * 16, 64, tok, RM.slots(16, T, d, 1), False)
+    ops.join()
     R = B * T
     x = tok
     self._layers = []
@@ -342,12 +345,15 @@ class LocoPlanTC(_PlanTC):
     # proprio token -> state MLP
     ds = self.buf("ds", (B, d))
     smap = RM.slots(1, T, d, 0)
-    ops.relu_bwd_f16(dx, smap, tok, smap, ds, RM.dense(d), B, d)
     s1, s2 = ws[("s1", B, 256)], ws[("s2", B, 256)]
     ds2 = self.buf("ds2", (B, 256)); ds1 = self.buf("ds1", (B, 256))
-    self._lin_bwd(gflat, "encoder.state_projector.projection.0.weight", s2, 256, ds, d, B, ds2, RM.dense(256), mask=s2)
-    self._lin_bwd(gflat, self.k_base[1], s1, 256, ds2, 256, B, ds1, RM.dense(256), mask=s1)
-    self._lin_bwd(gflat, self.k_base[0], self._st, self.Sp, ds1, 256, B, need_dx=False)
+
+    def state_branch():      # whole proprio-branch backward off the critical path
+      ops.relu_bwd_f16(dx, smap, tok, smap, ds, RM.dense(d), B, d)
+      self._lin_bwd(gflat, "encoder.state_projector.projection.0.weight", s2, 256, ds, d, B, ds2, RM.dense(256), mask=s2)
+      self._lin_bwd(gflat, self.k_base[1], s1, 256, ds2, 256, B, ds1, RM.dense(256), mask=s1)
+      self._lin_bwd(gflat, self.k_base[0], self._st, self.Sp, ds1, 256, B, need_dx=False)
+    self._side(state_branch)
     # depth tokens -> 1x1 up-conv (dY is the strided [B,16,64] window of the token gradient)
     a3 = ws[("a3", B, 16, 64)]
     up = "encoder.depth_up_conv.weight"
