@@ -27,6 +27,9 @@ FAMILIES = {
   "loco": (93, 12),
   "nature": (84, 6),
   "mlp": (84, 6),
+  # vision-only variants (starter/ppo_locotransformer_vision_only.py, ppo_nature_cnn_vision_only.py)
+  "vit": (0, 6),
+  "nvo": (0, 6),
 }
 
 
@@ -74,6 +77,16 @@ def build_reference_nets(networks, policies, family, S, A):
       encoder=enc, state_input_shape=S, visual_input_shape=(4, 64, 64), output_shape=A, **net)
     vf = networks.ImpalaEncoderProjNet(
       encoder=enc, state_input_shape=S, visual_input_shape=(4, 64, 64), output_shape=1, **net)
+  elif family == "vit":
+    enc = networks.TransformerEncoder(in_channels=4, hidden_shapes=[256, 256], visual_dim=256)
+    pf = policies.GaussianContPolicyTransformer(
+      encoder=enc, visual_input_shape=(4, 64, 64), output_shape=A, **net)
+    vf = networks.Transformer(encoder=enc, visual_input_shape=(4, 64, 64), output_shape=1, **net)
+  elif family == "nvo":
+    enc = networks.NatureEncoder(in_channels=4, hidden_shapes=[256, 256], visual_dim=256)
+    pf = policies.GaussianContPolicyNatureEncoderProj(
+      encoder=enc, visual_input_shape=(4, 64, 64), output_shape=A, **net)
+    vf = networks.NatureEncoderProjNet(encoder=enc, visual_input_shape=(4, 64, 64), output_shape=1, **net)
   else:
     net = {"append_hidden_shapes": [256, 256], "hidden_shapes": [256, 256],
            "base_type": networks.MLPBase}
@@ -167,7 +180,12 @@ def golden_family(mods, family):
     out["fwd/ent"] = upd["ent"].numpy()
     out["fwd/value"] = vf(obs).numpy()
     out["fwd/eval_act"] = pf.eval_act(obs)
-    out["fwd/value_1d"] = vf(obs[0]).numpy()      # 1-D input path
+    try:
+      out["fwd/value_1d"] = vf(obs[0]).numpy()    # 1-D input path
+    except TypeError:
+      # NatureEncoder.forward builds torch.Size([np.prod(())]) = [1.0] for un-batched input, which
+      # numpy >= 2 / torch 2.11 reject: the reference itself cannot run this case for `nvo`
+      pass
 
   # ---- (2) one PPO.update(batch) on B=16 (T=4 rows x E=4)
   T, E, Bm = 4, 4, 16

@@ -168,12 +168,36 @@ def nature_forward(P, x, S):
   return head(P, "seq_append_fcs.", torch.cat([vis, s], dim=-1))
 
 
+def vit_forward(P, x, S=0, n_head=1):
+  """Transformer.forward + TransformerEncoder.forward, vision only (reference nets.py:868-906,
+  base.py:428-494): 16 depth tokens, mean-pooled."""
+  B = x.shape[0]
+  img = x.reshape(B, 4, 64, 64)
+  feat = nature_cnn(P, "encoder.depth_visual_base.", img)
+  up = F.conv2d(feat, P["encoder.depth_up_conv.weight"], P["encoder.depth_up_conv.bias"])
+  tok = up.reshape(B, up.shape[1], 16).permute(0, 2, 1)
+  l = 0
+  while ("visual_append_layers.%d.linear1.weight" % l) in P:
+    tok = transformer_layer(P, "visual_append_layers.%d." % l, tok, n_head)
+    l += 1
+  return head(P, "visual_seq_append_fcs.", tok.mean(1))
+
+
+def nvo_forward(P, x, S=0):
+  """NatureEncoderProjNet.forward with a flattening NatureEncoder (reference nets.py:177-191,
+  base.py:334-342)."""
+  B = x.shape[0]
+  feat = nature_cnn(P, "encoder.", x.reshape(B, 4, 64, 64)).reshape(B, 1024)
+  return head(P, "seq_append_fcs.", feat)
+
+
 def mlp_forward(P, x, S=None):
   """Net.forward with base_type=MLPBase (reference nets.py:51-55)."""
   return head(P, "seq_append_fcs.", mlp_base(P, "base.", x))
 
 
-FORWARD = {"loco": loco_forward, "nature": nature_forward, "mlp": mlp_forward}
+FORWARD = {"loco": loco_forward, "nature": nature_forward, "mlp": mlp_forward, "vit": vit_forward,
+           "nvo": nvo_forward}
 
 
 def gaussian_update(mean, logstd_param, acts):
@@ -263,8 +287,8 @@ class PPOOracle:
     self.current_epoch = 0
 
   def _forward(self, P, x):
-    if self.family == "loco":
-      return loco_forward(P, x, self.S, self.n_head)
+    if self.family in ("loco", "vit"):
+      return self.fwd(P, x, self.S, self.n_head)
     return self.fwd(P, x, self.S)
 
   def values(self, obs):

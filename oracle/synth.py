@@ -170,6 +170,16 @@ def mlp_net_spec(out, din=256, hidden=(256, 256)):
   return _head_spec("seq_append_fcs.", din, hidden, out)
 
 
+def vit_encoder_spec(token_dim=64):
+  return (_nature_spec("encoder.depth_visual_base.") +
+          [("encoder.depth_up_conv.weight", (token_dim, 64, 1, 1)), ("encoder.depth_up_conv.bias", (token_dim,))])
+
+
+def vit_net_spec(out, n_layers=2, ff=256, hidden=(256, 256), token_dim=64):
+  spec = [kv for kv in loco_net_spec(out, n_layers, ff, hidden, token_dim) if not kv[0].startswith("visual_seq_append_fcs.")]
+  return spec + _head_spec("visual_seq_append_fcs.", token_dim, hidden, out)
+
+
 def make_family_weights(seed, family, S, A):
   """Returns (pf_sd, vf_sd) numpy state dicts with the *shared* tensors being the same
   arrays in both (encoder.* for loco/nature — reference starter/ppo_locotransformer.py:79-100;
@@ -182,6 +192,14 @@ def make_family_weights(seed, family, S, A):
     enc = make_weights(seed, nature_encoder_spec(S))
     pf = make_weights(seed + 1, [("logstd", (A,))] + nature_net_spec(A))
     vf = make_weights(seed + 2, nature_net_spec(1))
+  elif family == "vit":
+    enc = make_weights(seed, vit_encoder_spec())
+    pf = make_weights(seed + 1, [("logstd", (A,))] + vit_net_spec(A))
+    vf = make_weights(seed + 2, vit_net_spec(1))
+  elif family == "nvo":
+    enc = make_weights(seed, _nature_spec("encoder."))
+    pf = make_weights(seed + 1, [("logstd", (A,))] + _head_spec("seq_append_fcs.", 1024, (256, 256), A))
+    vf = make_weights(seed + 2, _head_spec("seq_append_fcs.", 1024, (256, 256), 1))
   elif family == "mlp":
     enc = make_weights(seed, mlp_base_spec(S))
     pf = make_weights(seed + 1, [("logstd", (A,))] + mlp_net_spec(A))

@@ -10,7 +10,7 @@ import numpy as np
 from oracle import synth
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-FAMILIES = {"loco": (93, 12), "nature": (84, 6), "mlp": (84, 6)}
+FAMILIES = {"loco": (93, 12), "nature": (84, 6), "mlp": (84, 6), "vit": (0, 6), "nvo": (0, 6)}
 
 INFO_KEYS = ["advs/mean", "advs/std", "advs/max", "advs/min", "Training/vf_loss", "grad_norm/vf",
              "Training/policy_loss", "logprob/mean", "logprob/std", "logprob/max", "logprob/min",

@@ -28,6 +28,16 @@ def build_nets(family, S, A):
       encoder=enc, state_input_shape=S, visual_input_shape=(4, 64, 64), output_shape=A, **net)
     vf = networks.ImpalaEncoderProjNet(
       encoder=enc, state_input_shape=S, visual_input_shape=(4, 64, 64), output_shape=1, **net)
+  elif family == "vit":
+    enc = networks.TransformerEncoder(in_channels=4, hidden_shapes=[256, 256], visual_dim=256)
+    pf = policies.GaussianContPolicyTransformer(
+      encoder=enc, visual_input_shape=(4, 64, 64), output_shape=A, **net)
+    vf = networks.Transformer(encoder=enc, visual_input_shape=(4, 64, 64), output_shape=1, **net)
+  elif family == "nvo":
+    enc = networks.NatureEncoder(in_channels=4, hidden_shapes=[256, 256], visual_dim=256)
+    pf = policies.GaussianContPolicyNatureEncoderProj(
+      encoder=enc, visual_input_shape=(4, 64, 64), output_shape=A, **net)
+    vf = networks.NatureEncoderProjNet(encoder=enc, visual_input_shape=(4, 64, 64), output_shape=1, **net)
   elif family == "mlp":
     net = {"append_hidden_shapes": [256, 256], "hidden_shapes": [256, 256], "base_type": networks.MLPBase}
     pf = policies.GaussianContPolicyBasicBias(input_shape=S, output_shape=A, **net)

@@ -12,7 +12,7 @@ from tests._harness import build_nets, fill_buffer
 from oracle import synth
 
 
-@pytest.mark.parametrize("family", ["loco", "nature", "mlp"])
+@pytest.mark.parametrize("family", ["loco", "nature", "mlp", "vit", "nvo"])
 def test_init_parity_with_reference(family):
   G = g.load(family)
   S, A = g.FAMILIES[family]

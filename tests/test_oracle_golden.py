@@ -35,7 +35,7 @@ def _oracle(family, **kw):
   return po.PPOOracle(family, pf, vf, S, **kw)
 
 
-@pytest.mark.parametrize("family", ["loco", "nature", "mlp"])
+@pytest.mark.parametrize("family", ["loco", "nature", "mlp", "vit", "nvo"])
 def test_forward_matches_reference(family):
   G = g.load(family)
   orc = _oracle(family)
@@ -48,10 +48,11 @@ def test_forward_matches_reference(family):
   assert g.rel_err(value.numpy(), G["fwd/value"]) < 2e-5
   assert g.rel_err(lp.numpy(), G["fwd/log_prob"]) < 2e-5
   assert g.rel_err(ent.numpy(), G["fwd/ent"]) < 1e-6
-  assert g.rel_err(orc.values(obs_t[:1]).numpy()[0], G["fwd/value_1d"]) < 2e-5
+  if "fwd/value_1d" in G:
+    assert g.rel_err(orc.values(obs_t[:1]).numpy()[0], G["fwd/value_1d"]) < 2e-5
 
 
-@pytest.mark.parametrize("family", ["loco", "nature", "mlp"])
+@pytest.mark.parametrize("family", ["loco", "nature", "mlp", "vit", "nvo"])
 def test_one_update_matches_reference(family):
   G = g.load(family)
   orc = _oracle(family, batch_size=16, opt_epochs=1)
@@ -75,7 +76,7 @@ def test_clipped_value_loss_matches_reference(family):
   g.check_summary(G, "updclip/vf", [(k, v.numpy()) for k, v in orc.vf.items()], 2e-4)
 
 
-@pytest.mark.parametrize("family", ["loco", "nature", "mlp"])
+@pytest.mark.parametrize("family", ["loco", "nature", "mlp", "vit", "nvo"])
 def test_update_per_epoch_matches_reference(family):
   G = g.load(family)
   orc = _oracle(family, batch_size=16, opt_epochs=2)

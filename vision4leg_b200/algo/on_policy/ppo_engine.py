@@ -191,7 +191,8 @@ class PPOUpdateEngine:
     expect = self.S + (engine.IMG_ELEMS if self.has_img else 0)
     if D != expect:
       raise V4LError("rollout observation width %d, expected %d" % (D, expect))
-    self.ops.h2d_2d(r["state"], self.S * 4, obs.data_ptr(), D * 4, self.S * 4, T * E)
+    if self.S:
+      self.ops.h2d_2d(r["state"], self.S * 4, obs.data_ptr(), D * 4, self.S * 4, T * E)
     if self.has_img:
       self.ops.h2d_2d(r["img"], engine.IMG_ELEMS * 4, obs.data_ptr() + self.S * 4, D * 4,
                       engine.IMG_ELEMS * 4, T * E)

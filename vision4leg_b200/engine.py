@@ -681,6 +681,52 @@ class LocoPlan(_Plan):
     self.trunk.backward(P, G, da3)
 
 
+class NatureVOPlan(_Plan):
+  """Vision-only NatureCNN: flatten(conv trunk) -> MLP head (reference nets.py:133-191 with a
+  flattening NatureEncoder, starter/ppo_nature_cnn_vision_only.py)."""
+  family = "nvo"
+
+  def __init__(self, ops, S, out_dim):
+    super().__init__(ops, out_dim)
+    self.S = 0
+    self.trunk = _ConvTrunk(self, "encoder.")
+    c, p = np.meshgrid(np.arange(64), np.arange(16), indexing="ij")
+    self.kflat = _i32((p * 64 + c).ravel(), self.device)      # torch flatten (c,p) over our (p,c)
+
+  def forward(self, P, inp, out):
+    B = inp.B
+    self._inp = inp
+    a3 = self.trunk.forward(P, inp)
+    self._hk = _head_keys(P, "seq_append_fcs.")
+    self._hacts = self._stack_fwd(P, self._hk, a3, RM.dense(1024), self.kflat, B, 1024, "h", False, out,
+                                  RM.dense(self.out_dim))
+    return out
+
+  def backward(self, P, G, d_out):
+    B = self._inp.B
+    a3 = self.trunk.a3
+    da3 = self.buf("da3", B, 16, 64)
+    # first head layer: dgrad scattered back to (p,c) order and masked by the trunk's ReLU
+    keys = self._hk
+    acts = self._hacts
+    dy, dy_map = d_out, RM.dense(self.out_dim)
+    for i in reversed(range(len(keys))):
+      wk, bk = keys[i]
+      w = P[wk]
+      N, K = w.shape
+      if i > 0:
+        a, a_map, _ = acts[i - 1]
+        self.ops.linear_wgrad(dy, dy_map, a, a_map, None, G[wk], G[bk], B, N, K)
+        dprev = self.buf("h_d%d" % (i - 1), B, K)
+        self.ops.linear_dgrad(dy, dy_map, w, dprev, RM.dense(K), B, N, K, mask=a, mask_map=a_map)
+        dy, dy_map = dprev, RM.dense(K)
+      else:
+        self.ops.linear_wgrad(dy, dy_map, a3, RM.dense(1024), self.kflat, G[wk], G[bk], B, N, K)
+        self.ops.linear_dgrad(dy, dy_map, w, da3, RM.dense(1024), B, N, K, mask=a3, mask_map=RM.dense(1024),
+                              dx_koff=self.kflat)
+    self.trunk.backward(P, G, da3)
+
+
 def make_plan(family, ops, S, out_dim, **kw):
   if family == "mlp":
     return MLPPlan(ops, S, out_dim)
@@ -690,4 +736,6 @@ def make_plan(family, ops, S, out_dim, **kw):
     return LocoPlan(ops, S, out_dim, **kw)
   if family == "vit":
     return LocoPlan(ops, 0, out_dim, has_state=False, **kw)
+  if family == "nvo":
+    return NatureVOPlan(ops, 0, out_dim)
   raise ValueError("unknown family %r" % (family,))

@@ -1,5 +1,6 @@
 from .nets import *      # noqa: F401,F403
-from .nets import Net, ImpalaEncoderProjNet, LocoTransformer, Transformer, ZeroNet  # noqa: F401
+from .nets import (Net, ImpalaEncoderProjNet, NatureEncoderProjNet, LocoTransformer,  # noqa: F401
+                   Transformer, ZeroNet)
 from .base import *      # noqa: F401,F403
 from .base import (MLPBase, NatureEncoder, NatureFuseEncoder, TransformerEncoder,  # noqa: F401
                    LocoTransformerEncoder, RLProjection, Flatten)

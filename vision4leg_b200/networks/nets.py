@@ -183,6 +183,33 @@ class ImpalaEncoderProjNet(_CudaNet, nn.Module):
     return self._net_forward(state)
 
 
+class NatureEncoderProjNet(_CudaNet, nn.Module):
+  """Vision-only: flattening NatureEncoder -> MLP head; reference nets.py:133-191
+  (starter/ppo_nature_cnn_vision_only.py)."""
+  _family, _has_img, _state_dim = "nvo", True, 0
+
+  def __init__(self, encoder, output_shape, visual_input_shape, append_hidden_shapes=[],
+               append_hidden_init_func=init.basic_init, net_last_init_func=init.uniform_init,
+               activation_func=nn.ReLU, add_ln=False, detach=False, **kwargs):
+    super().__init__()
+    if not isinstance(encoder, base.NatureEncoder) or not any(isinstance(m, base.Flatten) for m in encoder.layers):
+      raise NotImplementedError("NatureEncoderProjNet needs a flattening NatureEncoder")
+    if detach:
+      raise NotImplementedError("detach=True is unused by the shipped configs")
+    self.encoder = encoder
+    self.add_ln, self.detach = add_ln, detach
+    self.visual_input_shape = visual_input_shape
+    self.activation_func = activation_func
+    self.seq_append_fcs = _append_fcs(encoder.output_dim, append_hidden_shapes, output_shape,
+                                      append_hidden_init_func, net_last_init_func, activation_func, add_ln)
+    self.normalizer = None
+    self._out_dim = output_shape
+    _check_visual(visual_input_shape)
+
+  def forward(self, x):
+    return self._net_forward(x)
+
+
 def _check_visual(shape):
   if tuple(shape) != (4, 64, 64):
     raise NotImplementedError("visual_input_shape must be (4, 64, 64), got %r" % (tuple(shape),))

@@ -82,10 +82,13 @@ GaussianContPolicyBasicBias = _gaussian_policy(
   networks.Net, "Gaussian policy over Net (reference continuous_policy.py:239-254)")
 GaussianContPolicyImpalaEncoderProj = _gaussian_policy(
   networks.ImpalaEncoderProjNet, "reference continuous_policy.py:275-290")
+GaussianContPolicyNatureEncoderProj = _gaussian_policy(
+  networks.NatureEncoderProjNet, "reference continuous_policy.py:257-272")
 GaussianContPolicyTransformer = _gaussian_policy(
   networks.Transformer, "reference continuous_policy.py:461-475")
 GaussianContPolicyLocoTransformer = _gaussian_policy(
   networks.LocoTransformer, "reference continuous_policy.py:478-492")
 for _n in ("GaussianContPolicyBasicBias", "GaussianContPolicyImpalaEncoderProj",
+           "GaussianContPolicyNatureEncoderProj",
            "GaussianContPolicyTransformer", "GaussianContPolicyLocoTransformer"):
   globals()[_n].__name__ = globals()[_n].__qualname__ = _n
