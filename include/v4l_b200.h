@@ -245,7 +245,8 @@ int v4l_pack_f16(v4l_ctx* ctx, void* stream, const float* src, const int32_t* in
 
 /* fp32 CHW [n,4,64,64] depth stack -> f16 4x4 space-to-depth NHWC [n,16,16,64]
  * (channel = (py*4+px)*4+c): the layout the tensor-core conv1 reads (one swizzle atom per tap) */
-int v4l_ingest_img(v4l_ctx* ctx, void* stream, const float* img, void* out_s2d, int64_t n_img);
+int v4l_ingest_img(v4l_ctx* ctx, void* stream, const float* img, void* out_s2d, int64_t n_img,
+                   const int32_t* idx /* optional list of the n_img image rows to convert */);
 /* dst_f16[i, 0:dst_cols] = src[idx ? idx[i] : i, 0:src_cols] zero padded (proprio rows -> K-padded
  * f16 operand; also fp32 -> f16 conversion of loss gradients)                                */
 int v4l_gather_rows_f16(v4l_ctx* ctx, void* stream, const void* src, int src_is_f32,

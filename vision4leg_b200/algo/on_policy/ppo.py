@@ -54,7 +54,7 @@ class PPO(A2C):
 
   def update_per_epoch(self):
     eng, buf = self.engine, self.replay_buffer
-    eng.load_rollout(buf)
+    eng.load_rollout(buf, stream_obs=True)
     sample = buf.last_sample(["next_obs", "terminals"])
     eng.compute_advantages(sample["next_obs"], sample["terminals"], self.discount, self.tau,
                            buf.time_limit_filter, self.gae)

@@ -179,8 +179,11 @@ class PPOUpdateEngine:
     self._graphs.clear()            # captured graphs hold the old planes' addresses
     return r
 
-  def load_rollout(self, buf):
-    """Pinned host rows -> device planes (async on the current stream)."""
+  def load_rollout(self, buf, stream_obs=False):
+    """Pinned host rows -> device planes (async on the current stream).  With stream_obs the
+    observation rows are NOT copied here: run_epoch streams them on a copy stream in the order the
+    first opt-epoch consumes them, so the 1 GB host->device transfer overlaps the first
+    minibatches instead of preceding them."""
     host = buf._host
     T, E = buf._max_replay_buffer_size, buf.env_nums
     r = self._roll
@@ -191,14 +194,14 @@ class PPOUpdateEngine:
     expect = self.S + (engine.IMG_ELEMS if self.has_img else 0)
     if D != expect:
       raise V4LError("rollout observation width %d, expected %d" % (D, expect))
-    if self.S:
-      self.ops.h2d_2d(r["state"], self.S * 4, obs.data_ptr(), D * 4, self.S * 4, T * E)
-    if self.has_img:
-      self.ops.h2d_2d(r["img"], engine.IMG_ELEMS * 4, obs.data_ptr() + self.S * 4, D * 4,
-                      engine.IMG_ELEMS * 4, T * E)
+    self._pending_obs = None
+    if stream_obs:
+      self._pending_obs = (obs, D)
+    else:
+      self._copy_obs_rows(obs, D, 0, T * E)
+      if self.precision == "f16" and self.has_img:
+        self.ops.ingest_img(r["img"], r["imgs"], T * E)     # fp32 CHW -> fp16 space-to-depth NHWC
     self.h2d_bytes = T * E * D * 4
-    if self.precision == "f16":
-      self.ops.ingest_img(r["img"], r["imgs"], T * E)       # fp32 CHW -> fp16 space-to-depth NHWC
     for key in ("acts", "values", "rewards", "terminals"):
       src = host[key].reshape(T * E, -1)
       r[key].view(T * E, -1).copy_(src, non_blocking=True)
@@ -210,6 +213,28 @@ class PPOUpdateEngine:
     else:
       r["time_limits"] = None
     return r
+
+  def _copy_obs_rows(self, obs, D, n0, n):
+    """rows [n0, n0+n) of the pinned [N, D] host observations -> state / image planes"""
+    r = self._roll
+    base = obs.data_ptr() + n0 * D * 4
+    if self.S:
+      self.ops.h2d_2d(r["state"][n0:], self.S * 4, base, D * 4, self.S * 4, n)
+    if self.has_img:
+      self.ops.h2d_2d(r["img"][n0:], engine.IMG_ELEMS * 4, base + self.S * 4, D * 4, engine.IMG_ELEMS * 4, n)
+
+  def _stream_chunk(self, obs, D, trows, E, k, rows):
+    """Copy the observation rows of minibatch k (first opt-epoch) on the copy stream, convert
+    them for the tensor-core tier, and return the event that marks them resident."""
+    with self.ops.fork(2):
+      for t in trows:
+        self._copy_obs_rows(obs, D, int(t) * E, E)
+      if self.precision == "f16" and self.has_img:
+        r = self._roll
+        self.ops.ingest_img(r["img"], r["imgs"], len(trows) * E, idx=self._flat_idx[k * rows * E:])
+      ev = torch.cuda.Event()
+      ev.record()
+    return ev
 
   def load_rollout_arrays(self, roll):
     """Test/bench helper: same as load_rollout from a dict of [T,E,*] numpy arrays."""
@@ -410,9 +435,21 @@ class PPOUpdateEngine:
       self._flat_idx_static.copy_(self._flat_idx.view(-1))
       self._flat_idx = self._flat_idx_static
       self._slot.zero_()
-      for _ in range(n_mb):
+      pending, self._pending_obs = getattr(self, "_pending_obs", None), None
+      cur = torch.cuda.current_stream(dev)
+      for k in range(n_mb):
+        if pending is not None and k < n_full:
+          # interleaved with the launches so the CPU never runs far behind the GPU
+          ev = self._stream_chunk(pending[0], pending[1], perms[0][k * rows:(k + 1) * rows], E, k, rows)
+          cur.wait_event(ev)               # rows of minibatch k (first opt-epoch) have landed
         self._launch(B)
     else:
+      if getattr(self, "_pending_obs", None) is not None:
+        obs, D = self._pending_obs
+        self._pending_obs = None
+        self._copy_obs_rows(obs, D, 0, T * E)
+        if self.precision == "f16" and self.has_img:
+          self.ops.ingest_img(r["img"], r["imgs"], T * E)
       self._run_ragged(flat, T, E, rows)
     info = self._info[:n_mb, :len(INFO_KEYS)].cpu().numpy()
     self.d2h_bytes = info.nbytes

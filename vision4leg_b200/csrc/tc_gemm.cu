@@ -762,7 +762,8 @@ namespace {
 // fp32 CHW [4,64,64] observation image -> f16 4x4 space-to-depth NHWC [16,16,64],
 // channel = (py*4 + px)*4 + c for source pixel (4Y+py, 4X+px): the 8x8/4 conv becomes a 2x2/1
 // conv with 64-channel (128-byte) rows — exactly one TMA/UMMA swizzle atom per tap.
-__global__ void ingest_img_kernel(const float* __restrict__ img, __half* __restrict__ out, long long n_img) {
+__global__ void ingest_img_kernel(const float* __restrict__ img, __half* __restrict__ out, long long n_img,
+                                  const int32_t* __restrict__ idx) {
   v4l_pdl_enter();
   const long long total = n_img * 16 * 4 * 16;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
@@ -770,7 +771,7 @@ __global__ void ingest_img_kernel(const float* __restrict__ img, __half* __restr
     const int X = (int)(t & 15);
     const int py = (int)((t >> 4) & 3);
     const int Y = (int)((t >> 6) & 15);
-    const long long n = t >> 10;
+    const long long n = idx ? (long long)idx[t >> 10] : (t >> 10);    // optional row list (streamed ingest)
     const float* src = img + n * 16384 + (4 * Y + py) * 64 + 4 * X;
     float4 v[4];
 #pragma unroll
@@ -827,12 +828,13 @@ __global__ void relu_bwd_f16_kernel(const __half* __restrict__ dy, const v4l_row
 
 }  // namespace
 
-extern "C" int v4l_ingest_img(v4l_ctx* ctx, void* stream, const float* img, void* out_s2d, int64_t n_img) {
+extern "C" int v4l_ingest_img(v4l_ctx* ctx, void* stream, const float* img, void* out_s2d, int64_t n_img,
+                              const int32_t* idx) {
   V4L_REQUIRE(ctx && img && out_s2d && n_img >= 0, "v4l_ingest_img: bad argument");
   if (n_img == 0) return 0;
   const long long total = n_img * 1024;
   const int blocks = (int)min((long long)16 * ctx->sm_count, (total + 255) / 256);
-  V4L_LAUNCH(ingest_img_kernel, blocks, 256, 0, (cudaStream_t)stream, img, reinterpret_cast<__half*>(out_s2d), n_img);
+  V4L_LAUNCH(ingest_img_kernel, blocks, 256, 0, (cudaStream_t)stream, img, reinterpret_cast<__half*>(out_s2d), n_img, idx);
   V4L_CHECK_LAUNCH();
   return 0;
 }

@@ -195,8 +195,8 @@ class Ops:
                                   ptr(out)))
     self.launches += 2
 
-  def ingest_img(self, img_f32, out_s2d, n):
-    check(self.lib.v4l_ingest_img(self.h, self.ctx.stream(), ptr(img_f32), ptr(out_s2d), n))
+  def ingest_img(self, img_f32, out_s2d, n, idx=None):
+    check(self.lib.v4l_ingest_img(self.h, self.ctx.stream(), ptr(img_f32), ptr(out_s2d), n, ptr(idx)))
     self.launches += 1
 
   def gather_rows_f16(self, src, src_is_f32, idx, dst, rows, src_cols, src_stride, dst_cols, scale=1.0):
