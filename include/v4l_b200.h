@@ -247,6 +247,13 @@ int v4l_pack_f16(v4l_ctx* ctx, void* stream, const float* src, const int32_t* in
  * (channel = (py*4+px)*4+c): the layout the tensor-core conv1 reads (one swizzle atom per tap) */
 int v4l_ingest_img(v4l_ctx* ctx, void* stream, const float* img, void* out_s2d, int64_t n_img,
                    const int32_t* idx /* optional list of the n_img image rows to convert */);
+/* Zero-copy rollout ingest: row n (= idx[i] or i) of the [*, row_stride] fp32 observation matrix in
+ * PINNED HOST (or device) memory -> state_out[n, 0:S] fp32, img_out[n, 0:16384] fp32 (optional),
+ * s2d_out[n] fp16 [16,16,64] (optional), one CTA per row, PCIe reads issued by the SMs.
+ * Replaces reference on_policy.py:83-89 + ppo.py:136-140 (float64 gather, f64->f32, H2D).       */
+int v4l_ingest_rows(v4l_ctx* ctx, void* stream, const float* obs, int64_t row_stride, int S,
+                    const int32_t* idx, int64_t n_rows, float* state_out, float* img_out,
+                    void* s2d_out);
 /* dst_f16[i, 0:dst_cols] = src[idx ? idx[i] : i, 0:src_cols] zero padded (proprio rows -> K-padded
  * f16 operand; also fp32 -> f16 conversion of loss gradients)                                */
 int v4l_gather_rows_f16(v4l_ctx* ctx, void* stream, const void* src, int src_is_f32,

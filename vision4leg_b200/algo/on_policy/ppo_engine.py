@@ -226,12 +226,18 @@ class PPOUpdateEngine:
   def _stream_chunk(self, obs, D, trows, E, k, rows):
     """Copy the observation rows of minibatch k (first opt-epoch) on the copy stream, convert
     them for the tensor-core tier, and return the event that marks them resident."""
+    r = self._roll
     with self.ops.fork(2):
-      for t in trows:
-        self._copy_obs_rows(obs, D, int(t) * E, E)
-      if self.precision == "f16" and self.has_img:
-        r = self._roll
-        self.ops.ingest_img(r["img"], r["imgs"], len(trows) * E, idx=self._flat_idx[k * rows * E:])
+      if self.has_img:
+        # zero-copy: the SMs read this minibatch's rows from pinned host memory and write the
+        # device layouts directly (fp32 image plane only for the exact tier)
+        self.ops.ingest_rows(obs.data_ptr(), D, self.S, self._flat_idx[k * rows * E:], len(trows) * E,
+                             r["state"] if self.S else None,
+                             r["img"] if self.precision != "f16" else None,
+                             r.get("imgs") if self.precision == "f16" else None)
+      else:
+        for t in trows:
+          self._copy_obs_rows(obs, D, int(t) * E, E)
       ev = torch.cuda.Event()
       ev.record()
     return ev

@@ -868,3 +868,58 @@ extern "C" int v4l_relu_bwd_f16(v4l_ctx* ctx, void* stream, const void* dy, cons
   V4L_CHECK_LAUNCH();
   return 0;
 }
+
+// =================================================================================================
+// Zero-copy rollout ingest: one CTA per observation row reads it straight from PINNED HOST memory
+// (UVA pointer, PCIe reads issued by the SMs, fully coalesced 4-byte loads so the 4*S-byte offset of
+// the image inside the row needs no alignment) and writes the device-side layouts in one pass:
+// proprio plane fp32 [N,S], optional fp32 image plane [N,16384] (exact tier) and the fp16
+// space-to-depth image [N,16,16,64] (tensor-core tier).  Replaces a 1 GB staging copy + a
+// conversion pass, and lets the host->device stream follow the minibatch order of the first
+// opt-epoch with ONE launch per minibatch (row list = that minibatch's indices).
+// =================================================================================================
+namespace {
+__global__ void __launch_bounds__(256) ingest_rows_kernel(const float* __restrict__ obs, long long row_stride, int S,
+                                                          const int32_t* __restrict__ idx, float* __restrict__ state_out,
+                                                          float* __restrict__ img_out, __half* __restrict__ s2d_out) {
+  v4l_pdl_enter();
+  __shared__ __half sm[16384];
+  const long long n = idx ? (long long)idx[blockIdx.x] : (long long)blockIdx.x;
+  const float* src = obs + n * row_stride;
+  if (state_out)
+    for (int i = threadIdx.x; i < S; i += 256) state_out[n * S + i] = src[i];
+  const float* im = src + S;
+#pragma unroll 8
+  for (int j = 0; j < 64; ++j) {
+    const int e = j * 256 + threadIdx.x;
+    const float v = im[e];
+    if (img_out) img_out[n * 16384 + e] = v;
+    sm[e] = __float2half(v);
+  }
+  if (!s2d_out) return;
+  __syncthreads();
+  // 2048 chunks of 8 halfs: chunk = (Y, X, py, hi) -> pixels px = 2*hi, 2*hi+1, channels 0..3
+  __half* dst = s2d_out + n * 16384;
+  for (int q = threadIdx.x; q < 2048; q += 256) {
+    const int hi = q & 1, py = (q >> 1) & 3, X = (q >> 3) & 15, Y = q >> 7;
+    const int base = (4 * Y + py) * 64 + 4 * X + 2 * hi;
+    __half h[8];
+#pragma unroll
+    for (int px = 0; px < 2; ++px)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) h[px * 4 + c] = sm[c * 4096 + base + px];
+    *reinterpret_cast<uint4*>(dst + (Y * 16 + X) * 64 + py * 16 + hi * 8) = *reinterpret_cast<const uint4*>(h);
+  }
+}
+}  // namespace
+
+extern "C" int v4l_ingest_rows(v4l_ctx* ctx, void* stream, const float* obs, int64_t row_stride, int S,
+                               const int32_t* idx, int64_t n_rows, float* state_out, float* img_out,
+                               void* s2d_out) {
+  V4L_REQUIRE(ctx && obs && n_rows >= 0 && S >= 0 && row_stride >= S + 16384, "v4l_ingest_rows: bad argument");
+  V4L_REQUIRE(S == 0 || state_out, "v4l_ingest_rows: state_out is NULL");
+  if (n_rows == 0) return 0;
+  V4L_LAUNCH(ingest_rows_kernel, (unsigned)n_rows, 256, 0, (cudaStream_t)stream, obs, (long long)row_stride, S, idx,
+             state_out, img_out, reinterpret_cast<__half*>(s2d_out));
+  return 0;
+}

@@ -199,6 +199,11 @@ class Ops:
     check(self.lib.v4l_ingest_img(self.h, self.ctx.stream(), ptr(img_f32), ptr(out_s2d), n, ptr(idx)))
     self.launches += 1
 
+  def ingest_rows(self, obs_ptr, row_stride, S, idx, n_rows, state_out, img_out, s2d_out):
+    check(self.lib.v4l_ingest_rows(self.h, self.ctx.stream(), obs_ptr, row_stride, S, ptr(idx), n_rows,
+                                   ptr(state_out), ptr(img_out), ptr(s2d_out)))
+    self.launches += 1
+
   def gather_rows_f16(self, src, src_is_f32, idx, dst, rows, src_cols, src_stride, dst_cols, scale=1.0):
     check(self.lib.v4l_gather_rows_f16(self.h, self.ctx.stream(), ptr(src), 1 if src_is_f32 else 0, ptr(idx),
                                        ptr(dst), rows, src_cols, src_stride, dst_cols, scale))
