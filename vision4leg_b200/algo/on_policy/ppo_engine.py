@@ -229,9 +229,18 @@ class PPOUpdateEngine:
     r = self._roll
     with self.ops.fork(2):
       if self.has_img:
-        # zero-copy: the SMs read this minibatch's rows from pinned host memory and write the
-        # device layouts directly (fp32 image plane only for the exact tier)
-        self.ops.ingest_rows(obs.data_ptr(), D, self.S, self._flat_idx[k * rows * E:], len(trows) * E,
+        # copy engine: one contiguous 8-row block (E x D floats) per time row into a device staging
+        # matrix with the host layout; then ONE kernel splits/convert this minibatch's rows into the
+        # device layouts (fp32 image plane only for the exact tier).  No SM is tied up waiting on PCIe.
+        stage = r.get("stage")
+        if stage is None:
+          stage = r["stage"] = torch.empty((r["N"], D), device=self.device, dtype=torch.float32)
+        blk = E * D * 4
+        base_h, base_d = obs.data_ptr(), stage.data_ptr()
+        for t in trows:
+          off = int(t) * blk
+          self.ops.h2d_raw(base_d + off, base_h + off, blk)
+        self.ops.ingest_rows(base_d, D, self.S, self._flat_idx[k * rows * E:], len(trows) * E,
                              r["state"] if self.S else None,
                              r["img"] if self.precision != "f16" else None,
                              r.get("imgs") if self.precision == "f16" else None)

@@ -314,6 +314,10 @@ class Ops:
                                  ptr(hyper), ptr(info), ptr(slot), norm_slot))
     self.launches += 3
 
+  def h2d_raw(self, dst_ptr, src_ptr, nbytes):
+    """contiguous pinned-host -> device copy on the current stream (copy engine)"""
+    check(self.lib.v4l_h2d_2d(self.ctx.stream(), dst_ptr, nbytes, src_ptr, nbytes, nbytes, 1))
+
   def h2d_2d(self, dst, dpitch, src_ptr, spitch, width, height):
     check(self.lib.v4l_h2d_2d(self.ctx.stream(), ptr(dst), dpitch, src_ptr, spitch, width, height))
 
