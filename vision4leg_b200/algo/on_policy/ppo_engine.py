@@ -227,7 +227,9 @@ class PPOUpdateEngine:
     """Copy the observation rows of minibatch k (first opt-epoch) on the copy stream, convert
     them for the tensor-core tier, and return the event that marks them resident."""
     r = self._roll
-    with self.ops.fork(2):
+    # free-running copy stream: it was ordered after the main stream ONCE (run_epoch); waiting for
+    # the main stream here would serialise copy k+1 behind minibatch k
+    with self.ops.fork(2, wait=False):
       if self.has_img:
         # copy engine: one contiguous 8-row block (E x D floats) per time row into a device staging
         # matrix with the host layout; then ONE kernel splits/convert this minibatch's rows into the
@@ -452,6 +454,9 @@ class PPOUpdateEngine:
       self._slot.zero_()
       pending, self._pending_obs = getattr(self, "_pending_obs", None), None
       cur = torch.cuda.current_stream(dev)
+      if pending is not None:
+        with self.ops.fork(2):          # order the copy stream after the index upload / previous epoch
+          pass
       for k in range(n_mb):
         if pending is not None and k < n_full:
           # interleaved with the launches so the CPU never runs far behind the GPU

@@ -86,12 +86,12 @@ class Ops:
       sides[which] = torch.cuda.Stream(device=self.device)
     return sides[which]
 
-  def fork(self, which=0):
+  def fork(self, which=0, wait=True):
     """Context manager: launches inside go to side stream `which`, ordered after everything
-    issued so far on the current stream."""
+    issued so far on the current stream (wait=False: free-running, e.g. the copy stream)."""
     side = self._side_stream(which)
     cur = torch.cuda.current_stream(self.device)
-    if cur != side:
+    if wait and cur != side:
       side.wait_stream(cur)
     return torch.cuda.stream(side)
 
