@@ -437,7 +437,11 @@ def tc_conv1_roofline(args, eng, pk):
   ach = flops / sec / 1e12
   return {"kernel": "tc_gemm_kernel (conv1 forward: tcgen05.mma fp16, 4 tap-shifted TMA boxes, fused bias+ReLU)",
           "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-          "frac": ach / pk["bf16_tflops"], "traffic": None, "us_per_launch": sec * 1e6, "peak_src": pk["src"],
+          "frac": ach / pk["bf16_tflops"],
+          # dram__bytes_read.sum + dram__bytes_write.sum of this launch at minibatch 1024 from the
+          # `ncu --set full` capture profiles/r1_conv1_tc_gemm_ncu.txt (33.62 MB + 5.63 MB)
+          "traffic": 39.25e6 if B == 1024 else None,
+          "us_per_launch": sec * 1e6, "peak_src": pk["src"],
           "algorithmic_flops_per_launch": flops, "hbm_bytes_per_launch_algorithmic": by,
           "hbm_gbs_achieved": by / sec / 1e9, "hbm_frac": by / sec / 1e9 / pk["hbm_gbs"],
           "note": "N=32, K=256: 128 FLOP/B -> this layer is HBM/L2-feed bound, not tensor bound"}
