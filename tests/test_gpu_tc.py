@@ -287,3 +287,26 @@ def test_tc_tier_graph_replay_is_bit_identical():
     outs.append((agent.engine.bucket.flat.clone(), [tuple(i.values()) for i in logger.infos]))
   assert torch.equal(outs[0][0], outs[1][0])
   assert outs[0][1] == outs[1][1]
+
+
+@pytest.mark.parametrize("rows", [1, 51, 17408])
+def test_f16_layernorm_d64_fast_path(rows):
+  engine, ops = _ops()
+  torch.manual_seed(rows)
+  d = 64
+  a = torch.randn(rows, d, device=DEV).half(); r = torch.randn(rows, d, device=DEV).half()
+  gm = torch.randn(d, device=DEV); bt = torch.randn(d, device=DEV)
+  y = torch.empty(rows, d, device=DEV, dtype=torch.float16)
+  z = torch.empty(rows, d, device=DEV); st = torch.empty(rows, 2, device=DEV)
+  ops.ln_fwd_f16(a, r, gm, bt, y, z, st, rows, d)
+  af = (a.float() + r.float()).requires_grad_(True)
+  gmr, btr = gm.clone().requires_grad_(True), bt.clone().requires_grad_(True)
+  ref = F.layer_norm(af, (d,), gmr, btr, 1e-5)
+  assert rel(y.float(), ref) < 2e-3 and rel(z, af) < 1e-6
+  gy = torch.randn(rows, d, device=DEV).half()
+  ref.backward(gy.float())
+  dz = torch.empty(rows, d, device=DEV, dtype=torch.float16)
+  dg = torch.empty(d, device=DEV); db = torch.empty(d, device=DEV)
+  ops.ln_bwd_f16(gy, z, st, gm, dz, dg, db, rows, d, out_scale=0.25)
+  assert rel(dz.float(), af.grad) < 3e-3
+  assert rel(dg, 0.25 * gmr.grad) < 1e-4 and rel(db, 0.25 * btr.grad) < 1e-4

@@ -262,6 +262,73 @@ __global__ void ln_bwd_reduce_kernel(const float* __restrict__ part, int nparts,
   if (lane == 0) (which ? dbeta : dgamma)[c] = s * out_scale;
 }
 
+// ---- d = 64, fp16 IO fast paths: one 128-byte row per warp load (half2 per lane), grid-stride over rows
+__global__ void __launch_bounds__(256)
+ln_fwd_h64_kernel(const __half2* __restrict__ a, const __half2* __restrict__ res,
+                  const float2* __restrict__ gamma, const float2* __restrict__ beta,
+                  __half2* __restrict__ y, float2* __restrict__ z, float2* __restrict__ stats, int rows, float eps) {
+  v4l_pdl_enter();
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = gridDim.x * 8;
+  const float2 g = gamma[lane], b = beta[lane];
+  for (int row = warp; row < rows; row += nwarps) {
+    const long long o = (long long)row * 32 + lane;
+    float2 x = __half22float2(a[o]);
+    if (res) { const float2 r = __half22float2(res[o]); x.x += r.x; x.y += r.y; }
+    float s = x.x + x.y;
+#pragma unroll
+    for (int k = 16; k; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+    const float mean = s * (1.f / 64.f);
+    const float d0 = x.x - mean, d1 = x.y - mean;
+    float vs = d0 * d0 + d1 * d1;
+#pragma unroll
+    for (int k = 16; k; k >>= 1) vs += __shfl_xor_sync(0xffffffffu, vs, k);
+    const float rstd = rsqrtf(vs * (1.f / 64.f) + eps);
+    y[o] = __floats2half2_rn(d0 * rstd * g.x + b.x, d1 * rstd * g.y + b.y);
+    if (z) z[o] = x;
+    if (stats && lane == 0) stats[row] = make_float2(mean, rstd);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ln_bwd_h64_kernel(const __half2* __restrict__ dy, const float2* __restrict__ z, const float2* __restrict__ stats,
+                  const float2* __restrict__ gamma, __half2* __restrict__ dz, float* __restrict__ part, int rows) {
+  v4l_pdl_enter();
+  __shared__ float red[8][2][64];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int warp = blockIdx.x * 8 + w, nwarps = gridDim.x * 8;
+  const float2 g = gamma[lane];
+  float2 dg = make_float2(0.f, 0.f), db = make_float2(0.f, 0.f);
+  for (int row = warp; row < rows; row += nwarps) {
+    const long long o = (long long)row * 32 + lane;
+    const float2 st = stats[row];
+    const float2 gy = __half22float2(dy[o]);
+    const float2 zz = z[o];
+    const float xh0 = (zz.x - st.x) * st.y, xh1 = (zz.y - st.x) * st.y;
+    const float dx0 = gy.x * g.x, dx1 = gy.y * g.y;
+    dg.x = fmaf(gy.x, xh0, dg.x); dg.y = fmaf(gy.y, xh1, dg.y);
+    db.x += gy.x; db.y += gy.y;
+    float s1 = dx0 + dx1, s2 = dx0 * xh0 + dx1 * xh1;
+#pragma unroll
+    for (int k = 16; k; k >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, k);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, k);
+    }
+    const float m1 = s1 * (1.f / 64.f), m2 = s2 * (1.f / 64.f);
+    dz[o] = __floats2half2_rn(st.y * (dx0 - m1 - xh0 * m2), st.y * (dx1 - m1 - xh1 * m2));
+  }
+  red[w][0][2 * lane] = dg.x; red[w][0][2 * lane + 1] = dg.y;
+  red[w][1][2 * lane] = db.x; red[w][1][2 * lane + 1] = db.y;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][which][c];
+    part[((long long)blockIdx.x * 2 + which) * 64 + c] = s;
+  }
+}
+
 template <typename T_>
 __global__ void pool_fwd_kernel(const T_* __restrict__ tok, T_* __restrict__ out, int B, int T,
                                 int d, int mode) {
@@ -349,6 +416,12 @@ static int ln_fwd_impl(v4l_ctx* ctx, void* stream, const void* a, const void* re
   V4L_REQUIRE(ctx && a && gamma && beta && y, "v4l_ln_fwd: NULL argument");
   V4L_REQUIRE(d > 0 && d <= 32 * LN_MAXPER, "v4l_ln_fwd: d=%d unsupported (max %d)", d, 32 * LN_MAXPER);
   if (rows == 0) return 0;
+  if (sizeof(T_) == 2 && d == 64) {
+    const int ctas = min(v4l_cdiv(rows, 8), 8 * ctx->sm_count);
+    V4L_LAUNCH(ln_fwd_h64_kernel, ctas, 256, 0, (cudaStream_t)stream, (const __half2*)a, (const __half2*)res,
+               (const float2*)gamma, (const float2*)beta, (__half2*)y, (float2*)z, (float2*)stats, rows, eps);
+    return 0;
+  }
   V4L_LAUNCH((ln_fwd_kernel<T_>), v4l_cdiv(rows, 8), 256, 0, (cudaStream_t)stream, (const T_*)a, (const T_*)res, gamma, beta,
                                                                           (T_*)y, z, stats, rows, d, eps);
   V4L_CHECK_LAUNCH();
@@ -367,7 +440,13 @@ static int ln_bwd_impl(v4l_ctx* ctx, void* stream, const void* dy, const float* 
   ctas = v4l_cdiv(rows, rpc);
   V4L_REQUIRE((size_t)ctas * 2 * d <= ctx->scratch_elems, "v4l_ln_bwd: scratch too small");
   cudaStream_t s = (cudaStream_t)stream;
-  V4L_LAUNCH((ln_bwd_kernel<T_>), ctas, 256, 0, s, (const T_*)dy, z, stats, gamma, (T_*)dz, ctx->scratch, rows, d, rpc);
+  if (sizeof(T_) == 2 && d == 64) {
+    ctas = min(ctas, ctx->sm_count);
+    V4L_LAUNCH(ln_bwd_h64_kernel, ctas, 256, 0, s, (const __half2*)dy, (const float2*)z, (const float2*)stats,
+               (const float2*)gamma, (__half2*)dz, ctx->scratch, rows);
+  } else {
+    V4L_LAUNCH((ln_bwd_kernel<T_>), ctas, 256, 0, s, (const T_*)dy, z, stats, gamma, (T_*)dz, ctx->scratch, rows, d, rpc);
+  }
   V4L_CHECK_LAUNCH();
   V4L_LAUNCH(ln_bwd_reduce_kernel, v4l_cdiv(2 * d, 8), 256, 0, s, ctx->scratch, ctas, d, dgamma, dbeta, out_scale);
   V4L_CHECK_LAUNCH();
