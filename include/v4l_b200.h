@@ -129,6 +129,13 @@ int v4l_ln_bwd_f16(v4l_ctx* ctx, void* stream, const void* dy, const float* z, c
 int v4l_pool_fwd_f16(v4l_ctx* ctx, void* stream, const void* tok, void* out, int B, int T, int d, int mode);
 int v4l_pool_bwd_f16(v4l_ctx* ctx, void* stream, const void* dout, void* dtok, int B, int T, int d, int mode);
 
+/* Tensor-core attention core (single head, d = 64): several samples packed per 128-row tile, the
+ * per-sample TxT attention as block-diagonal tcgen05 MMAs (vision4leg_b200/csrc/tc_attn.cu).
+ * qkv fp16 [B*T,192], o fp16 [B*T,64], p fp32 [B,T,T], d_o fp16 [B*T,64], d_qkv fp16 [B*T,192].  */
+int v4l_tc_attn_fwd(v4l_ctx* ctx, void* stream, const void* qkv, void* o, float* p, int B, int T);
+int v4l_tc_attn_bwd(v4l_ctx* ctx, void* stream, const void* qkv, const float* p, const void* d_o,
+                    void* d_qkv, int B, int T);
+
 /* ---- GAE / discounted return: reverse segmented scan over the rollout buffer
  *      (reference torchrl/replay_buffers/on_policy.py:17-71; recurrence: SURVEY Appendix A4).
  * rewards/values/terminals/advs/rets: [T,E] fp32; time_limits addressed t*tl_st + e*tl_se

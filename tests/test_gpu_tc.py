@@ -310,3 +310,26 @@ def test_f16_layernorm_d64_fast_path(rows):
   ops.ln_bwd_f16(gy, z, st, gm, dz, dg, db, rows, d, out_scale=0.25)
   assert rel(dz.float(), af.grad) < 3e-3
   assert rel(dg, 0.25 * gmr.grad) < 1e-4 and rel(db, 0.25 * btr.grad) < 1e-4
+
+
+@pytest.mark.parametrize("B,T", [(7, 17), (1024, 17), (100, 16), (3, 17)])
+def test_tc_attention_fwd_bwd(B, T):
+  """Block-diagonal tcgen05 attention (7 x 17-token samples per 128-row tile) vs torch."""
+  engine, ops = _ops()
+  torch.manual_seed(B * 31 + T)
+  d = 64
+  qkv = (torch.randn(B, T, 3 * d, device=DEV)).half()
+  o = torch.full((B, T, d), float("nan"), device=DEV, dtype=torch.float16)
+  p = torch.full((B, 1, T, T), float("nan"), device=DEV)
+  ops.attn_fwd_f16(qkv, o, p, B, T, d, 1)
+  qr = qkv.float().requires_grad_(True)
+  q, k, v = qr.split(d, -1)
+  pr = torch.softmax(q @ k.transpose(-1, -2) / 8.0, -1)
+  ref = pr @ v
+  assert rel(p[:, 0], pr) < 3e-3
+  assert rel(o.float(), ref) < 3e-3
+  go = torch.randn(B, T, d, device=DEV).half()
+  ref.backward(go.float())
+  dqkv = torch.full((B, T, 3 * d), float("nan"), device=DEV, dtype=torch.float16)
+  ops.attn_bwd_f16(qkv, p, go, dqkv, B, T, d, 1)
+  assert rel(dqkv.float(), qr.grad) < 5e-3

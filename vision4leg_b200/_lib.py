@@ -102,6 +102,8 @@ SIGNATURES = {
   "v4l_ln_bwd_f16": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f],
   "v4l_pool_fwd_f16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
   "v4l_pool_bwd_f16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
+  "v4l_tc_attn_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i],
+  "v4l_tc_attn_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i],
   "v4l_gae": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i, _i, _d, _d, _i, _i],
   "v4l_select_rows": [_vp, _vp, _vp, _vp, _vp, _i],
   "v4l_slot_advance": [_vp, _vp, _vp, C.c_int32],

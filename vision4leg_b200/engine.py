@@ -216,10 +216,18 @@ class Ops:
     self.launches += 1
 
   def attn_fwd_f16(self, qkv, o, p, B, T, d, nh):
+    if nh == 1 and d == 64:          # tensor-core path: block-diagonal tcgen05 MMAs
+      check(self.lib.v4l_tc_attn_fwd(self.h, self.ctx.stream(), ptr(qkv), ptr(o), ptr(p), B, T))
+      self.launches += 1
+      return
     check(self.lib.v4l_attn_fwd_f16(self.h, self.ctx.stream(), ptr(qkv), ptr(o), ptr(p), B, T, d, nh))
     self.launches += 1
 
   def attn_bwd_f16(self, qkv, p, d_o, d_qkv, B, T, d, nh):
+    if nh == 1 and d == 64:
+      check(self.lib.v4l_tc_attn_bwd(self.h, self.ctx.stream(), ptr(qkv), ptr(p), ptr(d_o), ptr(d_qkv), B, T))
+      self.launches += 1
+      return
     check(self.lib.v4l_attn_bwd_f16(self.h, self.ctx.stream(), ptr(qkv), ptr(p), ptr(d_o), ptr(d_qkv),
                                      B, T, d, nh))
     self.launches += 1
