@@ -136,6 +136,40 @@ int v4l_tc_attn_fwd(v4l_ctx* ctx, void* stream, const void* qkv, void* o, float*
 int v4l_tc_attn_bwd(v4l_ctx* ctx, void* stream, const void* qkv, const float* p, const void* d_o,
                     void* d_qkv, int B, int T);
 
+/* Fused forward of one post-norm TransformerEncoderLayer (d=64, 1 head, FFN 256, ReLU, dropout 0;
+ * reference torchrl/networks/nets.py:949-955 -> torch nn.TransformerEncoderLayer) as ONE kernel:
+ * QKV GEMM -> block-diagonal attention -> out-proj -> +x, LayerNorm1 -> FFN1+ReLU -> FFN2 -> +h,
+ * LayerNorm2, six tcgen05 contractions chained through shared memory
+ * (vision4leg_b200/csrc/tc_block.cu).  x/y fp16 [B*T,64]; weights fp16 row-major [out,in]
+ * (w_in [192,64], w_o [64,64], w_1 [256,64], w_2 [64,256]); biases / LayerNorm affine fp32.
+ * Saved for the backward: qkv fp16 [B*T,192], p fp32 [B,T,T], o fp16 [B*T,64], z1/z2 fp32 [B*T,64]
+ * (pre-norm sums), st1/st2 fp32 [B*T,2] (mean, rstd), h fp16 [B*T,64], f1 fp16 [B*T,256].     */
+typedef struct v4l_tc_block_args {
+  const void* x; int32_t B, T; float eps;
+  const void *w_in, *w_o, *w_1, *w_2;
+  const float *b_in, *b_o, *g1, *be1, *b1, *b2, *g2, *be2;
+  void *qkv, *o, *h, *f1, *y;
+  float *p, *z1, *st1, *z2, *st2;    /* z1 / z2 may be NULL */
+  void *xh1, *xh2;                   /* fp16 [B*T,64] normalised rows (before the affine), or NULL */
+} v4l_tc_block_args;
+int v4l_tc_block_fwd(v4l_ctx* ctx, void* stream, const v4l_tc_block_args* args);
+
+/* Fused data-gradient pass of the same layer (torch autograd of nn.TransformerEncoderLayer):
+ * dy fp16 [B*T,64] -> dx fp16 [B*T,64], storing the row gradients the weight-gradient GEMMs consume:
+ * dz2 [B*T,64], df1 [B*T,256], dh [B*T,64], dz1 [B*T,64], dqkv [B*T,192] (all fp16).
+ * Weights in data-gradient orientation, fp16 row-major: w2d [256,64] = W2^T, w1d [64,256] = W1^T,
+ * wod [64,64] = Wo^T, wind [64,192] = Win^T.  g1, g2 = LayerNorm weights; xh1, xh2, st1, st2, qkv, p, f1 as saved
+ * by v4l_tc_block_fwd.  Weight / bias / LayerNorm-affine gradients: v4l_tc_wgrad on
+ * (x,dqkv) (o,dz1) (h,df1) (f1,dz2) (xh1,dh) (xh2,dy).                                         */
+typedef struct v4l_tc_block_bwd_args {
+  const void* dy; int32_t B, T, pad_;
+  const void *qkv, *xh1, *xh2, *f1;
+  const float *p, *st1, *st2, *g1, *g2;
+  const void *w2d, *w1d, *wod, *wind;
+  void *dz2, *df1, *dh, *dz1, *dqkv, *dx;
+} v4l_tc_block_bwd_args;
+int v4l_tc_block_bwd(v4l_ctx* ctx, void* stream, const v4l_tc_block_bwd_args* args);
+
 /* ---- GAE / discounted return: reverse segmented scan over the rollout buffer
  *      (reference torchrl/replay_buffers/on_policy.py:17-71; recurrence: SURVEY Appendix A4).
  * rewards/values/terminals/advs/rets: [T,E] fp32; time_limits addressed t*tl_st + e*tl_se

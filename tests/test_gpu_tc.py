@@ -333,3 +333,112 @@ def test_tc_attention_fwd_bwd(B, T):
   dqkv = torch.full((B, T, 3 * d), float("nan"), device=DEV, dtype=torch.float16)
   ops.attn_bwd_f16(qkv, p, go, dqkv, B, T, d, 1)
   assert rel(dqkv.float(), qr.grad) < 5e-3
+
+
+def _block_tensors(B, T, seed):
+  torch.manual_seed(seed)
+  layer = torch.nn.TransformerEncoderLayer(64, 1, 256, dropout=0.0).to(DEV)
+  with torch.no_grad():
+    for q in layer.parameters():           # non-trivial biases / LayerNorm affine
+      if q.dim() == 1:
+        q.add_(0.1 * torch.randn_like(q))
+  sd = {k: v.detach() for k, v in layer.state_dict().items()}
+  w = {"w_in": sd["self_attn.in_proj_weight"].half().contiguous(), "w_o": sd["self_attn.out_proj.weight"].half().contiguous(),
+       "w_1": sd["linear1.weight"].half().contiguous(), "w_2": sd["linear2.weight"].half().contiguous()}
+  par = {"b_in": sd["self_attn.in_proj_bias"], "b_o": sd["self_attn.out_proj.bias"], "g1": sd["norm1.weight"],
+         "be1": sd["norm1.bias"], "b1": sd["linear1.bias"], "b2": sd["linear2.bias"], "g2": sd["norm2.weight"],
+         "be2": sd["norm2.bias"]}
+  par = {k: v.float().contiguous() for k, v in par.items()}
+  x = torch.randn(B, T, 64, device=DEV).half()
+  return layer, w, par, x
+
+
+@pytest.mark.parametrize("B,T", [(7, 17), (1024, 17), (100, 16), (3, 17)])
+def test_tc_block_fwd_matches_torch_layer(B, T):
+  """Fused TransformerEncoderLayer forward (six chained tcgen05 contractions) vs the torch module
+  the reference instantiates (nets.py:949-955), run in fp32 on the fp16-rounded weights."""
+  engine, ops = _ops()
+  layer, w, par, x = _block_tensors(B, T, B + T)
+  R = B * T
+  nanh = lambda *s: torch.full(s, float("nan"), device=DEV, dtype=torch.float16)
+  nanf = lambda *s: torch.full(s, float("nan"), device=DEV)
+  out = {"qkv": nanh(R, 192), "o": nanh(R, 64), "h": nanh(R, 64), "f1": nanh(R, 256), "y": nanh(R, 64),
+         "p": nanf(B, T, T), "z1": nanf(R, 64), "st1": nanf(R, 2), "z2": nanf(R, 64), "st2": nanf(R, 2)}
+  ops.tc_block_fwd(x, B, T, w, par, out)
+  torch.cuda.synchronize()
+  with torch.no_grad():
+    xf = x.float()
+    qkv = xf @ w["w_in"].float().t() + par["b_in"]
+    q, k, v = qkv.split(64, -1)
+    pr = torch.softmax(q @ k.transpose(-1, -2) / 8.0, -1)
+    o = pr @ v
+    z1 = xf + o @ w["w_o"].float().t() + par["b_o"]
+    h = torch.nn.functional.layer_norm(z1, (64,), par["g1"], par["be1"])
+    f1 = torch.relu(h @ w["w_1"].float().t() + par["b1"])
+    z2 = h + f1 @ w["w_2"].float().t() + par["b2"]
+    y = torch.nn.functional.layer_norm(z2, (64,), par["g2"], par["be2"])
+    # and the torch module itself ([T,B,64] layout, the reference's call)
+    layer2 = torch.nn.TransformerEncoderLayer(64, 1, 256, dropout=0.0).to(DEV)
+    sd = layer.state_dict()
+    for kk, ww in (("self_attn.in_proj_weight", "w_in"), ("self_attn.out_proj.weight", "w_o"),
+                   ("linear1.weight", "w_1"), ("linear2.weight", "w_2")):
+      sd[kk] = w[ww].float()
+    layer2.load_state_dict(sd)
+    y_mod = layer2(xf.transpose(0, 1)).transpose(0, 1)
+  assert rel(y, y_mod) < 1e-4
+  tol = 4e-3
+  assert rel(out["qkv"].float().view(B, T, 192), qkv) < tol
+  assert rel(out["p"], pr) < tol
+  assert rel(out["o"].float().view(B, T, 64), o) < tol
+  assert rel(out["z1"].view(B, T, 64), z1) < tol
+  assert rel(out["h"].float().view(B, T, 64), h) < tol
+  assert rel(out["f1"].float().view(B, T, 256), f1) < tol
+  assert rel(out["z2"].view(B, T, 64), z2) < tol
+  assert rel(out["y"].float().view(B, T, 64), y) < tol
+  mean1 = z1.mean(-1); rstd1 = (z1.var(-1, unbiased=False) + 1e-5).rsqrt()
+  assert rel(out["st1"].view(B, T, 2)[..., 0], mean1) < tol and rel(out["st1"].view(B, T, 2)[..., 1], rstd1) < tol
+
+
+@pytest.mark.parametrize("B,T", [(7, 17), (1024, 17), (100, 16), (3, 17)])
+def test_tc_block_bwd_matches_torch_autograd(B, T):
+  """Fused data-gradient pass of the encoder layer vs torch autograd through the fp32 chain; the
+  LayerNorm affine gradients through the diag-of-GEMM route (xhat^T dy) vs autograd."""
+  engine, ops = _ops()
+  layer, w, par, x = _block_tensors(B, T, 3 * B + T)
+  R = B * T
+  H = lambda *s: torch.full(s, float("nan"), device=DEV, dtype=torch.float16)
+  Fz = lambda *s: torch.full(s, float("nan"), device=DEV)
+  out = {"qkv": H(R, 192), "o": H(R, 64), "h": H(R, 64), "f1": H(R, 256), "y": H(R, 64), "p": Fz(B, T, T),
+         "st1": Fz(R, 2), "st2": Fz(R, 2), "xh1": H(R, 64), "xh2": H(R, 64)}
+  ops.tc_block_fwd(x, B, T, w, par, out)
+  # fp32 chain with retained intermediates
+  xf = x.float().view(R, 64).requires_grad_(True)
+  g1 = par["g1"].clone().requires_grad_(True); g2 = par["g2"].clone().requires_grad_(True)
+  qkv = xf @ w["w_in"].float().t() + par["b_in"]; qkv.retain_grad()
+  q, k, v = qkv.view(B, T, 192).split(64, -1)
+  o = (torch.softmax(q @ k.transpose(-1, -2) / 8.0, -1) @ v).reshape(R, 64)
+  z1 = xf + o @ w["w_o"].float().t() + par["b_o"]; z1.retain_grad()
+  h = torch.nn.functional.layer_norm(z1, (64,), g1, par["be1"]); h.retain_grad()
+  a1 = h @ w["w_1"].float().t() + par["b1"]; a1.retain_grad()
+  # ReLU gate taken from the product's own activation: a pre-activation within fp16 rounding of 0
+  # may land on the other side in the fp32 chain, which flips that element's gradient entirely
+  gate = (out["f1"] > 0).float()
+  z2 = h + (a1 * gate) @ w["w_2"].float().t() + par["b2"]; z2.retain_grad()
+  y = torch.nn.functional.layer_norm(z2, (64,), g2, par["be2"])
+  dy = (torch.randn(R, 64, device=DEV) * 0.5).half()
+  y.backward(dy.float())
+  wd = {"w2d": w["w_2"].t().contiguous(), "w1d": w["w_1"].t().contiguous(), "wod": w["w_o"].t().contiguous(),
+        "wind": w["w_in"].t().contiguous()}
+  g = {"dz2": H(R, 64), "df1": H(R, 256), "dh": H(R, 64), "dz1": H(R, 64), "dqkv": H(R, 192), "dx": H(R, 64)}
+  ops.tc_block_bwd(dy, B, T, out, wd, par["g1"], par["g2"], g)
+  torch.cuda.synchronize()
+  tol = 6e-3
+  assert rel(g["dz2"].float(), z2.grad) < tol
+  assert rel(g["df1"].float(), a1.grad) < tol
+  assert rel(g["dh"].float(), h.grad) < tol
+  assert rel(g["dz1"].float(), z1.grad) < tol
+  assert rel(g["dqkv"].float(), qkv.grad) < tol
+  assert rel(g["dx"].float(), xf.grad) < tol
+  # LayerNorm affine gradients = diag(xhat^T dy), colsum(dy)
+  assert rel((out["xh2"].float() * dy.float()).sum(0), g2.grad) < tol
+  assert rel((out["xh1"].float() * g["dh"].float()).sum(0), g1.grad) < tol

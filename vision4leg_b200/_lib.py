@@ -76,6 +76,18 @@ class TcWgradArgs(C.Structure):
               ("dbias", C.c_void_p), ("defer", C.c_int32)]
 
 
+class TcBlockArgs(C.Structure):
+  _fields_ = [("x", C.c_void_p), ("B", C.c_int32), ("T", C.c_int32), ("eps", C.c_float)] + \
+    [(n, C.c_void_p) for n in ("w_in", "w_o", "w_1", "w_2", "b_in", "b_o", "g1", "be1", "b1", "b2", "g2", "be2",
+                               "qkv", "o", "h", "f1", "y", "p", "z1", "st1", "z2", "st2", "xh1", "xh2")]
+
+
+class TcBlockBwdArgs(C.Structure):
+  _fields_ = [("dy", C.c_void_p), ("B", C.c_int32), ("T", C.c_int32), ("pad_", C.c_int32)] + \
+    [(n, C.c_void_p) for n in ("qkv", "xh1", "xh2", "f1", "p", "st1", "st2", "g1", "g2", "w2d", "w1d", "wod", "wind",
+                               "dz2", "df1", "dh", "dz1", "dqkv", "dx")]
+
+
 _vp, _i, _i64, _f, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
 
 # name -> argtypes (restype is int unless listed in _RESTYPE)
@@ -103,6 +115,8 @@ SIGNATURES = {
   "v4l_pool_fwd_f16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
   "v4l_pool_bwd_f16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
   "v4l_tc_attn_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i],
+  "v4l_tc_block_fwd": [_vp, _vp, C.POINTER(TcBlockArgs)],
+  "v4l_tc_block_bwd": [_vp, _vp, C.POINTER(TcBlockBwdArgs)],
   "v4l_tc_attn_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i],
   "v4l_gae": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i, _i, _d, _d, _i, _i],
   "v4l_select_rows": [_vp, _vp, _vp, _vp, _vp, _i],

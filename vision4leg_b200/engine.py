@@ -223,6 +223,37 @@ class Ops:
     check(self.lib.v4l_attn_fwd_f16(self.h, self.ctx.stream(), ptr(qkv), ptr(o), ptr(p), B, T, d, nh))
     self.launches += 1
 
+  def tc_block_fwd(self, x, B, T, w, par, out, eps=1e-5):
+    """One fused TransformerEncoderLayer forward (v4l_tc_block_fwd). w: dict of fp16 weight tensors
+    (w_in, w_o, w_1, w_2); par: dict of fp32 vectors (b_in, b_o, g1, be1, b1, b2, g2, be2);
+    out: dict of output/saved tensors (qkv, o, h, f1, y, p, z1, st1, z2, st2)."""
+    a = _lib.TcBlockArgs()
+    a.x = ptr(x); a.B = B; a.T = T; a.eps = eps
+    for k in ("w_in", "w_o", "w_1", "w_2"):
+      setattr(a, k, ptr(w[k]))
+    for k in ("b_in", "b_o", "g1", "be1", "b1", "b2", "g2", "be2"):
+      setattr(a, k, ptr(par[k]))
+    for k in ("qkv", "o", "h", "f1", "y", "p", "z1", "st1", "z2", "st2", "xh1", "xh2"):
+      setattr(a, k, ptr(out.get(k)))
+    check(self.lib.v4l_tc_block_fwd(self.h, self.ctx.stream(), C.byref(a)))
+    self.launches += 1
+
+  def tc_block_bwd(self, dy, B, T, saved, w, g1, g2, out):
+    """Fused data-gradient pass of one encoder layer (v4l_tc_block_bwd). saved: qkv, xh1, xh2, f1, p,
+    st1, st2 from tc_block_fwd; w: fp16 dgrad-orientation weights (w2d, w1d, wod, wind);
+    out: dz2, df1, dh, dz1, dqkv, dx."""
+    a = _lib.TcBlockBwdArgs()
+    a.dy = ptr(dy); a.B = B; a.T = T
+    for k in ("qkv", "xh1", "xh2", "f1", "p", "st1", "st2"):
+      setattr(a, k, ptr(saved[k]))
+    a.g1, a.g2 = ptr(g1), ptr(g2)
+    for k in ("w2d", "w1d", "wod", "wind"):
+      setattr(a, k, ptr(w[k]))
+    for k in ("dz2", "df1", "dh", "dz1", "dqkv", "dx"):
+      setattr(a, k, ptr(out[k]))
+    check(self.lib.v4l_tc_block_bwd(self.h, self.ctx.stream(), C.byref(a)))
+    self.launches += 1
+
   def attn_bwd_f16(self, qkv, p, d_o, d_qkv, B, T, d, nh):
     if nh == 1 and d == 64:
       check(self.lib.v4l_tc_attn_bwd(self.h, self.ctx.stream(), ptr(qkv), ptr(p), ptr(d_o), ptr(d_qkv), B, T))

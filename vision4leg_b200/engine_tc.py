@@ -75,6 +75,11 @@ def _conv_tables(off, N, C, KH, KW, s):
   return _Packed(_ceil(N, 16), T * T * Cc, fwd), _Packed(_ceil(Cc, 16), T * T * _ceil(N, 64), dg)
 
 
+# LocoTransformer encoder layers (1 head, d=64) run as one fused kernel (csrc/tc_block.cu);
+# False = the unfused GEMM / attention / LayerNorm launches (kept for multi-head configurations).
+FUSED_LAYER = True
+
+
 class TcWeights:
   """Packed fp16 copies (forward and data-gradient orientations) of one network's GEMM weights."""
 
@@ -170,7 +175,7 @@ class _PlanTC:
       fn()
 
   def _lin_bwd(self, gflat, wname, x, x_cols, dy, dy_cols, M, dx=None, dx_map=None, mask=None, res=None,
-               need_dx=True, dy_pitch=0, dy_off=0):
+               need_dx=True, dy_pitch=0, dy_off=0, side=True):
     """dW, db from (x [M,x_cols], dy [M,dy_cols]) on the side stream; optionally
     dx = (dy @ W) * (mask > 0) + res on the main stream.  dy may be a column window of a wider
     matrix (row pitch dy_pitch elements, first column dy_off)."""
@@ -178,9 +183,13 @@ class _PlanTC:
     N, K = self.layout[wname][1][0], int(np.prod(self.layout[wname][1][1:]))
     inv = self._inv_scale
     st = (dy_pitch, dy_pitch, dy_pitch) if dy_pitch else None
-    self._side(lambda: self.ops.tc_wgrad(
+    wg = lambda: self.ops.tc_wgrad(
       x, (M, 1, 1, x_cols), dy, dy_cols, (M, 1, 1), (1, 1, 128), [(0, 0)], N, pk.dev_table, gflat,
-      out_scale=inv, dbias=self._view(gflat, wname[:-6] + "bias"), defer=True, dy_strides=st, dy_off=dy_off))
+      out_scale=inv, dbias=self._view(gflat, wname[:-6] + "bias"), defer=True, dy_strides=st, dy_off=dy_off)
+    if side:
+      self._side(wg)
+    else:
+      wg()
     if need_dx:
       pd = self.W.dgr[wname]
       self.ops.tc_gemm(dy, (M, 1, 1, dy_cols), (M, 1, 1), (1, 1, 128), [(0, 0)], pd.cols // 64, pd.w, pd.rows, K,
@@ -252,6 +261,7 @@ class LocoPlanTC(_PlanTC):
     super().__init__(ops, S, out_dim, layout, with_backward, "visual_seq_append_fcs.")
     self.n_heads = list(n_heads)
     self.T, self.d = 17, 64
+    self._diag = {}
 
   # ---- forward --------------------------------------------------------------------------------
   def forward(self, flat, imgs, idx, st, B, out):
@@ -276,9 +286,24 @@ class LocoPlanTC(_PlanTC):
     for l, nh in enumerate(self.n_heads):
       p = "visual_append_layers.%d." % l
       qkv = self.buf("qkv%d" % l, (R, 3 * d))
-      self._lin_fwd(flat, p + "self_attn.in_proj_weight", x, R, d, qkv, RM.dense(3 * d), False)
       o = self.buf("o%d" % l, (R, d))
       pr = self.buf("p%d" % l, (B, nh, T, T), torch.float32)
+      if nh == 1 and FUSED_LAYER:          # whole encoder layer in one tcgen05 kernel
+        h = self.buf("h%d" % l, (R, d)); f1 = self.buf("f1_%d" % l, (R, 256)); y = self.buf("y%d" % l, (R, d))
+        st1 = self.buf("st1_%d" % l, (R, 2), torch.float32); st2 = self.buf("st2_%d" % l, (R, 2), torch.float32)
+        xh1 = self.buf("xh1_%d" % l, (R, d)); xh2 = self.buf("xh2_%d" % l, (R, d))
+        w = {"w_in": self.W.fwd[p + "self_attn.in_proj_weight"].w, "w_o": self.W.fwd[p + "self_attn.out_proj.weight"].w,
+             "w_1": self.W.fwd[p + "linear1.weight"].w, "w_2": self.W.fwd[p + "linear2.weight"].w}
+        par = {"b_in": self._view(flat, p + "self_attn.in_proj_bias"), "b_o": self._view(flat, p + "self_attn.out_proj.bias"),
+               "g1": self._view(flat, p + "norm1.weight"), "be1": self._view(flat, p + "norm1.bias"),
+               "b1": self._view(flat, p + "linear1.bias"), "b2": self._view(flat, p + "linear2.bias"),
+               "g2": self._view(flat, p + "norm2.weight"), "be2": self._view(flat, p + "norm2.bias")}
+        ops.tc_block_fwd(x, B, T, w, par, dict(qkv=qkv, o=o, h=h, f1=f1, y=y, p=pr, st1=st1, st2=st2, xh1=xh1, xh2=xh2))
+        self._layers.append(dict(p=p, nh=nh, x=x, qkv=qkv, o=o, pr=pr, h=h, st1=st1, f1=f1, st2=st2, xh1=xh1, xh2=xh2,
+                                 fused=True))
+        x = y
+        continue
+      self._lin_fwd(flat, p + "self_attn.in_proj_weight", x, R, d, qkv, RM.dense(3 * d), False)
       ops.attn_fwd_f16(qkv, o, pr, B, T, d, nh)
       proj = self.buf("proj", (R, d))
       self._lin_fwd(flat, p + "self_attn.out_proj.weight", o, R, d, proj, RM.dense(d), False)
@@ -303,6 +328,42 @@ class LocoPlanTC(_PlanTC):
     return out
 
   # ---- backward -------------------------------------------------------------------------------
+  def _diag_table(self, name):
+    """index table that scatters the diagonal of a [64,64] xhat^T dy product to the LayerNorm weight
+    gradient (LayerNorm affine gradients ride on the weight-gradient GEMM)."""
+    t = self._diag.get(name)
+    if t is None:
+      tab = -np.ones((64, 64), np.int64)
+      tab[np.arange(64), np.arange(64)] = self.layout[name][0] + np.arange(64)
+      t = self._diag[name] = torch.tensor(tab.ravel().astype(np.int32), device=self.device)
+    return t
+
+  def _layer_bwd_fused(self, gflat, l, Ly, dy, B):
+    """One encoder layer: data gradients in one kernel (tc_block.cu), weight / bias / LayerNorm
+    gradients as side-stream GEMMs over the row gradients that kernel stores."""
+    ops, T, d, flat = self.ops, self.T, self.d, self._flat
+    R = B * T
+    p = Ly["p"]
+    inv = self._inv_scale
+    g = {k: self.buf("%s_%d" % (k, l), (R, n)) for k, n in (("dz2", d), ("df1", 256), ("dh", d), ("dz1", d),
+                                                            ("dqkv", 3 * d), ("dx", d))}
+    D = self.W.dgr
+    w = {"w2d": D[p + "linear2.weight"].w, "w1d": D[p + "linear1.weight"].w,
+         "wod": D[p + "self_attn.out_proj.weight"].w, "wind": D[p + "self_attn.in_proj_weight"].w}
+    saved = dict(qkv=Ly["qkv"], xh1=Ly["xh1"], xh2=Ly["xh2"], f1=Ly["f1"], p=Ly["pr"], st1=Ly["st1"], st2=Ly["st2"])
+    ops.tc_block_bwd(dy, B, T, saved, w, self._view(flat, p + "norm1.weight"), self._view(flat, p + "norm2.weight"), g)
+
+    def wgrads():
+      self._lin_bwd(gflat, p + "linear2.weight", Ly["f1"], 256, g["dz2"], d, R, need_dx=False, side=False)
+      self._lin_bwd(gflat, p + "linear1.weight", Ly["h"], d, g["df1"], 256, R, need_dx=False, side=False)
+      self._lin_bwd(gflat, p + "self_attn.out_proj.weight", Ly["o"], d, g["dz1"], d, R, need_dx=False, side=False)
+      self._lin_bwd(gflat, p + "self_attn.in_proj_weight", Ly["x"], d, g["dqkv"], 3 * d, R, need_dx=False, side=False)
+      for norm, xh, dyn in (("norm2", Ly["xh2"], dy), ("norm1", Ly["xh1"], g["dh"])):
+        ops.tc_wgrad(xh, (R, 1, 1, d), dyn, d, (R, 1, 1), (1, 1, 128), [(0, 0)], d, self._diag_table(p + norm + ".weight"),
+                     gflat, out_scale=inv, dbias=self._view(gflat, p + norm + ".bias"), defer=True)
+    self._side(wgrads)
+    return g["dx"]
+
   def backward(self, gflat, d_out):
     """d_out fp32 [B,out_dim]; writes every weight/bias/LayerNorm gradient (fp32) into gflat at
     the layout offsets."""
@@ -324,6 +385,9 @@ class LocoPlanTC(_PlanTC):
     for l in reversed(range(len(self._layers))):
       Ly = self._layers[l]
       p = Ly["p"]
+      if Ly.get("fused"):
+        dx = self._layer_bwd_fused(gflat, l, Ly, dx, B)
+        continue
       dz2 = self.buf("dz2_%d" % l, (R, d))
       ops.ln_bwd_f16(dx, Ly["z2"], Ly["st2"], self._view(flat, p + "norm2.weight"), dz2,
                      self._view(gflat, p + "norm2.weight"), self._view(gflat, p + "norm2.bias"), R, d, out_scale=inv)
