@@ -169,6 +169,9 @@ typedef struct v4l_tc_block_bwd_args {
   void *dz2, *df1, *dh, *dz1, *dqkv, *dx;
 } v4l_tc_block_bwd_args;
 int v4l_tc_block_bwd(v4l_ctx* ctx, void* stream, const v4l_tc_block_bwd_args* args);
+/* Profiling hook: per-phase globaltimer stamps (ns) of CTA 0 in the most recent fused forward
+ * (host_out[0..31]) and data-gradient (host_out[32..63]) launch; synchronises the device.  */
+int v4l_tc_block_timeline(unsigned long long* host_out);
 
 /* ---- GAE / discounted return: reverse segmented scan over the rollout buffer
  *      (reference torchrl/replay_buffers/on_policy.py:17-71; recurrence: SURVEY Appendix A4).

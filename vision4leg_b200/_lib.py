@@ -117,6 +117,7 @@ SIGNATURES = {
   "v4l_tc_attn_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i],
   "v4l_tc_block_fwd": [_vp, _vp, C.POINTER(TcBlockArgs)],
   "v4l_tc_block_bwd": [_vp, _vp, C.POINTER(TcBlockBwdArgs)],
+  "v4l_tc_block_timeline": [C.POINTER(C.c_uint64)],
   "v4l_tc_attn_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i],
   "v4l_gae": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i, _i, _d, _d, _i, _i],
   "v4l_select_rows": [_vp, _vp, _vp, _vp, _vp, _i],

@@ -427,6 +427,16 @@ __global__ void pf_loss_finalize_kernel(const double* __restrict__ part, int npa
 // =============================================================================================
 constexpr int ADAM_THREADS = 256;
 
+// sum of the per-CTA squared-norm partials by one warp: lane-strided partial sums, then a fixed
+// shuffle tree (the same order wherever it is called, so every CTA derives the same clip factor)
+__device__ __forceinline__ double sum_parts(const double* __restrict__ part, int nparts) {
+  double s = 0.0;
+  for (int i = threadIdx.x & 31; i < nparts; i += 32) s += part[i];
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
 __global__ void __launch_bounds__(ADAM_THREADS)
 sqnorm_kernel(const float* __restrict__ g, long long n, double* __restrict__ part) {
   v4l_pdl_enter();
@@ -447,11 +457,12 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
             const double* __restrict__ part, int nparts) {
   v4l_pdl_enter();
   __shared__ float s_coef;
-  if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int i = 0; i < nparts; ++i) s += part[i];       // same order in every CTA
-    const float total = (float)sqrt(s);
-    s_coef = fminf(hyper[4] / (total + 1e-6f), 1.f);     // clip_grad_norm_
+  if (threadIdx.x < 32) {
+    const double s = sum_parts(part, nparts);             // same order in every CTA
+    if (threadIdx.x == 0) {
+      const float total = (float)sqrt(s);
+      s_coef = fminf(hyper[4] / (total + 1e-6f), 1.f);    // clip_grad_norm_
+    }
   }
   __syncthreads();
   const float coef = s_coef;
@@ -474,12 +485,12 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 __global__ void adam_finish_kernel(float* hyper, const double* __restrict__ part, int nparts,
                                    float* info, const int32_t* slot, int norm_slot) {
   v4l_pdl_enter();
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    hyper[5] += 1.f;
-    if (info && norm_slot >= 0) {
-      double s = 0.0;
-      for (int i = 0; i < nparts; ++i) s += part[i];
-      info[(long long)(slot ? *slot : 0) * V4L_INFO_STRIDE + norm_slot] = (float)sqrt(s);
+  if (blockIdx.x == 0 && threadIdx.x < 32) {
+    const double s = sum_parts(part, nparts);
+    if (threadIdx.x == 0) {
+      hyper[5] += 1.f;
+      if (info && norm_slot >= 0)
+        info[(long long)(slot ? *slot : 0) * V4L_INFO_STRIDE + norm_slot] = (float)sqrt(s);
     }
   }
 }

@@ -21,6 +21,17 @@
 namespace {
 
 constexpr int BK_THREADS = 160;
+
+// phase timeline of CTA 0 (globaltimer ns), [0] forward kernel, [1] data-gradient kernel; read back by
+// v4l_tc_block_timeline().  One predicated store per phase: free next to the phases themselves.
+__device__ unsigned long long g_timeline[2][32];
+__device__ __forceinline__ void stamp(int which, int slot, bool on) {
+  if (on) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_timeline[which][slot] = t;
+  }
+}
 constexpr int TB = 128 * 128;              // one [128 rows][64 fp16] swizzled tile
 
 struct BlockParams {
@@ -76,6 +87,8 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
   __shared__ float s_par[192 + 64 * 6 + 256];   // b_in | b_o | g1 | be1 | b1(256) | b2 | g2 | be2
 
   v4l_pdl_trigger();
+  const bool tl = blockIdx.x == 0 && threadIdx.x == 32;
+  stamp(0, 0, tl);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * p.rows_per_tile;
   {  // zero the activation tiles (padding rows of a tile must be exact zeros / finite)
@@ -104,6 +117,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  stamp(0, 1, tl);
   const float *sb_in = s_par, *sb_o = s_par + 192, *sg1 = s_par + 256, *sbe1 = s_par + 320, *sb1 = s_par + 384,
               *sb2 = s_par + 640, *sg2 = s_par + 704, *sbe2 = s_par + 768;
   // TMEM columns: qkv [0,192)  S [192,320)  O [320,384)  proj [384,448)  f1 [0,256) (after qkv is consumed)
@@ -200,6 +214,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
 
     // ---- (1) qkv epilogue: + bias -> fp16 -> q/k/v tiles + global
     tc::mbar_wait(&bar_m[0], 0);
+    stamp(0, 3, tl);
     tc::tc_fence_after();
     for (int c0 = 0; c0 < 192; c0 += 32) {
       uint32_t v[32];
@@ -219,9 +234,11 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
     tc::tc_fence_before();
     tc::fence_proxy_async();
     tc::mbar_arrive(&bar_e[0]);
+    stamp(0, 2, tl);
 
     // ---- (2) masked softmax over the sample's own keys -> P (unnormalised, fp16) tiles
     tc::mbar_wait(&bar_m[1], 0);
+    stamp(0, 5, tl);
     tc::tc_fence_after();
     float mx = -3.0e38f;
     for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -254,6 +271,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
     tc::tc_fence_before();
     tc::fence_proxy_async();
     tc::mbar_arrive(&bar_e[1]);
+    stamp(0, 4, tl);
     if (live) {     // normalised probabilities of the block -> global (backward)
       float* prow = p.p + (long long)grow * p.T;
       for (int col = lo; col < hi; ++col) {
@@ -265,6 +283,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
 
     // ---- (3) O epilogue: / sum -> fp16 -> O tile + global
     tc::mbar_wait(&bar_m[2], 0);
+    stamp(0, 7, tl);
     tc::tc_fence_after();
 #pragma unroll
     for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -284,9 +303,11 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
     tc::tc_fence_before();
     tc::fence_proxy_async();
     tc::mbar_arrive(&bar_e[2]);
+    stamp(0, 6, tl);
 
     // ---- (4) out-proj epilogue: + bias + x -> LayerNorm1 -> h (tile over x, global), z1, stats1
     tc::mbar_wait(&bar_m[3], 0);
+    stamp(0, 9, tl);
     tc::tc_fence_after();
     {
       float zrow[64];
@@ -346,9 +367,11 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
     tc::tc_fence_before();
     tc::fence_proxy_async();
     tc::mbar_arrive(&bar_e[3]);
+    stamp(0, 8, tl);
 
     // ---- (5) FFN1 epilogue: + bias, ReLU -> f1 tiles (over q/k/v/P) + global
     tc::mbar_wait(&bar_m[4], 0);
+    stamp(0, 11, tl);
     tc::tc_fence_after();
     for (int c0 = 0; c0 < 256; c0 += 32) {
       uint32_t v[32];
@@ -368,9 +391,11 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
     tc::tc_fence_before();
     tc::fence_proxy_async();
     tc::mbar_arrive(&bar_e[4]);
+    stamp(0, 10, tl);
 
     // ---- (6) FFN2 epilogue: + bias + h -> LayerNorm2 -> y, z2, stats2
     tc::mbar_wait(&bar_m[5], 0);
+    stamp(0, 13, tl);
     tc::tc_fence_after();
     {
       float zrow[64];
@@ -425,6 +450,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
         }
       }
     }
+    stamp(0, 20, tl);
     tc::tc_fence_before();
   }
   __syncthreads();
@@ -504,6 +530,8 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
   __shared__ float s_g[128];                  // g2 | g1
 
   v4l_pdl_trigger();
+  const bool tl = blockIdx.x == 0 && threadIdx.x == 32;
+  stamp(1, 0, tl);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * p.rows_per_tile;
   {
@@ -525,6 +553,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  stamp(1, 1, tl);
   // TMEM columns: df1 [0,256)  dh [256,320)  do [320,384)  dx [384,448);  dP [0,128), dQ|dK|dV [128,320) later
   constexpr uint32_t C_DF1 = 0, C_DH = 256, C_DO = 320, C_DX = 384, C_DP = 0, C_DQKV = 128;
 
@@ -657,9 +686,11 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
     }
     tc::fence_proxy_async();
     tc::mbar_arrive(&bar_e[0]);
+    stamp(1, 2, tl);
 
     // ---- (b) df1 = (dz2 W2) * (f1 > 0) -> tiles R2 + global
     tc::mbar_wait(&bar_m[0], 0);
+    stamp(1, 3, tl);
     tc::tc_fence_after();
     for (int c0 = 0; c0 < 256; c0 += 32) {
       uint32_t v[32];
@@ -687,9 +718,11 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
     tc::tc_fence_before();
     tc::fence_proxy_async();
     tc::mbar_arrive(&bar_e[1]);
+    stamp(1, 4, tl);
 
     // ---- (c) dh = df1 W1 + dz2 -> global (LN1 affine gradients); LayerNorm1 backward -> dz1 (R3 + global)
     tc::mbar_wait(&bar_m[1], 0);
+    stamp(1, 5, tl);
     tc::tc_fence_after();
     {
       float d[64];
@@ -729,9 +762,11 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
     tc::tc_fence_before();
     tc::fence_proxy_async();
     tc::mbar_arrive(&bar_e[2]);
+    stamp(1, 6, tl);
 
     // ---- (d) do = dz1 Wo -> tile R1 (never leaves the SM)
     tc::mbar_wait(&bar_m[2], 0);
+    stamp(1, 7, tl);
     tc::tc_fence_after();
 #pragma unroll
     for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -747,9 +782,11 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
     tc::tc_fence_before();
     tc::fence_proxy_async();
     tc::mbar_arrive(&bar_e[3]);
+    stamp(1, 8, tl);
 
     // ---- (e) dS = P (dP - rowsum(dP P)) scale and P -> tiles R2 (dS: 0,1; P: 2,3)
     tc::mbar_wait(&bar_m[3], 0);
+    stamp(1, 9, tl);
     tc::tc_fence_after();
     {
       const float* prow = p.p + gr * p.T;
@@ -787,9 +824,11 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
     tc::tc_fence_before();
     tc::fence_proxy_async();
     tc::mbar_arrive(&bar_e[4]);
+    stamp(1, 10, tl);
 
     // ---- (f) dQ | dK | dV -> tiles R4 + global dqkv
     tc::mbar_wait(&bar_m[4], 0);
+    stamp(1, 11, tl);
     tc::tc_fence_after();
     for (int c0 = 0; c0 < 192; c0 += 32) {
       uint32_t v[32];
@@ -809,9 +848,11 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
     tc::tc_fence_before();
     tc::fence_proxy_async();
     tc::mbar_arrive(&bar_e[5]);
+    stamp(1, 12, tl);
 
     // ---- (g) dx = dqkv Win + dz1 -> global
     tc::mbar_wait(&bar_m[5], 0);
+    stamp(1, 13, tl);
     tc::tc_fence_after();
 #pragma unroll
     for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -832,6 +873,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
         if (live) *reinterpret_cast<uint4*>(p.dx + (long long)grow * 64 + c0 + 8 * q) = pack8(f);
       }
     }
+    stamp(1, 20, tl);
     tc::tc_fence_before();
   }
   __syncthreads();
@@ -908,5 +950,15 @@ extern "C" int v4l_tc_block_bwd(v4l_ctx* ctx, void* stream, const v4l_tc_block_b
     attr = true;
   }
   V4L_LAUNCH(tc_block_bwd_kernel, v4l_cdiv(a->B, spt), BK_THREADS, BWD_SMEM + 1024, (cudaStream_t)stream, p);
+  return 0;
+}
+
+// diagnostics: globaltimer stamps (ns) of CTA 0's epilogue thread in the most recent forward ([0..31])
+// and data-gradient ([32..63]) launch: 0 start, 1 set-up done, 2+2i epilogue i finished,
+// 3+2i MMA i result observed, 20 end.  Synchronises the device.
+extern "C" int v4l_tc_block_timeline(unsigned long long* host_out) {
+  V4L_REQUIRE(host_out, "v4l_tc_block_timeline: NULL argument");
+  V4L_CHECK_CUDA(cudaDeviceSynchronize());
+  V4L_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(unsigned long long) * 64));
   return 0;
 }

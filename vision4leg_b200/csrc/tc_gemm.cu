@@ -546,30 +546,46 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
 // partial[split][kp/128][kp%128][n]; dbias[n] = scale * sum_split partial[split][kin_tiles][0][n]
 struct ReduceJobs { v4l_reduce_job j[V4L_MAX_JOBS]; };
 
-__global__ void tc_wgrad_reduce_kernel(const __grid_constant__ ReduceJobs jobs) {
+__global__ void __launch_bounds__(256) tc_wgrad_reduce_kernel(const __grid_constant__ ReduceJobs jobs) {
+  // partial[split][kp][n] (n contiguous) -> dw[index[n][kp]] (kp contiguous): 32x32 tiles through
+  // shared memory so that both the split-sum reads and the scattered writes are coalesced
   v4l_pdl_enter();
+  __shared__ float tile[32][33];
   const v4l_reduce_job& J = jobs.j[blockIdx.y];
-  const long long nw = (long long)J.N_valid * J.Kp;
-  const long long total = nw + (J.has_bias ? J.N_valid : 0);
   const long long split_stride = (long long)(J.kin_tiles + J.has_bias) * 128 * J.Nmma;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x) {
-    const float* src;
-    float* dst;
-    if (e < nw) {
-      const int kp = (int)(e % J.Kp), n = (int)(e / J.Kp);        // consecutive threads: consecutive kp
-      const long long d = J.index ? (long long)J.index[(long long)n * J.Kp + kp] : e;
-      if (d < 0) continue;
-      dst = J.dw + d;
-      src = J.partial + (long long)kp * J.Nmma + n;
-    } else {
-      const int n = (int)(e - nw);
-      dst = J.dbias + n;
-      src = J.partial + (long long)J.kin_tiles * 128 * J.Nmma + n;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tk = (J.Kp + 31) >> 5, tn = (J.N_valid + 31) >> 5;
+  for (int t = blockIdx.x; t < tk * tn; t += gridDim.x) {
+    const int kp0 = (t % tk) << 5, n0 = (t / tk) << 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kp = kp0 + ty + 8 * i, n = n0 + tx;
+      float s = 0.f;
+      if (kp < J.Kp && n < J.N_valid) {
+        const float* src = J.partial + (long long)kp * J.Nmma + n;
+        for (int z = 0; z < J.splits; ++z) s += src[z * split_stride];
+      }
+      tile[ty + 8 * i][tx] = s;
     }
-    float s = 0.f;
-    for (int z = 0; z < J.splits; ++z) s += src[z * split_stride];
-    *dst = s * J.scale;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = n0 + ty + 8 * i, kp = kp0 + tx;
+      if (kp < J.Kp && n < J.N_valid) {
+        const long long e = (long long)n * J.Kp + kp;
+        const long long d = J.index ? (long long)J.index[e] : e;
+        if (d >= 0) J.dw[d] = tile[tx][ty + 8 * i] * J.scale;
+      }
+    }
+    __syncthreads();
+  }
+  if (J.has_bias && blockIdx.x == gridDim.x - 1) {
+    const float* src0 = J.partial + (long long)J.kin_tiles * 128 * J.Nmma;
+    for (int n = threadIdx.x; n < J.N_valid; n += blockDim.x) {
+      float s = 0.f;
+      for (int z = 0; z < J.splits; ++z) s += src0[z * split_stride + n];
+      J.dbias[n] = s * J.scale;
+    }
   }
 }
 
@@ -688,7 +704,9 @@ extern "C" int v4l_tc_wgrad(v4l_ctx* ctx, void* stream, const v4l_tc_wgrad_args*
   }
   float* region = a->defer ? ctx->defer_base + ctx->defer_cursor : ctx->scratch;
   const size_t avail = a->defer ? ctx->defer_elems - ctx->defer_cursor : ctx->scratch_elems;
-  int splits = max(1, min(p.num_tiles, min(32, ctx->sm_count / ytiles)));
+  // split-K over the row tiles: >= 8 row tiles per CTA (the partial sums cost 128 x Nmma floats of
+  // traffic per CTA, twice), at most one wave; several of these launches run side by side
+  int splits = max(1, min(p.num_tiles / 8, min(48, ctx->sm_count / ytiles)));
   splits = (int)min((size_t)splits, avail / ((size_t)ytiles * 128 * Nmma));
   V4L_REQUIRE(splits >= 1, "v4l_tc_wgrad: scratch too small (flush deferred reductions more often)");
   p.tiles_per_split = v4l_cdiv(p.num_tiles, splits);
@@ -727,7 +745,7 @@ extern "C" int v4l_tc_wgrad_flush(v4l_ctx* ctx, void* stream) {
   ReduceJobs all;
   memset(&all, 0, sizeof(all));
   for (int i = 0; i < ctx->n_jobs; ++i) all.j[i] = ctx->jobs[i];
-  V4L_LAUNCH(tc_wgrad_reduce_kernel, dim3(16, ctx->n_jobs), 256, 0, (cudaStream_t)stream, all);
+  V4L_LAUNCH(tc_wgrad_reduce_kernel, dim3(32, ctx->n_jobs), 256, 0, (cudaStream_t)stream, all);
   ctx->n_jobs = 0;
   ctx->defer_cursor = 0;
   V4L_CHECK_LAUNCH();

@@ -78,6 +78,7 @@ def _conv_tables(off, N, C, KH, KW, s):
 # LocoTransformer encoder layers (1 head, d=64) run as one fused kernel (csrc/tc_block.cu);
 # False = the unfused GEMM / attention / LayerNorm launches (kept for multi-head configurations).
 FUSED_LAYER = True
+N_WGRAD_STREAMS = 4
 
 
 class TcWeights:
@@ -135,6 +136,7 @@ class _PlanTC:
     self.layout = layout
     self.W = TcWeights(ops, layout, with_dgrad=with_backward)
     self._ws = {}
+    self._rr, self._forked = 0, set()
     self.k_base = [k for k in layout if k.startswith("encoder.base.seq_fcs.") and k.endswith("weight")]
     self.k_head = sorted((k for k in layout if k.startswith(head_prefix) and k.endswith("weight")),
                          key=lambda k: int(k.split(".")[-2]))
@@ -168,11 +170,22 @@ class _PlanTC:
     self.ops.tc_gemm(x, (M, 1, 1, K), (M, 1, 1), (1, 1, 128), [(0, 0)], pk.cols // 64, pk.w, pk.rows, N, bias,
                      out, out_map, c_f32=c_f32, flags=RELU if relu else 0)
 
-  def _side(self, fn):
-    """Run `fn` (weight-gradient launches) on the side stream: they only READ activations and
-    gradients that are never overwritten during this backward, so they leave the critical path."""
-    with self.ops.fork():
+  def _side(self, fn, which=None):
+    """Run `fn` on a side stream, ordered after what has been issued so far.  Weight-gradient
+    launches only READ activations and gradients that are never overwritten during this backward,
+    so they leave the critical path; they are small grids (8-96 CTAs), hence round-robin over
+    N_WGRAD_STREAMS streams so that several run at once.  `which` pins a branch to one stream."""
+    if which is None:
+      which = "w%d" % (self._rr % N_WGRAD_STREAMS)
+      self._rr += 1
+    self._forked.add(which)
+    with self.ops.fork(which):
       fn()
+
+  def _join_all(self):
+    for w in sorted(self._forked, key=str):
+      self.ops.join(w)
+    self._forked.clear()
 
   def _lin_bwd(self, gflat, wname, x, x_cols, dy, dy_cols, M, dx=None, dx_map=None, mask=None, res=None,
                need_dx=True, dy_pitch=0, dy_off=0, side=True):
@@ -276,10 +289,10 @@ class LocoPlanTC(_PlanTC):
       self._lin_fwd(flat, self.k_base[0], st, B, self.Sp, s1, RM.dense(256), True)
       self._lin_fwd(flat, self.k_base[1], s1, B, 256, s2, RM.dense(256), True)
       self._lin_fwd(flat, "encoder.state_projector.projection.0.weight", s2, B, 256, tok, RM.slots(1, T, d, 0), True)
-    self._side(state_branch)
+    self._side(state_branch, which=0)
     a3 = self._trunk_fwd(flat, imgs, idx, B, "encoder.depth_visual_base.layers.")
     self._lin_fwd(flat, "encoder.depth_up_conv.weight", a3, B * 16, 64, tok, RM.slots(16, T, d, 1), False)
-    ops.join()
+    self._join_all()
     R = B * T
     x = tok
     self._layers = []
@@ -353,15 +366,14 @@ class LocoPlanTC(_PlanTC):
     saved = dict(qkv=Ly["qkv"], xh1=Ly["xh1"], xh2=Ly["xh2"], f1=Ly["f1"], p=Ly["pr"], st1=Ly["st1"], st2=Ly["st2"])
     ops.tc_block_bwd(dy, B, T, saved, w, self._view(flat, p + "norm1.weight"), self._view(flat, p + "norm2.weight"), g)
 
-    def wgrads():
-      self._lin_bwd(gflat, p + "linear2.weight", Ly["f1"], 256, g["dz2"], d, R, need_dx=False, side=False)
-      self._lin_bwd(gflat, p + "linear1.weight", Ly["h"], d, g["df1"], 256, R, need_dx=False, side=False)
-      self._lin_bwd(gflat, p + "self_attn.out_proj.weight", Ly["o"], d, g["dz1"], d, R, need_dx=False, side=False)
-      self._lin_bwd(gflat, p + "self_attn.in_proj_weight", Ly["x"], d, g["dqkv"], 3 * d, R, need_dx=False, side=False)
-      for norm, xh, dyn in (("norm2", Ly["xh2"], dy), ("norm1", Ly["xh1"], g["dh"])):
-        ops.tc_wgrad(xh, (R, 1, 1, d), dyn, d, (R, 1, 1), (1, 1, 128), [(0, 0)], d, self._diag_table(p + norm + ".weight"),
-                     gflat, out_scale=inv, dbias=self._view(gflat, p + norm + ".bias"), defer=True)
-    self._side(wgrads)
+    self._lin_bwd(gflat, p + "linear2.weight", Ly["f1"], 256, g["dz2"], d, R, need_dx=False)
+    self._lin_bwd(gflat, p + "linear1.weight", Ly["h"], d, g["df1"], 256, R, need_dx=False)
+    self._lin_bwd(gflat, p + "self_attn.out_proj.weight", Ly["o"], d, g["dz1"], d, R, need_dx=False)
+    self._lin_bwd(gflat, p + "self_attn.in_proj_weight", Ly["x"], d, g["dqkv"], 3 * d, R, need_dx=False)
+    for norm, xh, dyn in (("norm2", Ly["xh2"], dy), ("norm1", Ly["xh1"], g["dh"])):
+      self._side(lambda: ops.tc_wgrad(
+        xh, (R, 1, 1, d), dyn, d, (R, 1, 1), (1, 1, 128), [(0, 0)], d, self._diag_table(p + norm + ".weight"),
+        gflat, out_scale=inv, dbias=self._view(gflat, p + norm + ".bias"), defer=True))
     return g["dx"]
 
   def backward(self, gflat, d_out):
@@ -417,7 +429,7 @@ class LocoPlanTC(_PlanTC):
       self._lin_bwd(gflat, "encoder.state_projector.projection.0.weight", s2, 256, ds, d, B, ds2, RM.dense(256), mask=s2)
       self._lin_bwd(gflat, self.k_base[1], s1, 256, ds2, 256, B, ds1, RM.dense(256), mask=s1)
       self._lin_bwd(gflat, self.k_base[0], self._st, self.Sp, ds1, 256, B, need_dx=False)
-    self._side(state_branch)
+    self._side(state_branch, which=0)
     # depth tokens -> 1x1 up-conv (dY is the strided [B,16,64] window of the token gradient)
     a3 = ws[("a3", B, 16, 64)]
     up = "encoder.depth_up_conv.weight"
@@ -430,7 +442,7 @@ class LocoPlanTC(_PlanTC):
     ops.tc_gemm(dx, (B, 1, 16, 64), (B, 1, 16), (16, 1, 8), [(0, 0)], 1, pd.w, pd.rows, 64, None, da3,
                 RM(16, 16 * 64, 64, 0), mask=a3, a_strides=strides, a_off=d)
     self._trunk_bwd(gflat, da3, B, "encoder.depth_visual_base.layers.")
-    ops.join()
+    self._join_all()
     ops.tc_wgrad_flush()
 
 
@@ -477,7 +489,7 @@ class NaturePlanTC(_PlanTC):
     da3 = self.buf("da3", (B, 16, 64))
     self._lin_bwd(gflat, self.k_proj, a3, 1024, dcat, self.vd, B, da3, RM.dense(1024), mask=a3, dy_pitch=W, dy_off=0)
     self._trunk_bwd(gflat, da3, B, "encoder.visual_base.layers.")
-    ops.join()
+    self._join_all()
     ops.tc_wgrad_flush()
 
 
