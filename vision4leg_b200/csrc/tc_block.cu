@@ -40,6 +40,7 @@ struct BlockParams {
   CUtensorMap tm_wo;       // [64, 64]  box {64, 64}
   CUtensorMap tm_w1;       // [256, 64] box {64, 256}
   CUtensorMap tm_w2;       // [64, 256] box {64, 64} (4 k-chunks)
+  CUtensorMap tm_qkv_o, tm_o_o, tm_h_o, tm_f1_o;   // outputs [R,192] [R,64] [R,64] [R,256], box {64, rows_per_tile}
   int R, T, rows_per_tile;
   float scale, eps;
   const float *b_in, *b_o, *g1, *be1, *b1, *b2, *g2, *be2;
@@ -79,6 +80,23 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return w;
 }
 
+// Walk NCOLS accumulator columns (a multiple of 64) in 32-column chunks with the TMEM load of the next
+// chunk in flight while the current one is processed: fn(c0, v) gets the 32 fp32 bit patterns.
+template <int NCOLS, class F>
+__device__ __forceinline__ void tmem_walk(uint32_t taddr, F&& fn) {
+  uint32_t va[32], vb[32];
+  tc::tmem_ld_32x32(taddr, va);
+#pragma unroll
+  for (int c0 = 0; c0 < NCOLS; c0 += 64) {
+    tc::tmem_ld_wait();
+    tc::tmem_ld_32x32(taddr + c0 + 32, vb);
+    fn(c0, va);
+    tc::tmem_ld_wait();
+    if (c0 + 64 < NCOLS) tc::tmem_ld_32x32(taddr + c0 + 64, va);
+    fn(c0 + 32, vb);
+  }
+}
+
 __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __grid_constant__ BlockParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -98,6 +116,8 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&p.tm_x); tc::tma_prefetch_desc(&p.tm_win); tc::tma_prefetch_desc(&p.tm_wo);
     tc::tma_prefetch_desc(&p.tm_w1); tc::tma_prefetch_desc(&p.tm_w2);
+    tc::tma_prefetch_desc(&p.tm_qkv_o); tc::tma_prefetch_desc(&p.tm_o_o); tc::tma_prefetch_desc(&p.tm_h_o);
+    tc::tma_prefetch_desc(&p.tm_f1_o);
     tc::mbar_init(&bar_in, 1); tc::mbar_init(&bar_w, 1);
     for (int i = 0; i < 6; ++i) tc::mbar_init(&bar_m[i], 1);
     for (int i = 0; i < 5; ++i) tc::mbar_init(&bar_e[i], 128);
@@ -145,9 +165,11 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
                        tc::umma_smem_desc(base + OFF_WIN + k * 32, 0, 1024), id, k ? 1u : 0u);
         tc::umma_commit(&bar_m[0]);
       }
-      // (2) S = Q K^T
+      // (2) S = Q K^T   (the q|k|v tiles leave for HBM by TMA meanwhile)
       tc::mbar_wait(&bar_e[0], 0);
       tc::tc_fence_after();
+      for (int c = 0; c < 3; ++c) tc::tma_store_2d(&p.tm_qkv_o, sm + OFF_QKV + c * TB, c * 64, row0);
+      tc::tma_store_commit();
       {
         const uint32_t id = tc::umma_idesc_f16(128, 128, 0, 0);
 #pragma unroll
@@ -171,6 +193,8 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
       tc::mbar_wait(&bar_e[2], 0);
       tc::mbar_wait(&bar_w, 0);
       tc::tc_fence_after();
+      tc::tma_store_2d(&p.tm_o_o, sm + OFF_O, 0, row0);
+      tc::tma_store_commit();
       {
         const uint32_t id = tc::umma_idesc_f16(128, 64, 0, 0);
 #pragma unroll
@@ -182,6 +206,9 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
       // (5) f1 = h W1^T   (h lives where x was)
       tc::mbar_wait(&bar_e[3], 0);
       tc::tc_fence_after();
+      tc::tma_store_wait_read();            // q|k|v have left: the f1 epilogue may overwrite their tiles
+      tc::tma_store_2d(&p.tm_h_o, sm + OFF_X, 0, row0);
+      tc::tma_store_commit();
       {
         const uint32_t id = tc::umma_idesc_f16(128, 256, 0, 0);
 #pragma unroll
@@ -193,6 +220,8 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
       // (6) f2 = f1 W2^T  (K = 256: 4 tiles of A, 4 k-chunk tiles of W2)
       tc::mbar_wait(&bar_e[4], 0);
       tc::tc_fence_after();
+      for (int c = 0; c < 4; ++c) tc::tma_store_2d(&p.tm_f1_o, sm + OFF_F1 + c * TB, c * 64, row0);
+      tc::tma_store_commit();
       {
         const uint32_t id = tc::umma_idesc_f16(128, 64, 0, 0);
 #pragma unroll
@@ -202,6 +231,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
                        k ? 1u : 0u);
         tc::umma_commit(&bar_m[5]);
       }
+      tc::tma_store_wait_all();
     }
   } else {
     const int quad = warp & 3;
@@ -216,21 +246,16 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
     tc::mbar_wait(&bar_m[0], 0);
     stamp(0, 3, tl);
     tc::tc_fence_after();
-    for (int c0 = 0; c0 < 192; c0 += 32) {
-      uint32_t v[32];
-      tc::tmem_ld_32x32(ta + C_QKV + c0, v);
-      tc::tmem_ld_wait();
+    tmem_walk<192>(ta + C_QKV, [&](int c0, const uint32_t (&v)[32]) {
       float f[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = live ? __uint_as_float(v[j]) + sb_in[c0 + j] : 0.f;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const uint4 w = pack8(f + 8 * q);
         const int col = c0 + 8 * q;
-        st_sw(sm + OFF_QKV + (col >> 6) * TB, r, (col & 63) >> 3, w);
-        if (live) *reinterpret_cast<uint4*>(p.qkv + (long long)grow * 192 + col) = w;
+        st_sw(sm + OFF_QKV + (col >> 6) * TB, r, (col & 63) >> 3, pack8(f + 8 * q));
       }
-    }
+    });
     tc::tc_fence_before();
     tc::fence_proxy_async();
     tc::mbar_arrive(&bar_e[0]);
@@ -240,31 +265,40 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
     tc::mbar_wait(&bar_m[1], 0);
     stamp(0, 5, tl);
     tc::tc_fence_after();
+    // only the 32-column chunks that hold this warp's samples are read (TMEM loads are warp-wide);
+    // each thread then touches the 1-2 chunks of its own sample; the rest of P stays zero (prologue)
+    const int wlo = ((quad * 32) / p.T) * p.T;
+    const int whi = ((quad * 32 + 31) / p.T + 1) * p.T;
+    const int cb = wlo & ~31, ce = min(128, (whi + 31) & ~31);
     float mx = -3.0e38f;
-    for (int c0 = 0; c0 < 128; c0 += 32) {
+    for (int c0 = cb; c0 < ce; c0 += 32) {
       uint32_t v[32];
       tc::tmem_ld_32x32(ta + C_S + c0, v);
       tc::tmem_ld_wait();
+      if (c0 + 32 > lo && c0 < hi) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (c0 + j >= lo && c0 + j < hi) mx = fmaxf(mx, __uint_as_float(v[j]));
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j >= lo && c0 + j < hi) mx = fmaxf(mx, __uint_as_float(v[j]));
+      }
     }
     float sum = 0.f;
-    for (int c0 = 0; c0 < 128; c0 += 32) {
+    for (int c0 = cb; c0 < ce; c0 += 32) {
       uint32_t v[32];
       tc::tmem_ld_32x32(ta + C_S + c0, v);
       tc::tmem_ld_wait();
-      float e[32];
+      if (c0 + 32 > lo && c0 < hi) {
+        float e[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const bool in = live && (c0 + j >= lo) && (c0 + j < hi);
-        e[j] = in ? __expf((__uint_as_float(v[j]) - mx) * p.scale) : 0.f;
-        sum += e[j];
-      }
+        for (int j = 0; j < 32; ++j) {
+          const bool in = live && (c0 + j >= lo) && (c0 + j < hi);
+          e[j] = in ? __expf((__uint_as_float(v[j]) - mx) * p.scale) : 0.f;
+          sum += e[j];
+        }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int col = c0 + 8 * q;
-        st_sw(sm + OFF_P + (col >> 6) * TB, r, (col & 63) >> 3, pack8(e + 8 * q));
+        for (int q = 0; q < 4; ++q) {
+          const int col = c0 + 8 * q;
+          st_sw(sm + OFF_P + (col >> 6) * TB, r, (col & 63) >> 3, pack8(e + 8 * q));
+        }
       }
     }
     const float inv = live ? 1.f / sum : 0.f;
@@ -295,9 +329,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
       for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * inv;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const uint4 w = pack8(f + 8 * q);
-        st_sw(sm + OFF_O, r, (c0 >> 3) + q, w);
-        if (live) *reinterpret_cast<uint4*>(p.o + (long long)grow * 64 + c0 + 8 * q) = w;
+        st_sw(sm + OFF_O, r, (c0 >> 3) + q, pack8(f + 8 * q));
       }
     }
     tc::tc_fence_before();
@@ -359,9 +391,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
           const int c = 8 * q + j;
           f[j] = live ? zrow[c] * sg1[c] + sbe1[c] : 0.f;
         }
-        const uint4 w = pack8(f);
-        st_sw(sm + OFF_X, r, q, w);                       // h replaces x (each thread only touches its row)
-        if (live) *reinterpret_cast<uint4*>(p.h + (long long)grow * 64 + 8 * q) = w;
+        st_sw(sm + OFF_X, r, q, pack8(f));                // h replaces x (each thread only touches its row)
       }
     }
     tc::tc_fence_before();
@@ -373,21 +403,16 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
     tc::mbar_wait(&bar_m[4], 0);
     stamp(0, 11, tl);
     tc::tc_fence_after();
-    for (int c0 = 0; c0 < 256; c0 += 32) {
-      uint32_t v[32];
-      tc::tmem_ld_32x32(ta + C_F1 + c0, v);
-      tc::tmem_ld_wait();
+    tmem_walk<256>(ta + C_F1, [&](int c0, const uint32_t (&v)[32]) {
       float f[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = live ? fmaxf(__uint_as_float(v[j]) + sb1[c0 + j], 0.f) : 0.f;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const uint4 w = pack8(f + 8 * q);
         const int col = c0 + 8 * q;
-        st_sw(sm + OFF_F1 + (col >> 6) * TB, r, (col & 63) >> 3, w);
-        if (live) *reinterpret_cast<uint4*>(p.f1 + (long long)grow * 256 + col) = w;
+        st_sw(sm + OFF_F1 + (col >> 6) * TB, r, (col & 63) >> 3, pack8(f + 8 * q));
       }
-    }
+    });
     tc::tc_fence_before();
     tc::fence_proxy_async();
     tc::mbar_arrive(&bar_e[4]);
@@ -473,6 +498,8 @@ struct BlockBwdParams {
   CUtensorMap tm_w1d;      // [64,256]  box {64,64}    (W1^T: rows = h column), 4 k-chunks
   CUtensorMap tm_wod;      // [64,64]   box {64,64}
   CUtensorMap tm_wind;     // [64,192]  box {64,64}    (Win^T: rows = x column), 3 k-chunks
+  CUtensorMap tm_f1;       // [R,256]   box {64, rows_per_tile}: ReLU gate, loaded where df1 is written
+  CUtensorMap tm_dz2_o, tm_df1_o, tm_dz1_o, tm_dqkv_o;     // outputs, box {64, rows_per_tile}
   int R, T, rows_per_tile;
   float scale;
   const float *g1, *g2, *st1, *st2, *p;
@@ -525,7 +552,7 @@ __device__ __forceinline__ void ln_bwd_row(float (&d)[64], const uint4 (&xh)[8],
 __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __grid_constant__ BlockBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t bar_qkv, bar_wa, bar_wb, bar_m[6], bar_e[6];
+  __shared__ uint64_t bar_qkv, bar_f1, bar_wa, bar_wb, bar_m[6], bar_e[6];
   __shared__ uint32_t tmem_slot;
   __shared__ float s_g[128];                  // g2 | g1
 
@@ -540,8 +567,10 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
   }
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&p.tm_qkv); tc::tma_prefetch_desc(&p.tm_w2d); tc::tma_prefetch_desc(&p.tm_w1d);
-    tc::tma_prefetch_desc(&p.tm_wod); tc::tma_prefetch_desc(&p.tm_wind);
-    tc::mbar_init(&bar_qkv, 1); tc::mbar_init(&bar_wa, 1); tc::mbar_init(&bar_wb, 1);
+    tc::tma_prefetch_desc(&p.tm_wod); tc::tma_prefetch_desc(&p.tm_wind); tc::tma_prefetch_desc(&p.tm_f1);
+    tc::tma_prefetch_desc(&p.tm_dz2_o); tc::tma_prefetch_desc(&p.tm_df1_o); tc::tma_prefetch_desc(&p.tm_dz1_o);
+    tc::tma_prefetch_desc(&p.tm_dqkv_o);
+    tc::mbar_init(&bar_qkv, 1); tc::mbar_init(&bar_f1, 1); tc::mbar_init(&bar_wa, 1); tc::mbar_init(&bar_wb, 1);
     for (int i = 0; i < 6; ++i) { tc::mbar_init(&bar_m[i], 1); tc::mbar_init(&bar_e[i], 128); }
     tc::fence_barrier_init();
   }
@@ -563,12 +592,16 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
       tc::mbar_expect_tx(&bar_wa, 64u * 1024u);
       tc::tma_load_2d(sm + BO_W, &p.tm_w2d, &bar_wa, 0, 0);
       for (int c = 0; c < 4; ++c) tc::tma_load_2d(sm + BO_W + 32 * 1024 + c * 8192, &p.tm_w1d, &bar_wa, c * 64, 0);
+      tc::mbar_expect_tx(&bar_f1, 4u * p.rows_per_tile * 128u);
+      for (int c = 0; c < 4; ++c) tc::tma_load_2d(sm + BO_R2 + c * TB, &p.tm_f1, &bar_f1, c * 64, row0);
       tc::mbar_expect_tx(&bar_qkv, 3u * p.rows_per_tile * 128u);
       for (int c = 0; c < 3; ++c) tc::tma_load_2d(sm + BO_R4 + c * TB, &p.tm_qkv, &bar_qkv, c * 64, row0);
       // (1) df1 = dz2 W2
       tc::mbar_wait(&bar_e[0], 0);
       tc::mbar_wait(&bar_wa, 0);
       tc::tc_fence_after();
+      tc::tma_store_2d(&p.tm_dz2_o, sm + BO_R1, 0, row0);
+      tc::tma_store_commit();
       {
         const uint32_t id = tc::umma_idesc_f16(128, 256, 0, 0);
 #pragma unroll
@@ -580,6 +613,8 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
       // (2) dh = df1 W1
       tc::mbar_wait(&bar_e[1], 0);
       tc::tc_fence_after();
+      for (int c = 0; c < 4; ++c) tc::tma_store_2d(&p.tm_df1_o, sm + BO_R2 + c * TB, c * 64, row0);
+      tc::tma_store_commit();
       {
         const uint32_t id = tc::umma_idesc_f16(128, 64, 0, 0);
 #pragma unroll
@@ -598,6 +633,9 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
       tc::mbar_wait(&bar_e[2], 0);
       tc::mbar_wait(&bar_wb, 0);
       tc::tc_fence_after();
+      tc::tma_store_wait_read();            // dz2 and df1 have left: do / dS / P may overwrite their tiles
+      tc::tma_store_2d(&p.tm_dz1_o, sm + BO_R3, 0, row0);
+      tc::tma_store_commit();
       {
         const uint32_t id = tc::umma_idesc_f16(128, 64, 0, 0);
 #pragma unroll
@@ -641,6 +679,8 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
       // (6) dx = dqkv Win
       tc::mbar_wait(&bar_e[5], 0);
       tc::tc_fence_after();
+      for (int c = 0; c < 3; ++c) tc::tma_store_2d(&p.tm_dqkv_o, sm + BO_R4 + c * TB, c * 64, row0);
+      tc::tma_store_commit();
       {
         const uint32_t id = tc::umma_idesc_f16(128, 64, 0, 0);
 #pragma unroll
@@ -650,6 +690,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
                        k ? 1u : 0u);
         tc::umma_commit(&bar_m[5]);
       }
+      tc::tma_store_wait_all();
     }
   } else {
     const int quad = warp & 3;
@@ -681,7 +722,6 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
         uint4 w = pack8(d + 8 * q);
         if (!live) w = make_uint4(0, 0, 0, 0);
         st_sw(sm + BO_R1, r, q, w);
-        if (live) *reinterpret_cast<uint4*>(p.dz2 + (long long)grow * 64 + 8 * q) = w;
       }
     }
     tc::fence_proxy_async();
@@ -692,16 +732,14 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
     tc::mbar_wait(&bar_m[0], 0);
     stamp(1, 3, tl);
     tc::tc_fence_after();
-    for (int c0 = 0; c0 < 256; c0 += 32) {
-      uint32_t v[32];
-      tc::tmem_ld_32x32(ta + C_DF1 + c0, v);
-      uint4 m[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) m[q] = *reinterpret_cast<const uint4*>(p.f1 + gr * 256 + c0 + 8 * q);
-      tc::tmem_ld_wait();
+    tc::mbar_wait(&bar_f1, 0);              // the forward activation f1 sits in the tiles df1 replaces
+    tmem_walk<256>(ta + C_DF1, [&](int c0, const uint32_t (&v)[32]) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const uint32_t mw[4] = {m[q].x, m[q].y, m[q].z, m[q].w};
+        const int col = c0 + 8 * q;
+        uint8_t* tile = sm + BO_R2 + (col >> 6) * TB;
+        const uint4 m = ld_sw(tile, r, (col & 63) >> 3);
+        const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
         float f[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -709,12 +747,9 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
           f[2 * j] = (live && a.x > 0.f) ? __uint_as_float(v[8 * q + 2 * j]) : 0.f;
           f[2 * j + 1] = (live && a.y > 0.f) ? __uint_as_float(v[8 * q + 2 * j + 1]) : 0.f;
         }
-        const uint4 w = pack8(f);
-        const int col = c0 + 8 * q;
-        st_sw(sm + BO_R2 + (col >> 6) * TB, r, (col & 63) >> 3, w);
-        if (live) *reinterpret_cast<uint4*>(p.df1 + (long long)grow * 256 + col) = w;
+        st_sw(tile, r, (col & 63) >> 3, pack8(f));
       }
-    }
+    });
     tc::tc_fence_before();
     tc::fence_proxy_async();
     tc::mbar_arrive(&bar_e[1]);
@@ -756,7 +791,6 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
         uint4 w = pack8(d + 8 * q);
         if (!live) w = make_uint4(0, 0, 0, 0);
         st_sw(sm + BO_R3, r, q, w);
-        if (live) *reinterpret_cast<uint4*>(p.dz1 + (long long)grow * 64 + 8 * q) = w;
       }
     }
     tc::tc_fence_before();
@@ -790,31 +824,40 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
     tc::tc_fence_after();
     {
       const float* prow = p.p + gr * p.T;
+      const int wlo = ((quad * 32) / p.T) * p.T;
+      const int whi = ((quad * 32 + 31) / p.T + 1) * p.T;
+      const int cb = wlo & ~31, ce = min(128, (whi + 31) & ~31);     // chunks holding this warp's samples
       float dot = 0.f;
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = cb; c0 < ce; c0 += 32) {
         uint32_t v[32];
         tc::tmem_ld_32x32(ta + C_DP + c0, v);
         tc::tmem_ld_wait();
-        if (live) {
+        if (live && c0 + 32 > lo && c0 < hi) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (c0 + j >= lo && c0 + j < hi) dot = fmaf(__uint_as_float(v[j]), prow[c0 + j - lo], dot);
         }
       }
       for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t v[32];
-        tc::tmem_ld_32x32(ta + C_DP + c0, v);
-        tc::tmem_ld_wait();
+        const bool own = (c0 + 32 > lo) && (c0 < hi);
         float ds[32], pp[32];
+        if (c0 >= cb && c0 < ce) {            // warp-uniform
+          uint32_t v[32];
+          tc::tmem_ld_32x32(ta + C_DP + c0, v);
+          tc::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const bool in = live && (c0 + j >= lo) && (c0 + j < hi);
-          const float pv = in ? prow[c0 + j - lo] : 0.f;
-          pp[j] = pv;
-          ds[j] = in ? pv * (__uint_as_float(v[j]) - dot) * p.scale : 0.f;
+          for (int j = 0; j < 32; ++j) {
+            const bool in = live && own && (c0 + j >= lo) && (c0 + j < hi);
+            const float pv = in ? prow[c0 + j - lo] : 0.f;
+            pp[j] = pv;
+            ds[j] = in ? pv * (__uint_as_float(v[j]) - dot) * p.scale : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { pp[j] = 0.f; ds[j] = 0.f; }
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 4; ++q) {         // every chunk is written: the tiles held df1 before
           const int col = c0 + 8 * q;
           st_sw(sm + BO_R2 + (col >> 6) * TB, r, (col & 63) >> 3, pack8(ds + 8 * q));
           st_sw(sm + BO_R2 + (2 + (col >> 6)) * TB, r, (col & 63) >> 3, pack8(pp + 8 * q));
@@ -830,21 +873,16 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
     tc::mbar_wait(&bar_m[4], 0);
     stamp(1, 11, tl);
     tc::tc_fence_after();
-    for (int c0 = 0; c0 < 192; c0 += 32) {
-      uint32_t v[32];
-      tc::tmem_ld_32x32(ta + C_DQKV + c0, v);
-      tc::tmem_ld_wait();
+    tmem_walk<192>(ta + C_DQKV, [&](int c0, const uint32_t (&v)[32]) {
       float f[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = live ? __uint_as_float(v[j]) : 0.f;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const uint4 w = pack8(f + 8 * q);
         const int col = c0 + 8 * q;
-        st_sw(sm + BO_R4 + (col >> 6) * TB, r, (col & 63) >> 3, w);
-        if (live) *reinterpret_cast<uint4*>(p.dqkv + (long long)grow * 192 + col) = w;
+        st_sw(sm + BO_R4 + (col >> 6) * TB, r, (col & 63) >> 3, pack8(f + 8 * q));
       }
-    }
+    });
     tc::tc_fence_before();
     tc::fence_proxy_async();
     tc::mbar_arrive(&bar_e[5]);
@@ -909,6 +947,10 @@ extern "C" int v4l_tc_block_fwd(v4l_ctx* ctx, void* stream, const v4l_tc_block_a
   if (int r = enc2(&p.tm_wo, a->w_o, 64, 64, 64, who)) return r;
   if (int r = enc2(&p.tm_w1, a->w_1, 64, 256, 256, who)) return r;
   if (int r = enc2(&p.tm_w2, a->w_2, 256, 64, 64, who)) return r;
+  if (int r = enc2(&p.tm_qkv_o, a->qkv, 192, p.R, p.rows_per_tile, who)) return r;
+  if (int r = enc2(&p.tm_o_o, a->o, 64, p.R, p.rows_per_tile, who)) return r;
+  if (int r = enc2(&p.tm_h_o, a->h, 64, p.R, p.rows_per_tile, who)) return r;
+  if (int r = enc2(&p.tm_f1_o, a->f1, 256, p.R, p.rows_per_tile, who)) return r;
   p.b_in = a->b_in; p.b_o = a->b_o; p.g1 = a->g1; p.be1 = a->be1; p.b1 = a->b1; p.b2 = a->b2; p.g2 = a->g2; p.be2 = a->be2;
   p.qkv = (__half*)a->qkv; p.o = (__half*)a->o; p.h = (__half*)a->h; p.f1 = (__half*)a->f1; p.y = (__half*)a->y;
   p.p = a->p; p.z1 = a->z1; p.st1 = a->st1; p.z2 = a->z2; p.st2 = a->st2;
@@ -940,6 +982,11 @@ extern "C" int v4l_tc_block_bwd(v4l_ctx* ctx, void* stream, const v4l_tc_block_b
   if (int r = enc2(&p.tm_w1d, a->w1d, 256, 64, 64, who)) return r;
   if (int r = enc2(&p.tm_wod, a->wod, 64, 64, 64, who)) return r;
   if (int r = enc2(&p.tm_wind, a->wind, 192, 64, 64, who)) return r;
+  if (int r = enc2(&p.tm_f1, a->f1, 256, p.R, p.rows_per_tile, who)) return r;
+  if (int r = enc2(&p.tm_dz2_o, a->dz2, 64, p.R, p.rows_per_tile, who)) return r;
+  if (int r = enc2(&p.tm_df1_o, a->df1, 256, p.R, p.rows_per_tile, who)) return r;
+  if (int r = enc2(&p.tm_dz1_o, a->dz1, 64, p.R, p.rows_per_tile, who)) return r;
+  if (int r = enc2(&p.tm_dqkv_o, a->dqkv, 192, p.R, p.rows_per_tile, who)) return r;
   p.g1 = a->g1; p.g2 = a->g2; p.st1 = a->st1; p.st2 = a->st2; p.p = a->p;
   p.dy = (const __half*)a->dy; p.xh1 = (const __half*)a->xh1; p.xh2 = (const __half*)a->xh2; p.f1 = (const __half*)a->f1;
   p.dz2 = (__half*)a->dz2; p.df1 = (__half*)a->df1; p.dh = (__half*)a->dh; p.dz1 = (__half*)a->dz1;
