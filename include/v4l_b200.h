@@ -312,6 +312,10 @@ int v4l_relu_bwd_f16(v4l_ctx* ctx, void* stream, const void* dy, const v4l_rowma
  *      reference on_policy.py:83-89 / ppo.py:136-140.  Sizes in bytes.                       */
 int v4l_h2d_2d(void* stream, void* dst, size_t dpitch, const void* h_src, size_t spitch,
                size_t width, size_t height);
+/* Streamed ingest, copy-engine leg: rows[i] (host int32, any order) of a pinned host matrix with
+ * row_bytes-byte rows -> the same rows of a device matrix; one batched copy per call.            */
+int v4l_h2d_rows(void* stream, void* dst_base, const void* src_base, const int32_t* rows, int n_rows,
+                 size_t row_bytes);
 
 #ifdef __cplusplus
 }

@@ -138,6 +138,7 @@ SIGNATURES = {
                         _i, _i],
   "v4l_pack_f16": [_vp, _vp, _vp, _vp, _vp, _i64],
   "v4l_h2d_2d": [_vp, _vp, _sz, _vp, _sz, _sz, _sz],
+  "v4l_h2d_rows": [_vp, _vp, _vp, _vp, _i, _sz],
 }
 _RESTYPE = {"v4l_last_error": C.c_char_p}
 

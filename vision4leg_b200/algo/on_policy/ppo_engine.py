@@ -237,12 +237,8 @@ class PPOUpdateEngine:
         stage = r.get("stage")
         if stage is None:
           stage = r["stage"] = torch.empty((r["N"], D), device=self.device, dtype=torch.float32)
-        blk = E * D * 4
-        base_h, base_d = obs.data_ptr(), stage.data_ptr()
-        for t in trows:
-          off = int(t) * blk
-          self.ops.h2d_raw(base_d + off, base_h + off, blk)
-        self.ops.ingest_rows(base_d, D, self.S, self._flat_idx[k * rows * E:], len(trows) * E,
+        self.ops.h2d_rows(stage.data_ptr(), obs.data_ptr(), np.ascontiguousarray(trows, dtype=np.int32), E * D * 4)
+        self.ops.ingest_rows(stage.data_ptr(), D, self.S, self._flat_idx[k * rows * E:], len(trows) * E,
                              r["state"] if self.S else None,
                              r["img"] if self.precision != "f16" else None,
                              r.get("imgs") if self.precision == "f16" else None)

@@ -3,6 +3,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <vector>
+#include <string.h>
+
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -73,5 +77,47 @@ extern "C" int v4l_h2d_2d(void* stream, void* dst, size_t dpitch, const void* h_
                           size_t width, size_t height) {
   V4L_CHECK_CUDA(cudaMemcpy2DAsync(dst, dpitch, h_src, spitch, width, height,
                                    cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+// Rows t of a pinned host matrix -> the same rows of a device matrix (row_bytes each), one call per
+// minibatch: sorted, adjacent rows merged, then ONE cudaMemcpyBatchAsync (copy engine; no per-row
+// driver call).  Falls back to a loop of cudaMemcpyAsync if the driver rejects the batch call.
+extern "C" int v4l_h2d_rows(void* stream, void* dst_base, const void* src_base, const int32_t* rows,
+                            int n_rows, size_t row_bytes) {
+  if (n_rows <= 0) return 0;
+  if (!dst_base || !src_base || !rows) { v4l_set_error("v4l_h2d_rows: NULL argument"); return -1; }
+  static thread_local std::vector<int32_t> order;
+  static thread_local std::vector<void*> dsts, srcs;
+  static thread_local std::vector<size_t> sizes;
+  order.assign(rows, rows + n_rows);
+  std::sort(order.begin(), order.end());
+  dsts.clear(); srcs.clear(); sizes.clear();
+  for (int i = 0; i < n_rows;) {
+    int j = i + 1;
+    while (j < n_rows && order[j] == order[j - 1] + 1) ++j;
+    const size_t off = (size_t)order[i] * row_bytes;
+    dsts.push_back((char*)dst_base + off);
+    srcs.push_back((char*)const_cast<void*>(src_base) + off);
+    sizes.push_back((size_t)(j - i) * row_bytes);
+    i = j;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  static int batch_ok = -1;                 // -1 untested, 0 unsupported, 1 works
+  if (batch_ok != 0) {
+    cudaMemcpyAttributes attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+    attr.flags = cudaMemcpyFlagPreferOverlapWithCompute;
+    size_t attr_idx = 0, fail = 0;
+    cudaError_t e = cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(), dsts.size(), &attr, &attr_idx, 1,
+                                         &fail, s);
+    if (e == cudaSuccess) { batch_ok = 1; return 0; }
+    if (batch_ok == 1) { v4l_set_error("cudaMemcpyBatchAsync -> %s", cudaGetErrorString(e)); return -2; }
+    (void)cudaGetLastError();
+    batch_ok = 0;
+  }
+  for (size_t i = 0; i < dsts.size(); ++i)
+    V4L_CHECK_CUDA(cudaMemcpyAsync(dsts[i], srcs[i], sizes[i], cudaMemcpyHostToDevice, s));
   return 0;
 }

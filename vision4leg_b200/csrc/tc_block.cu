@@ -67,6 +67,11 @@ __device__ __forceinline__ void st_sw(uint8_t* tile, int row, int chunk, uint4 v
 __device__ __forceinline__ uint4 ld_sw(const uint8_t* tile, int row, int chunk) {
   return *reinterpret_cast<const uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4));
 }
+__device__ __forceinline__ float ex2_approx(float x) {     // one MUFU.EX2 (results below 2^-126 flush to 0)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pk2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -94,6 +99,38 @@ __device__ __forceinline__ void tmem_walk(uint32_t taddr, F&& fn) {
     tc::tmem_ld_wait();
     if (c0 + 64 < NCOLS) tc::tmem_ld_32x32(taddr + c0 + 64, va);
     fn(c0 + 32, vb);
+  }
+}
+
+// Attention-score chunks: of the 128 accumulator columns at taddr, read the 32-column chunks
+// [cb, ce) that hold this warp's samples (TMEM loads are warp-wide; next load in flight while the
+// current chunk is looked at) and keep, per thread, the chunk holding the first (ownA) and the last
+// (ownB, may equal ownA) key column of its own sample.
+__device__ __forceinline__ void tmem_own_chunks(uint32_t taddr, int cb, int ce, int ownA, int ownB,
+                                                uint32_t (&ka)[32], uint32_t (&kb)[32]) {
+  uint32_t va[32], vb[32];
+  tc::tmem_ld_32x32(taddr + cb, va);
+#pragma unroll
+  for (int i = 0; i < 4; i += 2) {
+    const int c0 = cb + 32 * i;
+    if (c0 < ce) {
+      tc::tmem_ld_wait();
+      if (c0 + 32 < ce) tc::tmem_ld_32x32(taddr + c0 + 32, vb);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (c0 == ownA) ka[j] = va[j];
+        if (c0 == ownB) kb[j] = va[j];
+      }
+      if (c0 + 32 < ce) {
+        tc::tmem_ld_wait();
+        if (c0 + 64 < ce) tc::tmem_ld_32x32(taddr + c0 + 64, va);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (c0 + 32 == ownA) ka[j] = vb[j];
+          if (c0 + 32 == ownB) kb[j] = vb[j];
+        }
+      }
+    }
   }
 }
 
@@ -265,38 +302,49 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
     tc::mbar_wait(&bar_m[1], 0);
     stamp(0, 5, tl);
     tc::tc_fence_after();
-    // only the 32-column chunks that hold this warp's samples are read (TMEM loads are warp-wide);
-    // each thread then touches the 1-2 chunks of its own sample; the rest of P stays zero (prologue)
+    // one pass: the thread's own score chunk(s) are kept in registers; the rest of P stays zero (prologue)
     const int wlo = ((quad * 32) / p.T) * p.T;
     const int whi = ((quad * 32 + 31) / p.T + 1) * p.T;
     const int cb = wlo & ~31, ce = min(128, (whi + 31) & ~31);
-    float mx = -3.0e38f;
-    for (int c0 = cb; c0 < ce; c0 += 32) {
-      uint32_t v[32];
-      tc::tmem_ld_32x32(ta + C_S + c0, v);
-      tc::tmem_ld_wait();
-      if (c0 + 32 > lo && c0 < hi) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j >= lo && c0 + j < hi) mx = fmaxf(mx, __uint_as_float(v[j]));
-      }
-    }
+    const int ownA = min(lo, 127) & ~31, ownB = min(hi - 1, 127) & ~31;
     float sum = 0.f;
-    for (int c0 = cb; c0 < ce; c0 += 32) {
-      uint32_t v[32];
-      tc::tmem_ld_32x32(ta + C_S + c0, v);
-      tc::tmem_ld_wait();
-      if (c0 + 32 > lo && c0 < hi) {
-        float e[32];
+    {
+      uint32_t ka[32], kb[32];
+      tmem_own_chunks(ta + C_S, cb, ce, ownA, ownB, ka, kb);
+      const bool two = ownB != ownA;
+      float mx = -3.0e38f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (ownA + j >= lo && ownA + j < hi) mx = fmaxf(mx, __uint_as_float(ka[j]));
+        if (two && ownB + j < hi) mx = fmaxf(mx, __uint_as_float(kb[j]));
+      }
+      const float sc2 = p.scale * 1.4426950408889634f;      // exp(x * scale) = 2^(x * scale * log2 e)
+      float e[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        // exp unconditionally on a clamped argument, then select: a per-element branch around the
+        // MUFU costs far more than the exp itself
+        const bool in = live && (ownA + j >= lo) && (ownA + j < hi);
+        const float t = ex2_approx(fminf((__uint_as_float(ka[j]) - mx) * sc2, 0.f));
+        e[j] = in ? t : 0.f;
+        sum += e[j];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int col = ownA + 8 * q;
+        st_sw(sm + OFF_P + (col >> 6) * TB, r, (col & 63) >> 3, pack8(e + 8 * q));
+      }
+      if (two) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const bool in = live && (c0 + j >= lo) && (c0 + j < hi);
-          e[j] = in ? __expf((__uint_as_float(v[j]) - mx) * p.scale) : 0.f;
+          const bool in = live && (ownB + j < hi);
+          const float t = ex2_approx(fminf((__uint_as_float(kb[j]) - mx) * sc2, 0.f));
+          e[j] = in ? t : 0.f;
           sum += e[j];
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int col = c0 + 8 * q;
+          const int col = ownB + 8 * q;
           st_sw(sm + OFF_P + (col >> 6) * TB, r, (col & 63) >> 3, pack8(e + 8 * q));
         }
       }
@@ -756,6 +804,9 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
     stamp(1, 4, tl);
 
     // ---- (c) dh = df1 W1 + dz2 -> global (LN1 affine gradients); LayerNorm1 backward -> dz1 (R3 + global)
+    uint4 xh1r[8];
+    ld_row64(p.xh1 + gr * 64, xh1r);        // fetched ahead of the MMA wait
+    const float rstd1 = p.st1[gr * 2 + 1];
     tc::mbar_wait(&bar_m[1], 0);
     stamp(1, 5, tl);
     tc::tc_fence_after();
@@ -778,14 +829,11 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
           }
         }
       }
-      uint4 xh[8];
-      ld_row64(p.xh1 + gr * 64, xh);
-      const float rstd = p.st1[gr * 2 + 1];
       if (live) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(p.dh + (long long)grow * 64 + 8 * q) = pack8(d + 8 * q);
       }
-      ln_bwd_row(d, xh, rstd, sg1);
+      ln_bwd_row(d, xh1r, rstd1, sg1);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         uint4 w = pack8(d + 8 * q);
@@ -819,45 +867,47 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
     stamp(1, 8, tl);
 
     // ---- (e) dS = P (dP - rowsum(dP P)) scale and P -> tiles R2 (dS: 0,1; P: 2,3)
+    // the saved probabilities of this query row, aligned to its own 32-column chunk(s), are fetched
+    // before waiting for dP so that their latency hides behind the MMA
+    const int ownA = min(lo, 127) & ~31, ownB = min(hi - 1, 127) & ~31;
+    const bool two = ownB != ownA;
+    float pa[32], pb[32];
+    {
+      const float* prow = p.p + gr * p.T;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int ia = ownA + j - lo, ib = ownB + j - lo;
+        pa[j] = (live && ia >= 0 && ia < p.T) ? prow[ia] : 0.f;
+        pb[j] = (live && two && ib < p.T) ? prow[ib] : 0.f;
+      }
+    }
     tc::mbar_wait(&bar_m[3], 0);
     stamp(1, 9, tl);
     tc::tc_fence_after();
     {
-      const float* prow = p.p + gr * p.T;
       const int wlo = ((quad * 32) / p.T) * p.T;
       const int whi = ((quad * 32 + 31) / p.T + 1) * p.T;
       const int cb = wlo & ~31, ce = min(128, (whi + 31) & ~31);     // chunks holding this warp's samples
+      uint32_t ka[32], kb[32];
+      tmem_own_chunks(ta + C_DP, cb, ce, ownA, ownB, ka, kb);
       float dot = 0.f;
-      for (int c0 = cb; c0 < ce; c0 += 32) {
-        uint32_t v[32];
-        tc::tmem_ld_32x32(ta + C_DP + c0, v);
-        tc::tmem_ld_wait();
-        if (live && c0 + 32 > lo && c0 < hi) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j >= lo && c0 + j < hi) dot = fmaf(__uint_as_float(v[j]), prow[c0 + j - lo], dot);
-        }
+      for (int j = 0; j < 32; ++j) {
+        dot = fmaf(__uint_as_float(ka[j]), pa[j], dot);
+        if (two) dot = fmaf(__uint_as_float(kb[j]), pb[j], dot);
       }
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        const bool own = (c0 + 32 > lo) && (c0 < hi);
+#pragma unroll
+      for (int c0 = 0; c0 < 128; c0 += 32) {   // every chunk is written: the tiles held df1 before
         float ds[32], pp[32];
-        if (c0 >= cb && c0 < ce) {            // warp-uniform
-          uint32_t v[32];
-          tc::tmem_ld_32x32(ta + C_DP + c0, v);
-          tc::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const bool in = live && own && (c0 + j >= lo) && (c0 + j < hi);
-            const float pv = in ? prow[c0 + j - lo] : 0.f;
-            pp[j] = pv;
-            ds[j] = in ? pv * (__uint_as_float(v[j]) - dot) * p.scale : 0.f;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { pp[j] = 0.f; ds[j] = 0.f; }
+        for (int j = 0; j < 32; ++j) {
+          const float pv = (c0 == ownA) ? pa[j] : ((c0 == ownB) ? pb[j] : 0.f);
+          const float dp = (c0 == ownA) ? __uint_as_float(ka[j]) : __uint_as_float(kb[j]);
+          pp[j] = pv;
+          ds[j] = pv * (dp - dot) * p.scale;     // pv == 0 off the sample's block
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {         // every chunk is written: the tiles held df1 before
+        for (int q = 0; q < 4; ++q) {
           const int col = c0 + 8 * q;
           st_sw(sm + BO_R2 + (col >> 6) * TB, r, (col & 63) >> 3, pack8(ds + 8 * q));
           st_sw(sm + BO_R2 + (2 + (col >> 6)) * TB, r, (col & 63) >> 3, pack8(pp + 8 * q));

@@ -22,7 +22,7 @@
 namespace {
 
 constexpr int TC_THREADS = 192;
-constexpr int TC_STAGES = 4;
+constexpr int TC_MAX_STAGES = 8;                 // TMA ring depth: as many stages as fit in ~196 KB
 constexpr int A_TILE_BYTES = 128 * 128;          // 128 rows x 64 f16
 constexpr int ACC_COLS = 256;                    // TMEM columns per accumulator stage
 constexpr int MAX_TAPS = 16;
@@ -44,6 +44,7 @@ struct TcGemmParams {
   int flags;
   const int32_t* a_idx;
   const __half* res;              // optional residual added to the result (same addressing as c)
+  int stages;                     // TMA ring depth
 };
 
 __device__ __forceinline__ float h16_lo(uint32_t u) { return __half2float(__ushort_as_half(static_cast<unsigned short>(u & 0xffffu))); }
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem base is only guaranteed 16-B aligned: round up to 1024 (SWIZZLE_128B atoms)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], tmem_full[2], tmem_empty[2];
+  __shared__ uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_bias[256];
 
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&p.tmap_a);
     tc::tma_prefetch_desc(&p.tmap_b);
-    for (int s = 0; s < TC_STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { tc::mbar_init(&tmem_full[s], 1); tc::mbar_init(&tmem_empty[s], 128); }
     tc::fence_barrier_init();
   }
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
           tc::mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
           tc::tma_load_4d(sa, &p.tmap_a, &full_bar[stage], kc * 64, p.tap_dw[tap], h0 + p.tap_dh[tap], ab0);
           tc::tma_load_2d(sb, &p.tmap_b, &full_bar[stage], it * 64, n0);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
             tc::umma_f16(d_tmem, adesc, bdesc, idesc, (it | k) ? 1u : 0u);
           }
           tc::umma_commit(&empty_bar[stage]);                // frees the smem stage when MMAs retire
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         tc::umma_commit(&tmem_full[acc]);                    // accumulator ready for the epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -343,7 +344,11 @@ extern "C" int v4l_tc_gemm(v4l_ctx* ctx, void* stream, const v4l_tc_gemm_args* a
   p.res = reinterpret_cast<const __half*>(a->res);
   V4L_REQUIRE(!a->a_idx || a->bb == 1, "v4l_tc_gemm: a_idx needs single-item boxes (bb == 1)");
 
-  const size_t smem = (size_t)TC_STAGES * (A_TILE_BYTES + (size_t)Nchunk * 128) + 1024;
+  // ring depth: the loads are latency-bound (one 16-48 KB stage per ~1 us of L2/HBM latency), so the
+  // bytes in flight per SM set the feed rate of the narrow-N convolution layers
+  const size_t stage_bytes = A_TILE_BYTES + (size_t)Nchunk * 128;
+  p.stages = (int)max((size_t)2, min((size_t)TC_MAX_STAGES, (size_t)(196 * 1024) / stage_bytes));
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     V4L_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -357,6 +357,10 @@ class Ops:
     """contiguous pinned-host -> device copy on the current stream (copy engine)"""
     check(self.lib.v4l_h2d_2d(self.ctx.stream(), dst_ptr, nbytes, src_ptr, nbytes, nbytes, 1))
 
+  def h2d_rows(self, dst_ptr, src_ptr, rows, row_bytes):
+    """rows: contiguous int32 numpy array of row numbers; copies those rows pinned-host -> device"""
+    check(self.lib.v4l_h2d_rows(self.ctx.stream(), dst_ptr, src_ptr, rows.ctypes.data, len(rows), row_bytes))
+
   def h2d_2d(self, dst, dpitch, src_ptr, spitch, width, height):
     check(self.lib.v4l_h2d_2d(self.ctx.stream(), ptr(dst), dpitch, src_ptr, spitch, width, height))
 
