@@ -10,10 +10,10 @@
 //     shifts).  Plain matrices are the degenerate case W = H = 1, B = M.
 //   * W is a packed f16 weight matrix [N, taps*kchunks*64] (K-major), one TMA box {64, N}.
 //   * both land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes.
-// Warp roles (192 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 =
-// TMEM allocator + single-thread MMA issuer, warps 2-5 = epilogue (TMEM -> registers -> bias /
-// ReLU / ReLU-mask / accumulate -> global).  4-stage smem ring, 2 TMEM accumulator stages so
-// the epilogue of tile i overlaps the MMAs of tile i+1.
+// Warp roles (320 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 =
+// TMEM allocator + single-thread MMA issuer, warps 2-5 and 6-9 = two epilogue warpgroups, one per
+// TMEM accumulator stage (TMEM -> registers -> bias / ReLU / ReLU-mask / accumulate -> global).
+// 4-8-stage smem ring; the epilogue of tile i overlaps the MMAs and the epilogue of tile i+1.
 #include <string.h>
 
 #include "common.cuh"
@@ -21,7 +21,7 @@
 
 namespace {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;                   // TMA warp, MMA warp, 2 x 4 epilogue warps
 constexpr int TC_MAX_STAGES = 8;                 // TMA ring depth: as many stages as fit in ~196 KB
 constexpr int A_TILE_BYTES = 128 * 128;          // 128 rows x 64 f16
 constexpr int ACC_COLS = 256;                    // TMEM columns per accumulator stage
@@ -96,11 +96,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     // ============================== TMA producer ==============================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      // minibatch row gather (bb == 1 only): the index of the NEXT tile's image is fetched while this
+      // tile's loads are issued, so the dependent global load never stalls the single producer thread
+      int idx_next = (p.a_idx && blockIdx.x < p.num_tiles) ? p.a_idx[blockIdx.x / p.h_tiles] : 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int b0, h0;
         if (p.bb == 1) { b0 = tile / p.h_tiles; h0 = (tile - b0 * p.h_tiles) * p.bh; }
         else           { b0 = tile * p.bb; h0 = 0; }
-        const int ab0 = p.a_idx ? p.a_idx[b0] : b0;          // minibatch row gather (bb == 1 only)
+        const int ab0 = p.a_idx ? idx_next : b0;
+        if (p.a_idx && tile + gridDim.x < p.num_tiles) idx_next = p.a_idx[(tile + gridDim.x) / p.h_tiles];
         for (int it = 0; it < k_iters; ++it) {
           const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -143,23 +147,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     }
   } else {
     // ============================== epilogue ==================================
+    // two epilogue warpgroups (warps 2-5, 6-9), one per TMEM accumulator stage: tiles alternate
+    // between them, so unloading tile i overlaps both the MMAs and the unloading of tile i+1
+    const int wg = (warp - 2) >> 2;
     const int quad = warp & 3;                               // TMEM lane quadrant of this warp
     const int r = quad * 32 + lane;                          // row inside the tile
     const bool relu = p.flags & V4L_RELU, accum = p.flags & V4L_ACCUM;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const int acc = wg;
+    uint32_t acc_phase = 0;
+    // row r of the box = (w fastest, then h, then b)
+    const int ww = r % p.bw;
+    const int t2 = r / p.bw;
+    const int hh = t2 % p.bh;
+    const int bi = t2 / p.bh;
+    // output address of this thread's row in a tile (table look-ups inside): computed one tile
+    // ahead so that its global-load latency hides behind the current tile
+    auto row_of = [&](int tile, bool& ok) -> long long {
       int b0, h0;
       if (p.bb == 1) { b0 = tile / p.h_tiles; h0 = (tile - b0 * p.h_tiles) * p.bh; }
       else           { b0 = tile * p.bb; h0 = 0; }
-      // row r of the box = (w fastest, then h, then b)
-      const int ww = r % p.bw;
-      const int t2 = r / p.bw;
-      const int hh = t2 % p.bh;
-      const int bi = t2 / p.bh;
       const int b = b0 + bi, h = h0 + hh;
-      const bool row_ok = (r < box_rows) && (b < p.B) && (h < p.Hout);
-      long long row_addr = 0;
-      if (row_ok) row_addr = v4l_row_addr(p.c_map, (b * p.Hout + h) * p.Wout + ww) + n0;
+      ok = (r < box_rows) && (b < p.B) && (h < p.Hout);
+      return ok ? v4l_row_addr(p.c_map, (b * p.Hout + h) * p.Wout + ww) + n0 : 0;
+    };
+    const int tile_step = 2 * gridDim.x;
+    int tile = blockIdx.x + wg * gridDim.x;
+    bool ok_next = false;
+    long long addr_next = tile < p.num_tiles ? row_of(tile, ok_next) : 0;
+    for (; tile < p.num_tiles; tile += tile_step) {
+      const bool row_ok = ok_next;
+      const long long row_addr = addr_next;
+      if (tile + tile_step < p.num_tiles) addr_next = row_of(tile + tile_step, ok_next);
 
       tc::mbar_wait(&tmem_full[acc], acc_phase);
       tc::tc_fence_after();
@@ -246,7 +264,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       }
       tc::tc_fence_before();
       tc::mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      acc_phase ^= 1;
     }
   }
   __syncthreads();
@@ -476,11 +494,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
         a_tap[j] = tap; a_c0[j] = c0;
       }
       int stage = 0; uint32_t phase = 0;
+      // gather index of the next tile's image fetched one tile ahead (see tc_gemm_kernel)
+      int idx_next = (p.x_idx && tile_lo < tile_hi) ? p.x_idx[p.bb == 1 ? tile_lo / p.h_tiles : tile_lo * p.bb] : 0;
       for (int tile = tile_lo; tile < tile_hi; ++tile) {
         int b0, h0;
         if (p.bb == 1) { b0 = tile / p.h_tiles; h0 = (tile - b0 * p.h_tiles) * p.bh; }
         else           { b0 = tile * p.bb; h0 = 0; }
-        const int xb0 = p.x_idx ? p.x_idx[b0] : b0;
+        const int xb0 = p.x_idx ? idx_next : b0;
+        if (p.x_idx && tile + 1 < tile_hi) idx_next = p.x_idx[p.bb == 1 ? (tile + 1) / p.h_tiles : (tile + 1) * p.bb];
         for (int sub = 0; sub < p.n_sub; ++sub) {
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* s = smem + stage * stage_bytes;
