@@ -376,6 +376,10 @@ def dominant_kernel_roofline(args, eng, pk):
   from vision4leg_b200 import engine as E
   ops, B = eng.ops, args.batch
   if eng.precision == "f16":
+    if args.model == "loco":
+      roof = tc_block_roofline(args, eng, pk)
+      roof["second_kernel"] = tc_conv1_roofline(args, eng, pk)
+      return roof
     return tc_conv1_roofline(args, eng, pk)
   plan = eng.plan_pf
   trunk = plan.trunk
@@ -404,6 +408,64 @@ def dominant_kernel_roofline(args, eng, pk):
           "traffic": None, "us_per_launch": sec * 1e6, "peak_src": pk["src"],
           "algorithmic_flops_per_launch": flops,
           "hbm_bytes_per_launch_algorithmic": B * 65536 + B * 225 * 32 * 4}
+
+
+def tc_block_roofline(args, eng, pk):
+  """Tensor-core tier, LocoTransformer: the fused encoder-layer forward kernel (tc_block_fwd_kernel:
+  six chained tcgen05 contractions per 7-sample tile) is the largest single-kernel share of the step
+  (6 launches per minibatch, profiles/r1_f16_launches_summary.md).  Timed alone with CUDA events.
+  Algorithmic work per sample (17 tokens, d=64, FFN 256): 4 projections 2*17*64*(192+64+256+256) FLOP +
+  attention 2*2*17*17*64 FLOP = 1.745 MFLOP; algorithmic HBM bytes per sample = x in + y out + everything
+  the backward needs (qkv, o, h, f1, the two normalised rows: fp16; P and the two (mean, rstd): fp32)
+  = 17*(64+64+192+64+64+256+64+64)*2 + 17*17*4 + 17*16 = 31 076 B  =>  56 FLOP/B, left of the 251 FLOP/B
+  ridge: the kernel is bounded by the HBM roof (the stores for the backward), not the tensor roof."""
+  ops, B = eng.ops, args.batch
+  plan = eng.plan_pf
+  flat = eng.pf_flat
+  T, d = plan.T, plan.d
+  R = B * T
+  p = "visual_append_layers.0."
+  x = plan.buf("tok0", (B, T, d))
+  w = {"w_in": plan.W.fwd[p + "self_attn.in_proj_weight"].w, "w_o": plan.W.fwd[p + "self_attn.out_proj.weight"].w,
+       "w_1": plan.W.fwd[p + "linear1.weight"].w, "w_2": plan.W.fwd[p + "linear2.weight"].w}
+  par = {"b_in": plan._view(flat, p + "self_attn.in_proj_bias"), "b_o": plan._view(flat, p + "self_attn.out_proj.bias"),
+         "g1": plan._view(flat, p + "norm1.weight"), "be1": plan._view(flat, p + "norm1.bias"),
+         "b1": plan._view(flat, p + "linear1.bias"), "b2": plan._view(flat, p + "linear2.bias"),
+         "g2": plan._view(flat, p + "norm2.weight"), "be2": plan._view(flat, p + "norm2.bias")}
+  h16 = lambda *s: torch.empty(s, device=ops.device, dtype=torch.float16)
+  f32 = lambda *s: torch.empty(s, device=ops.device)
+  out = dict(qkv=h16(R, 192), o=h16(R, d), h=h16(R, d), f1=h16(R, 256), y=h16(R, d), p=f32(B, 1, T, T),
+             st1=f32(R, 2), st2=f32(R, 2), xh1=h16(R, d), xh2=h16(R, d))
+  run = lambda: ops.tc_block_fwd(x, B, T, w, par, out)
+  for _ in range(3):
+    run()
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  reps = 20
+  e0.record()
+  for _ in range(reps):
+    run()
+  e1.record()
+  torch.cuda.synchronize()
+  sec = e0.elapsed_time(e1) / 1e3 / reps
+  flops = B * (2.0 * T * d * (192 + 64 + 256 + 256) + 4.0 * T * T * d)
+  by = B * (T * (64 + 64 + 192 + 64 + 64 + 256 + 64 + 64) * 2 + T * T * 4 + T * 16)
+  gbs = by / sec / 1e9
+  return {"kernel": "tc_block_fwd_kernel (one TransformerEncoderLayer forward: QKV, block-diagonal attention, "
+                    "out-proj, LN, FFN, LN as six chained tcgen05.mma contractions; TMA loads/stores)",
+          "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+          # dram__bytes_read.sum + dram__bytes_write.sum of one launch at minibatch 1024 from the
+          # `ncu --set full` capture (profiles/r1_tc_block_ncu.txt)
+          "traffic": TC_BLOCK_FWD_DRAM_BYTES_B1024 if B == 1024 else None,
+          "us_per_launch": sec * 1e6, "peak_src": pk["src"],
+          "algorithmic_bytes_per_launch": by, "algorithmic_flops_per_launch": flops,
+          "tensor_tflops_achieved": flops / sec / 1e12, "tensor_frac": flops / sec / 1e12 / pk["bf16_tflops"],
+          "note": "minibatch 1024 = 147 tiles = ONE wave of 148 SMs: the launch time is the latency of one tile's "
+                  "six-deep MMA->epilogue chain (profiles/r1_tc_block_timeline.txt), so the fraction grows with "
+                  "the minibatch (tools/bench_block.py: 2.0 TB/s at 65536)"}
+
+
+TC_BLOCK_FWD_DRAM_BYTES_B1024 = 2430720 + 17152     # dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_tc_block_ncu.txt
 
 
 def tc_conv1_roofline(args, eng, pk):
@@ -444,7 +506,11 @@ def tc_conv1_roofline(args, eng, pk):
           "us_per_launch": sec * 1e6, "peak_src": pk["src"],
           "algorithmic_flops_per_launch": flops, "hbm_bytes_per_launch_algorithmic": by,
           "hbm_gbs_achieved": by / sec / 1e9, "hbm_frac": by / sec / 1e9 / pk["hbm_gbs"],
-          "note": "N=32, K=256: 128 FLOP/B -> this layer is HBM/L2-feed bound, not tensor bound"}
+          "note": "N=32: every tcgen05.mma (K=16) still streams its 128x16 A operand from shared memory "
+                  "(~128 cycles), so a 128-row tile costs 16 x 128 cycles whatever N is: 12.5 % of the tensor "
+                  "roof is this shape's ceiling with A in shared memory (measured: ring depth, epilogue "
+                  "warpgroups, accumulator stages, a single-load descriptor-shifted variant (tc_conv.cu) and a "
+                  "table-driven issue loop all leave 25 us unchanged)"}
 
 
 if __name__ == "__main__":

@@ -136,6 +136,23 @@ int v4l_tc_attn_fwd(v4l_ctx* ctx, void* stream, const void* qkv, void* o, float*
 int v4l_tc_attn_bwd(v4l_ctx* ctx, void* stream, const void* qkv, const float* p, const void* d_o,
                     void* d_qkv, int B, int T);
 
+/* "Flat" valid convolution (NatureCNN trunk forward, reference torchrl/networks/base.py:304-342):
+ * x fp16 [x_rows, C] = images flattened to rows img * P + h * Wg + w (C a multiple of 64); each
+ * 128-row tile is loaded once and tap (dh, dw) is the same shared-memory tile read through a UMMA
+ * descriptor shifted by dh * Wg + dw rows (vision4leg_b200/csrc/tc_conv.cu).  Output rows with
+ * h < Hout, w < Wout are stored through c_map at row index (img * Hout + h) * Wout + w; w = packed
+ * fp16 [N_pad, n_taps * C] (tap-major K).  x_idx (optional, P % 128 == 0): image i of the problem is
+ * image x_idx[i] of x.  mode: 1 = one copy of the tile, shifted descriptor starts (default);
+ * 0 = one pre-shifted copy per (shift mod 8), atom-aligned starts.                               */
+typedef struct v4l_tc_conv_flat_args {
+  const void* x; int64_t x_rows; int32_t C, P, Wg, Hout, Wout;
+  int32_t n_taps; int32_t tap_dw[16], tap_dh[16];
+  const void* w; int32_t N_pad, N_valid; const float* bias;
+  void* c; v4l_rowmap c_map;
+  int64_t n_img; const int32_t* x_idx; int32_t flags, mode;
+} v4l_tc_conv_flat_args;
+int v4l_tc_conv_flat(v4l_ctx* ctx, void* stream, const v4l_tc_conv_flat_args* args);
+
 /* Fused forward of one post-norm TransformerEncoderLayer (d=64, 1 head, FFN 256, ReLU, dropout 0;
  * reference torchrl/networks/nets.py:949-955 -> torch nn.TransformerEncoderLayer) as ONE kernel:
  * QKV GEMM -> block-diagonal attention -> out-proj -> +x, LayerNorm1 -> FFN1+ReLU -> FFN2 -> +h,

@@ -442,3 +442,45 @@ def test_tc_block_bwd_matches_torch_autograd(B, T):
   # LayerNorm affine gradients = diag(xhat^T dy), colsum(dy)
   assert rel((out["xh2"].float() * dy.float()).sum(0), g2.grad) < tol
   assert rel((out["xh1"].float() * g["dh"].float()).sum(0), g1.grad) < tol
+
+
+@pytest.mark.parametrize("layer,mode", [("conv1", 0), ("conv1", 1), ("conv2", 1), ("conv3", 1)])
+def test_tc_conv_flat_is_bit_identical_to_tap_boxes(layer, mode):
+  """Single-load trunk convolution (taps = UMMA descriptors shifted by dh*Wg+dw rows of one shared-
+  memory tile, csrc/tc_conv.cu) vs the tap-box tc_gemm path, which the tier tests pin to the oracle:
+  same fp16 products in the same order, so the outputs must match bit for bit."""
+  engine, ops = _ops()
+  from vision4leg_b200.engine import RM, RELU
+  torch.manual_seed(7)
+  B = 37
+  taps2 = [(dx, dy) for dy in range(2) for dx in range(2)]
+  taps3 = [(kw, kh) for kh in range(3) for kw in range(3)]
+  if layer == "conv1":
+    Nimg = 3 * B
+    x = (torch.randn(Nimg, 16, 16, 64, device=DEV) * 0.5).half()
+    idx = torch.randperm(Nimg, device=DEV)[:B].int().contiguous()
+    oh, ow = np.meshgrid(np.arange(15), np.arange(15), indexing="ij")
+    pos = torch.tensor((((oh // 2) * 8 + ow // 2) * 128 + ((oh % 2) * 2 + ow % 2) * 32).ravel().astype(np.int32), device=DEV)
+    cfg = dict(xs=(Nimg, 16, 16, 64), og=(B, 15, 15), box=(15, 8, 1), taps=taps2, kch=1, N=32, oshape=(B, 8, 8, 128),
+               cmap=lambda: RM(225, 8 * 8 * 128, 0, 0, pos_off=pos), flat=(64, 256, 16, 15, 15))
+  elif layer == "conv2":
+    x = (torch.randn(B, 8, 8, 128, device=DEV) * 0.5).half(); idx = None
+    cfg = dict(xs=(B, 8, 8, 128), og=(B, 6, 6), box=(6, 6, 3), taps=taps2, kch=2, N=64, oshape=(B, 6, 6, 64),
+               cmap=lambda: RM(36, 36 * 64, 64, 0), flat=(128, 64, 8, 6, 6))
+  else:
+    x = (torch.randn(B, 6, 6, 64, device=DEV) * 0.5).half(); idx = None
+    cfg = dict(xs=(B, 6, 6, 64), og=(B, 4, 4), box=(4, 4, 8), taps=taps3, kch=1, N=64, oshape=(B, 16, 64),
+               cmap=lambda: RM(16, 16 * 64, 64, 0), flat=(64, 36, 6, 4, 4))
+  K = len(cfg["taps"]) * cfg["kch"] * 64
+  w = (torch.randn(cfg["N"], K, device=DEV) * 0.05).half()
+  bias = torch.randn(cfg["N"], device=DEV) * 0.1
+  ref = torch.zeros(cfg["oshape"], device=DEV, dtype=torch.float16)
+  out = torch.zeros(cfg["oshape"], device=DEV, dtype=torch.float16)
+  ops.tc_gemm(x, cfg["xs"], cfg["og"], cfg["box"], cfg["taps"], cfg["kch"], w, cfg["N"], cfg["N"], bias, ref, cfg["cmap"](),
+              flags=RELU, a_idx=idx)
+  C_, P, Wg, Ho, Wo = cfg["flat"]
+  ops.tc_conv_flat(x, C_, P, Wg, Ho, Wo, cfg["taps"], w, cfg["N"], cfg["N"], bias, out, cfg["cmap"](), B, x_idx=idx,
+                   flags=RELU, mode=mode)
+  torch.cuda.synchronize()
+  assert float(ref.float().abs().max()) > 0.1
+  assert torch.equal(out, ref)

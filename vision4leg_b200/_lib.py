@@ -76,6 +76,14 @@ class TcWgradArgs(C.Structure):
               ("dbias", C.c_void_p), ("defer", C.c_int32)]
 
 
+class TcConvFlatArgs(C.Structure):
+  _fields_ = [("x", C.c_void_p), ("x_rows", C.c_int64), ("C", C.c_int32), ("P", C.c_int32), ("Wg", C.c_int32),
+              ("Hout", C.c_int32), ("Wout", C.c_int32), ("n_taps", C.c_int32), ("tap_dw", C.c_int32 * 16),
+              ("tap_dh", C.c_int32 * 16), ("w", C.c_void_p), ("N_pad", C.c_int32), ("N_valid", C.c_int32),
+              ("bias", C.c_void_p), ("c", C.c_void_p), ("c_map", RowMap), ("n_img", C.c_int64),
+              ("x_idx", C.c_void_p), ("flags", C.c_int32), ("mode", C.c_int32)]
+
+
 class TcBlockArgs(C.Structure):
   _fields_ = [("x", C.c_void_p), ("B", C.c_int32), ("T", C.c_int32), ("eps", C.c_float)] + \
     [(n, C.c_void_p) for n in ("w_in", "w_o", "w_1", "w_2", "b_in", "b_o", "g1", "be1", "b1", "b2", "g2", "be2",
@@ -115,6 +123,7 @@ SIGNATURES = {
   "v4l_pool_fwd_f16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
   "v4l_pool_bwd_f16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
   "v4l_tc_attn_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i],
+  "v4l_tc_conv_flat": [_vp, _vp, C.POINTER(TcConvFlatArgs)],
   "v4l_tc_block_fwd": [_vp, _vp, C.POINTER(TcBlockArgs)],
   "v4l_tc_block_bwd": [_vp, _vp, C.POINTER(TcBlockBwdArgs)],
   "v4l_tc_block_timeline": [C.POINTER(C.c_uint64)],

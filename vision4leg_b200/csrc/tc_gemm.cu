@@ -10,8 +10,8 @@
 //     shifts).  Plain matrices are the degenerate case W = H = 1, B = M.
 //   * W is a packed f16 weight matrix [N, taps*kchunks*64] (K-major), one TMA box {64, N}.
 //   * both land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes.
-// Warp roles (320 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 =
-// TMEM allocator + single-thread MMA issuer, warps 2-5 and 6-9 = two epilogue warpgroups, one per
+// Warp roles (576 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 =
+// TMEM allocator + single-thread MMA issuer, then 2 (N > 128) or 4 epilogue warpgroups, one per
 // TMEM accumulator stage (TMEM -> registers -> bias / ReLU / ReLU-mask / accumulate -> global).
 // 4-8-stage smem ring; the epilogue of tile i overlaps the MMAs and the epilogue of tile i+1.
 #include <string.h>
@@ -21,7 +21,8 @@
 
 namespace {
 
-constexpr int TC_THREADS = 320;                   // TMA warp, MMA warp, 2 x 4 epilogue warps
+constexpr int TC_THREADS = 64 + 4 * 128;          // TMA warp, MMA warp, up to 4 epilogue warpgroups
+constexpr int TC_MAX_ACC = 4;
 constexpr int TC_MAX_STAGES = 8;                 // TMA ring depth: as many stages as fit in ~196 KB
 constexpr int A_TILE_BYTES = 128 * 128;          // 128 rows x 64 f16
 constexpr int ACC_COLS = 256;                    // TMEM columns per accumulator stage
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem base is only guaranteed 16-B aligned: round up to 1024 (SWIZZLE_128B atoms)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], tmem_full[2], tmem_empty[2];
+  __shared__ uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], tmem_full[TC_MAX_ACC], tmem_empty[TC_MAX_ACC];
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_bias[256];
 
@@ -72,12 +73,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   const int box_rows = p.bw * p.bh * p.bb;
   const uint32_t a_bytes = static_cast<uint32_t>(box_rows) * 128u;
   const int k_iters = p.n_taps * p.kchunks;
+  // accumulator stages in TMEM = epilogue warpgroups (narrow layers: the MMA -> epilogue -> MMA
+  // hand-over, not the MMAs, bounds a tile, so several tiles must be in flight)
+  const int n_acc = p.N <= 128 ? 4 : 2;
+  const int acc_cols = 512 / n_acc;
 
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&p.tmap_a);
     tc::tma_prefetch_desc(&p.tmap_b);
     for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(&tmem_full[s], 1); tc::mbar_init(&tmem_empty[s], 128); }
+    for (int s = 0; s < TC_MAX_ACC; ++s) { tc::mbar_init(&tmem_full[s], 1); tc::mbar_init(&tmem_empty[s], 128); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(&tmem_base_slot, 512);
@@ -126,7 +131,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+        const uint32_t d_tmem = tmem_base + acc * acc_cols;
         for (int it = 0; it < k_iters; ++it) {
           tc::mbar_wait(&full_bar[stage], phase);
           tc::tc_fence_after();
@@ -142,13 +147,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         tc::umma_commit(&tmem_full[acc]);                    // accumulator ready for the epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else {
+  } else if (((warp - 2) >> 2) < n_acc) {
     // ============================== epilogue ==================================
-    // two epilogue warpgroups (warps 2-5, 6-9), one per TMEM accumulator stage: tiles alternate
-    // between them, so unloading tile i overlaps both the MMAs and the unloading of tile i+1
+    // one epilogue warpgroup per TMEM accumulator stage, tiles round-robin: unloading tile i
+    // overlaps the MMAs and the unloading of the following tiles
     const int wg = (warp - 2) >> 2;
     const int quad = warp & 3;                               // TMEM lane quadrant of this warp
     const int r = quad * 32 + lane;                          // row inside the tile
@@ -170,7 +175,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       ok = (r < box_rows) && (b < p.B) && (h < p.Hout);
       return ok ? v4l_row_addr(p.c_map, (b * p.Hout + h) * p.Wout + ww) + n0 : 0;
     };
-    const int tile_step = 2 * gridDim.x;
+    const int tile_step = n_acc * gridDim.x;
     int tile = blockIdx.x + wg * gridDim.x;
     bool ok_next = false;
     long long addr_next = tile < p.num_tiles ? row_of(tile, ok_next) : 0;
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 
       tc::mbar_wait(&tmem_full[acc], acc_phase);
       tc::tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * ACC_COLS;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * acc_cols;
       for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t v[32];
         if (N - c0 >= 32) {

@@ -157,6 +157,20 @@ class Ops:
     check(self.lib.v4l_tc_gemm(self.h, self.ctx.stream(), C.byref(g)))
     self.launches += 1
 
+  def tc_conv_flat(self, x, C_, P, Wg, Hout, Wout, taps, w, N_pad, N_valid, bias, c, c_map, n_img, x_idx=None,
+                   flags=0, mode=0):
+    """valid convolution on the flattened (image, position) grid; x fp16 [rows, C_]; taps [(dw, dh)]"""
+    g = _lib.TcConvFlatArgs()
+    g.x, g.x_rows, g.C = ptr(x), x.numel() // C_, C_
+    g.P, g.Wg, g.Hout, g.Wout = P, Wg, Hout, Wout
+    g.n_taps = len(taps)
+    for i, (dw_, dh_) in enumerate(taps):
+      g.tap_dw[i], g.tap_dh[i] = dw_, dh_
+    g.w, g.N_pad, g.N_valid, g.bias = ptr(w), N_pad, N_valid, ptr(bias)
+    g.c, g.c_map, g.n_img, g.x_idx, g.flags, g.mode = ptr(c), c_map.c(), n_img, ptr(x_idx), flags, mode
+    check(self.lib.v4l_tc_conv_flat(self.h, self.ctx.stream(), C.byref(g)))
+    self.launches += 1
+
   def tc_wgrad(self, x, x_shape, dy, dy_C, out_grid, box, taps, N_valid, index, dw, x_idx=None,
                x_estride=1, subs=None, dy_strides=None, dy_off=0, x_strides=None, out_scale=1.0,
                dbias=None, defer=False):
