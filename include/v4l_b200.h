@@ -308,6 +308,11 @@ int v4l_pack_f16(v4l_ctx* ctx, void* stream, const float* src, const int32_t* in
  * (channel = (py*4+px)*4+c): the layout the tensor-core conv1 reads (one swizzle atom per tap) */
 int v4l_ingest_img(v4l_ctx* ctx, void* stream, const float* img, void* out_s2d, int64_t n_img,
                    const int32_t* idx /* optional list of the n_img image rows to convert */);
+/* Same re-ordering from an fp16 [n, 4, 64, 64] source: the replay buffer's half-precision staging copy
+ * of the depth stack (vision4leg_b200/replay_buffers/on_policy.py), which halves the host->device
+ * bytes of the streamed ingest.  idx: optional row list.                                         */
+int v4l_ingest_img_f16(v4l_ctx* ctx, void* stream, const void* img_f16, void* out_s2d, int64_t n_img,
+                       const int32_t* idx);
 /* Zero-copy rollout ingest: row n (= idx[i] or i) of the [*, row_stride] fp32 observation matrix in
  * PINNED HOST (or device) memory -> state_out[n, 0:S] fp32, img_out[n, 0:16384] fp32 (optional),
  * s2d_out[n] fp16 [16,16,64] (optional), one CTA per row, PCIe reads issued by the SMs.

@@ -484,3 +484,40 @@ def test_tc_conv_flat_is_bit_identical_to_tap_boxes(layer, mode):
   torch.cuda.synchronize()
   assert float(ref.float().abs().max()) > 0.1
   assert torch.equal(out, ref)
+
+
+def test_half_image_staging_is_bit_identical():
+  """Streaming the replay buffer's pinned fp16 copy of the depth stack (half the host->device bytes)
+  must give exactly the parameters and statistics of streaming the fp32 rows: the device rounds the
+  images to fp16 with the same round-to-nearest the buffer's numpy cast uses.  The second epoch
+  exercises rows written by add_sample AFTER the staging was enabled."""
+  from oracle import synth
+  from tests import _golden as g
+  from tests._harness import build_nets, load_np_sd, make_ppo, fill_buffer
+  outs = []
+  for half in (False, True):
+    S, A = g.FAMILIES["loco"]
+    pf, vf = build_nets("loco", S, A)
+    pf_np, vf_np = g.family_weights("loco")
+    load_np_sd(pf, pf_np); load_np_sd(vf, vf_np)
+    pf, vf = pf.to(DEV), vf.to(DEV)
+    roll = synth.make_rollout(5, 16, 4, S, A, p_term=0.1)
+    buf = fill_buffer(roll, 16, 4)
+    agent, logger = make_ppo(pf, vf, buf, A, 16, 64, 2, device=DEV)
+    agent.precision = "f16"
+    agent.half_image_staging = half
+    agent.current_epoch = 3
+    np.random.seed(9)
+    agent.update_per_epoch()
+    assert (agent.engine.h2d_bytes < 16 * 4 * (S + 16384) * 4) == half
+    roll2 = synth.make_rollout(6, 16, 4, S, A, p_term=0.1)
+    for t in range(16):                       # next rollout through the public add_sample
+      nxt = roll2["obs"][t + 1] if t + 1 < 16 else roll2["last_obs"]
+      buf.add_sample({"obs": roll2["obs"][t], "next_obs": nxt, "acts": roll2["acts"][t], "values": roll2["values"][t],
+                      "rewards": roll2["rewards"][t], "terminals": roll2["terminals"][t],
+                      "time_limits": roll2["time_limits"][t]})
+    agent.current_epoch = 4
+    agent.update_per_epoch()
+    outs.append((agent.engine.bucket.flat.clone(), [tuple(i.values()) for i in logger.infos]))
+  assert torch.equal(outs[0][0], outs[1][0])
+  assert outs[0][1] == outs[1][1]

@@ -67,3 +67,26 @@ def test_replay_buffer_bookkeeping():
   np.testing.assert_array_equal(batches[0]["acts"], roll["acts"][perm[:2]].reshape(6, A))
   with pytest.raises(AssertionError):
     next(buf.one_iteration(4, ["obs"], False))
+
+
+def test_replay_buffer_half_image_staging_tracks_add_sample():
+  """enable_half_image_staging: rows already stored are converted once, later add_sample calls keep
+  the fp16 image copy and the packed proprio copy in step with the fp32 rows (ring overwrite too)."""
+  import numpy as np
+  from vision4leg_b200.replay_buffers import OnPolicyReplayBuffer
+  rng = np.random.default_rng(0)
+  T, E, S, I = 5, 2, 3, 8
+  buf = OnPolicyReplayBuffer(env_nums=E, max_replay_buffer_size=T * E)
+  def sample():
+    return {"obs": rng.standard_normal((E, S + I)).astype(np.float32), "next_obs": rng.standard_normal((E, S + I)),
+            "acts": rng.standard_normal((E, 2)), "rewards": rng.standard_normal((E, 1))}
+  for _ in range(3):
+    buf.add_sample(sample())
+  buf.enable_half_image_staging(S)
+  for _ in range(4):                    # wraps around the ring
+    buf.add_sample(sample())
+  n = buf.num_steps_can_sample()
+  assert n == T
+  np.testing.assert_array_equal(buf._obs_img16[:n], buf._obs[:n, :, S:].astype(np.float16))
+  np.testing.assert_array_equal(buf._obs_state[:n, :, :S], buf._obs[:n, :, :S])
+  assert buf._obs_img16.dtype == np.float16

@@ -59,9 +59,7 @@ for name, x, xs, og, box, taps, kch, w, Np, Nv, bias, oshape, cmap, xi, fl in ca
   f_ref = lambda: ops.tc_gemm(x, xs, og, box, taps, kch, w, Np, Nv, bias, ref, cmap(), flags=RELU, a_idx=xi)
   f_ref(); t_ref = timeit(f_ref)
   line = "%s B=%d  tap-box %.1f us |" % (name, B, t_ref)
-  for mode in (0, 1):
-    if mode == 0 and name != "conv1":
-      continue
+  for mode in (1 + 16, 1 + 32, 1 + 64):
     out = torch.zeros(oshape, device=DEV, dtype=torch.float16)
     f = lambda: ops.tc_conv_flat(x, fl["C_"], fl["P"], fl["Wg"], fl["Hout"], fl["Wout"], taps, w, Np, Nv, bias, out, cmap(),
                                  B, x_idx=xi, flags=RELU, mode=mode)
@@ -69,7 +67,7 @@ for name, x, xs, og, box, taps, kch, w, Np, Nv, bias, oshape, cmap, xi, fl in ca
       f(); torch.cuda.synchronize()
       e = rel(out, ref)
       t = timeit(f)
-      line += "  mode %d: err %.2e %.1f us" % (mode, e, t)
+      line += "  group %d: err %.2e %.1f us" % (mode >> 4, e, t)
     except Exception as ex:
       line += "  mode %d: FAILED %s" % (mode, str(ex)[:60])
   print(line)

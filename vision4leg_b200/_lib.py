@@ -141,6 +141,7 @@ SIGNATURES = {
   "v4l_tc_wgrad_flush": [_vp, _vp],
   "v4l_colsum_f16": [_vp, _vp, _vp, C.POINTER(RowMap), _i, _i, _i, _f, _vp],
   "v4l_ingest_img": [_vp, _vp, _vp, _vp, _i64, _vp],
+  "v4l_ingest_img_f16": [_vp, _vp, _vp, _vp, _i64, _vp],
   "v4l_ingest_rows": [_vp, _vp, _vp, _i64, _i, _vp, _i64, _vp, _vp, _vp],
   "v4l_gather_rows_f16": [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i64, _i, _f],
   "v4l_relu_bwd_f16": [_vp, _vp, _vp, C.POINTER(RowMap), _vp, C.POINTER(RowMap), _vp, C.POINTER(RowMap),

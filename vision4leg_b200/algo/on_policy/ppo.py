@@ -29,6 +29,7 @@ class PPO(A2C):
     self.process_group = None       # set to a torch.distributed group for data-parallel updates
     self.use_cuda_graph = True
     self.precision = "fp32"         # "fp32": exact CUDA-core tier; "fp16": tcgen05 tensor-core tier
+    self.half_image_staging = True  # f16 tier: stream the buffer's fp16 copy of the depth stack (same values)
     self._engine = None
 
   @property
@@ -54,6 +55,10 @@ class PPO(A2C):
 
   def update_per_epoch(self):
     eng, buf = self.engine, self.replay_buffer
+    if self.precision == "f16" and self.half_image_staging and eng.has_img and hasattr(buf, "enable_half_image_staging"):
+      # the tensor-core tier consumes the depth stack in fp16: let the buffer keep a pinned fp16 copy
+      # (maintained by add_sample; rows already stored are converted once, here) and stream that
+      buf.enable_half_image_staging(eng.S)
     eng.load_rollout(buf, stream_obs=True)
     sample = buf.last_sample(["next_obs", "terminals"])
     eng.compute_advantages(sample["next_obs"], sample["terminals"], self.discount, self.tau,

@@ -195,13 +195,20 @@ class PPOUpdateEngine:
     if D != expect:
       raise V4LError("rollout observation width %d, expected %d" % (D, expect))
     self._pending_obs = None
+    self._pending_half = None
     if stream_obs:
       self._pending_obs = (obs, D)
+      if self.precision == "f16" and self.has_img and host.get("obs_img16") is not None \
+          and getattr(buf, "_half_S", None) == self.S:
+        # stream the buffer's fp16 staging copy of the depth stack (+ packed proprio rows) instead
+        self._pending_half = (host["obs_img16"], host["obs_state"])
     else:
       self._copy_obs_rows(obs, D, 0, T * E)
       if self.precision == "f16" and self.has_img:
         self.ops.ingest_img(r["img"], r["imgs"], T * E)     # fp32 CHW -> fp16 space-to-depth NHWC
     self.h2d_bytes = T * E * D * 4
+    if self._pending_half is not None:
+      self.h2d_bytes = T * E * (engine.IMG_ELEMS * 2 + self.S * 4)
     for key in ("acts", "values", "rewards", "terminals"):
       src = host[key].reshape(T * E, -1)
       r[key].view(T * E, -1).copy_(src, non_blocking=True)
@@ -230,7 +237,19 @@ class PPOUpdateEngine:
     # free-running copy stream: it was ordered after the main stream ONCE (run_epoch); waiting for
     # the main stream here would serialise copy k+1 behind minibatch k
     with self.ops.fork(2, wait=False):
-      if self.has_img:
+      half = getattr(self, "_pending_half_cur", None)
+      if half is not None:
+        img16, st32 = half
+        stage = r.get("stage16")
+        if stage is None:
+          stage = r["stage16"] = torch.empty((r["N"], engine.IMG_ELEMS), device=self.device, dtype=torch.float16)
+        tr = np.ascontiguousarray(trows, dtype=np.int32)
+        self.ops.h2d_rows(stage.data_ptr(), img16.data_ptr(), tr, E * engine.IMG_ELEMS * 2)
+        if self.S:        # proprio rows go straight into their fp32 plane (same layout on both sides)
+          assert st32.shape[-1] == self.S
+          self.ops.h2d_rows(r["state"].data_ptr(), st32.data_ptr(), tr, E * self.S * 4)
+        self.ops.ingest_img_f16(stage.data_ptr(), r["imgs"], len(trows) * E, self._flat_idx[k * rows * E:])
+      elif self.has_img:
         # copy engine: one contiguous 8-row block (E x D floats) per time row into a device staging
         # matrix with the host layout; then ONE kernel splits/convert this minibatch's rows into the
         # device layouts (fp32 image plane only for the exact tier).  No SM is tied up waiting on PCIe.
@@ -449,6 +468,7 @@ class PPOUpdateEngine:
       self._flat_idx = self._flat_idx_static
       self._slot.zero_()
       pending, self._pending_obs = getattr(self, "_pending_obs", None), None
+      self._pending_half_cur, self._pending_half = getattr(self, "_pending_half", None), None
       cur = torch.cuda.current_stream(dev)
       if pending is not None:
         with self.ops.fork(2):          # order the copy stream after the index upload / previous epoch
@@ -463,6 +483,9 @@ class PPOUpdateEngine:
       if getattr(self, "_pending_obs", None) is not None:
         obs, D = self._pending_obs
         self._pending_obs = None
+        if self._pending_half is not None:    # ragged epochs copy the fp32 rows up front
+          self.h2d_bytes += T * E * D * 4 - T * E * (engine.IMG_ELEMS * 2 + self.S * 4)
+          self._pending_half = None
         self._copy_obs_rows(obs, D, 0, T * E)
         if self.precision == "f16" and self.has_img:
           self.ops.ingest_img(r["img"], r["imgs"], T * E)

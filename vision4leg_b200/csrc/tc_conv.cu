@@ -47,7 +47,68 @@ struct ConvFlatParams {
   __half* c;
   v4l_rowmap c_map;
   int stages;
+  int group;                   // tiles whose MMAs are issued interleaved (independent accumulators)
 };
+
+// Consecutive tcgen05.mma into the SAME accumulator form a dependent chain (~85 ns each whatever N
+// is: measured), so narrow layers are bound by that latency, not by the MMA's width.  The MMAs of G
+// tiles (independent accumulators, G <= accumulator stages) are therefore issued interleaved; everything
+// is kept in registers (static indices) because this single thread's instruction stream is the next limit.
+struct IssueCtx {
+  uint64_t *full_bar, *empty_bar, *tmem_full, *tmem_empty;
+  const uint32_t* aoff;
+  const uint64_t* bdesc;
+  uint32_t ring_addr, stage_bytes, tmem_base;
+  int acc_cols, n_acc, n_mma;
+  uint32_t idesc;
+  int stages, num_tiles;
+};
+
+template <int G>
+__device__ __forceinline__ void issue_mmas(const IssueCtx& c) {
+  int stage = 0; uint32_t phase = 0;
+  int acc = 0; uint32_t acc_phase = 0;
+  const int step = static_cast<int>(gridDim.x);
+  for (int tile = blockIdx.x; tile < c.num_tiles; tile += G * step) {
+    bool v[G];
+    uint32_t d[G];
+    uint64_t ab[G];
+    uint64_t *eb[G], *tf[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      v[g] = tile + g * step < c.num_tiles;
+      d[g] = 0; ab[g] = 0; eb[g] = nullptr; tf[g] = nullptr;
+      if (v[g]) {
+        tc::mbar_wait(&c.tmem_empty[acc], acc_phase ^ 1);
+        tc::mbar_wait(&c.full_bar[stage], phase);
+        d[g] = c.tmem_base + acc * c.acc_cols;
+        ab[g] = tc::umma_smem_desc(c.ring_addr + stage * c.stage_bytes, 0, 1024);
+        eb[g] = &c.empty_bar[stage]; tf[g] = &c.tmem_full[acc];
+        if (++stage == c.stages) { stage = 0; phase ^= 1; }
+        if (++acc == c.n_acc) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    tc::tc_fence_after();
+    {
+      const uint32_t ao = c.aoff[0];
+      const uint64_t bd = c.bdesc[0];
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        if (v[g]) tc::umma_f16(d[g], ab[g] + ao, bd, c.idesc, 0u);
+    }
+#pragma unroll 2
+    for (int i = 1; i < c.n_mma; ++i) {
+      const uint32_t ao = c.aoff[i];
+      const uint64_t bd = c.bdesc[i];
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        if (v[g]) tc::umma_f16(d[g], ab[g] + ao, bd, c.idesc, 1u);
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+      if (v[g]) { tc::umma_commit(eb[g]); tc::umma_commit(tf[g]); }
+  }
+}
 
 __global__ void __launch_bounds__(CV_THREADS, 1) tc_conv_flat_kernel(const __grid_constant__ ConvFlatParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -138,22 +199,11 @@ __global__ void __launch_bounds__(CV_THREADS, 1) tc_conv_flat_kernel(const __gri
     if (lane == 0) {
       const uint32_t idesc = tc::umma_idesc_f16(128, N, 0, 0);
       tc::mbar_wait(&w_bar, 0);
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tc::mbar_wait(&full_bar[stage], phase);
-        tc::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * acc_cols;
-        const uint64_t abase = tc::umma_smem_desc(tc::smem_u32(ring + stage * stage_bytes), 0, 1024);
-        tc::umma_f16(d_tmem, abase + s_aoff[0], s_bdesc[0], idesc, 0u);
-#pragma unroll 4
-        for (int i = 1; i < n_mma; ++i) tc::umma_f16(d_tmem, abase + s_aoff[i], s_bdesc[i], idesc, 1u);
-        tc::umma_commit(&empty_bar[stage]);
-        tc::umma_commit(&tmem_full[acc]);
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
-        if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
-      }
+      IssueCtx c{full_bar, empty_bar, tmem_full, tmem_empty, s_aoff, s_bdesc, tc::smem_u32(ring), stage_bytes, tmem_base,
+                 acc_cols, n_acc, n_mma, idesc, p.stages, p.num_tiles};
+      if (p.group >= 4) issue_mmas<4>(c);
+      else if (p.group == 2) issue_mmas<2>(c);
+      else issue_mmas<1>(c);
     }
   } else if (((warp - 2) >> 2) < n_acc) {
     // ============================== epilogue ==================================
@@ -230,7 +280,7 @@ extern "C" int v4l_tc_conv_flat(v4l_ctx* ctx, void* stream, const v4l_tc_conv_fl
   V4L_REQUIRE(a->n_taps >= 1 && a->n_taps <= CV_MAX_TAPS, "v4l_tc_conv_flat: bad taps");
   V4L_REQUIRE(a->N_pad % 32 == 0 && a->N_pad >= 32 && a->N_pad <= 256 && a->N_valid >= 1 && a->N_valid <= a->N_pad &&
               a->N_valid % 8 == 0, "v4l_tc_conv_flat: N_pad=%d N_valid=%d", a->N_pad, a->N_valid);
-  V4L_REQUIRE(a->mode == 0 || a->mode == 1, "v4l_tc_conv_flat: bad mode");
+  V4L_REQUIRE((a->mode & 15) <= 1 && (a->mode >> 4) <= 4, "v4l_tc_conv_flat: bad mode");
   V4L_REQUIRE(a->P >= 1 && a->Wg >= 1 && a->Hout >= 1 && a->Wout <= a->Wg && a->Hout * a->Wg <= a->P + a->Wg,
               "v4l_tc_conv_flat: bad grid");
   V4L_REQUIRE(!a->x_idx || a->P % 128 == 0, "v4l_tc_conv_flat: gathered images need P %% 128 == 0");
@@ -247,8 +297,9 @@ extern "C" int v4l_tc_conv_flat(v4l_ctx* ctx, void* stream, const v4l_tc_conv_fl
     max_shift = max(max_shift, p.shift[t]);
     seen[p.shift[t] & 7] = true;
   }
-  p.mode = a->mode;
-  if (a->mode == 0) {
+  p.mode = a->mode & 15;
+  p.group = (a->mode >> 4) ? (a->mode >> 4) : 2;      // bits 4-7: interleave group (default 2)
+  if (p.mode == 0) {
     for (int q = 0; q < 8; ++q) if (seen[q]) p.copy_res[p.n_copies++] = q;
   } else {
     p.n_copies = 1; p.copy_res[0] = 0;
@@ -278,6 +329,7 @@ extern "C" int v4l_tc_conv_flat(v4l_ctx* ctx, void* stream, const v4l_tc_conv_fl
   const size_t stage_bytes = (size_t)p.n_copies * p.kc * p.load_rows * 128;
   V4L_REQUIRE(w_bytes + 2 * stage_bytes <= 200 * 1024, "v4l_tc_conv_flat: weights + 2 stages exceed shared memory");
   p.stages = (int)min((size_t)CV_MAX_STAGES, (200 * 1024 - w_bytes) / stage_bytes);
+  p.group = min(p.group, min(p.stages, a->N_pad <= 128 ? 4 : 2));
   const size_t smem = w_bytes + (size_t)p.stages * stage_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {

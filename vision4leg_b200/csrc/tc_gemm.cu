@@ -811,6 +811,37 @@ namespace {
 // fp32 CHW [4,64,64] observation image -> f16 4x4 space-to-depth NHWC [16,16,64],
 // channel = (py*4 + px)*4 + c for source pixel (4Y+py, 4X+px): the 8x8/4 conv becomes a 2x2/1
 // conv with 64-channel (128-byte) rows — exactly one TMA/UMMA swizzle atom per tap.
+// fp16 source (the replay buffer's half-precision staging copy of the depth stack): same re-ordering,
+// the fp32 -> fp16 rounding already happened on the host (round-to-nearest, identical values)
+__global__ void ingest_img_f16_kernel(const __half* __restrict__ img, __half* __restrict__ out, long long n_img,
+                                      const int32_t* __restrict__ idx) {
+  v4l_pdl_enter();
+  const long long total = n_img * 16 * 4 * 16;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int X = (int)(t & 15);
+    const int py = (int)((t >> 4) & 3);
+    const int Y = (int)((t >> 6) & 15);
+    const long long n = idx ? (long long)idx[t >> 10] : (t >> 10);
+    const __half* src = img + n * 16384 + (4 * Y + py) * 64 + 4 * X;
+    unsigned short h[4][4];                        // [c][px]
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint2 v = *reinterpret_cast<const uint2*>(src + c * 4096);
+      h[c][0] = v.x & 0xffffu; h[c][1] = v.x >> 16; h[c][2] = v.y & 0xffffu; h[c][3] = v.y >> 16;
+    }
+    uint32_t w[8];
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      w[2 * px] = (uint32_t)h[0][px] | ((uint32_t)h[1][px] << 16);
+      w[2 * px + 1] = (uint32_t)h[2][px] | ((uint32_t)h[3][px] << 16);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + ((n * 16 + Y) * 16 + X) * 64 + py * 16);
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
 __global__ void ingest_img_kernel(const float* __restrict__ img, __half* __restrict__ out, long long n_img,
                                   const int32_t* __restrict__ idx) {
   v4l_pdl_enter();
@@ -884,6 +915,18 @@ extern "C" int v4l_ingest_img(v4l_ctx* ctx, void* stream, const float* img, void
   const long long total = n_img * 1024;
   const int blocks = (int)min((long long)16 * ctx->sm_count, (total + 255) / 256);
   V4L_LAUNCH(ingest_img_kernel, blocks, 256, 0, (cudaStream_t)stream, img, reinterpret_cast<__half*>(out_s2d), n_img, idx);
+  V4L_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int v4l_ingest_img_f16(v4l_ctx* ctx, void* stream, const void* img_f16, void* out_s2d, int64_t n_img,
+                                  const int32_t* idx) {
+  V4L_REQUIRE(ctx && img_f16 && out_s2d && n_img >= 0, "v4l_ingest_img_f16: bad argument");
+  if (n_img == 0) return 0;
+  const long long total = n_img * 1024;
+  const int blocks = (int)min((long long)16 * ctx->sm_count, (total + 255) / 256);
+  V4L_LAUNCH(ingest_img_f16_kernel, blocks, 256, 0, (cudaStream_t)stream, reinterpret_cast<const __half*>(img_f16),
+             reinterpret_cast<__half*>(out_s2d), n_img, idx);
   V4L_CHECK_LAUNCH();
   return 0;
 }

@@ -213,6 +213,10 @@ class Ops:
     check(self.lib.v4l_ingest_img(self.h, self.ctx.stream(), ptr(img_f32), ptr(out_s2d), n, ptr(idx)))
     self.launches += 1
 
+  def ingest_img_f16(self, img_f16_ptr, out_s2d, n, idx=None):
+    check(self.lib.v4l_ingest_img_f16(self.h, self.ctx.stream(), img_f16_ptr, ptr(out_s2d), n, ptr(idx)))
+    self.launches += 1
+
   def ingest_rows(self, obs_ptr, row_stride, S, idx, n_rows, state_out, img_out, s2d_out):
     check(self.lib.v4l_ingest_rows(self.h, self.ctx.stream(), obs_ptr, row_stride, S, ptr(idx), n_rows,
                                    ptr(state_out), ptr(img_out), ptr(s2d_out)))

@@ -24,6 +24,7 @@ class BaseReplayBuffer:
     self._size = 0
     self.time_limit_filter = time_limit_filter
     self._host = {}            # key -> pinned torch tensor backing the numpy view `_key`
+    self._half_S = None        # proprio width once half-precision image staging is enabled
     self.device = None         # set by the algorithm (PPO) or defaults to the current device
 
   # ---- storage --------------------------------------------------------------------------------
@@ -44,7 +45,41 @@ class BaseReplayBuffer:
           self._next_obs[0, ...] = val
       else:
         getattr(self, "_" + key)[self._top, ...] = val
+        if key == "obs" and self._half_S is not None:
+          self._write_half_staging(self._top)
     self._advance()
+
+  # ---- half-precision staging of the depth stack ---------------------------------------------------
+  def enable_half_image_staging(self, state_dim):
+    """Keep, next to the fp32 observation rows, a pinned fp16 copy of their image part and a packed
+    fp32 copy of their proprio part, maintained by add_sample.  The tensor-core tier of the PPO update
+    rounds the depth stack to fp16 anyway (round-to-nearest on the device == numpy's cast here), so
+    streaming this copy instead of the fp32 rows halves the host->device bytes of every update without
+    changing a single value it computes.  Rows already stored are converted once."""
+    S = int(state_dim)
+    if self._half_S == S:
+      return
+    self._half_S = S
+    if "obs" in self._host:
+      self._alloc_half()
+      for t in range(self._size if self._size < self._max_replay_buffer_size else self._max_replay_buffer_size):
+        self._write_half_staging(t)
+
+  def _alloc_half(self):
+    T, E, D = self._obs.shape
+    S = self._half_S
+    pin = lambda t: t.pin_memory() if torch.cuda.is_available() else t
+    self._host["obs_img16"] = pin(torch.zeros((T, E, D - S), dtype=torch.float16))
+    self._host["obs_state"] = pin(torch.zeros((T, E, max(S, 1)), dtype=torch.float32))
+    self._obs_img16, self._obs_state = self._host["obs_img16"].numpy(), self._host["obs_state"].numpy()
+
+  def _write_half_staging(self, t):
+    if "obs_img16" not in self._host:
+      self._alloc_half()
+    S = self._half_S
+    self._obs_img16[t] = self._obs[t, :, S:]
+    if S:
+      self._obs_state[t, :, :S] = self._obs[t, :, :S]
 
   def terminate_episode(self):
     pass
