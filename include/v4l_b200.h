@@ -226,12 +226,15 @@ int v4l_vf_loss(v4l_ctx* ctx, void* stream, const float* values, const float* re
                 float* info, const int32_t* slot);
 /* actor loss: log-prob, ratio, clipped surrogate, entropy bonus and their gradients w.r.t.
  * mean [n,A] and logstd [A]  (ppo.py:42-92).  target_mean/target_logstd come from the frozen
- * target policy; adv is normalised with the (possibly all-reduced) stats of v4l_adv_stats.   */
+ * target policy; adv is normalised with the (possibly all-reduced) stats of v4l_adv_stats.
+ * The target policy is frozen for a whole update_per_epoch (ppo.py:34), so its mean for a rollout row
+ * can be computed once (first opt-epoch) into a [N,A] table and re-read afterwards: target_indexed. */
 int v4l_pf_loss(v4l_ctx* ctx, void* stream, const float* mean, const float* logstd,
                 const float* target_mean, const float* target_logstd, const float* acts,
                 const float* adv, const int32_t* idx, const double* adv_stats,
                 float* d_mean, float* d_logstd, int n, int A, float inv_global, float inv_local,
-                float clip_para, float entropy_coeff, float* info, const int32_t* slot);
+                float clip_para, float entropy_coeff, float* info, const int32_t* slot,
+                int target_indexed /* 0: target_mean is [n,A] (row i); 1: a per-rollout table read at row idx[i] */);
 
 /* ---- clip_grad_norm_(0.5) + Adam(eps=1e-5) over a flat bucket
  *      (reference ppo.py:71-75,116-120; a2c.py:30-40).

@@ -175,6 +175,8 @@ class PPOUpdateEngine:
       r["img"] = f(N, engine.IMG_ELEMS)
       if self.precision == "f16":
         r["imgs"] = torch.empty((N, 16, 16, 64), device=dev, dtype=torch.float16)
+    if self.precision == "f16":
+      r["tmean_all"] = f(N, self.A)        # target-policy action means, filled during the first opt-epoch
     self._roll = r
     self._graphs.clear()            # captured graphs hold the old planes' addresses
     return r
@@ -353,7 +355,7 @@ class PPOUpdateEngine:
       return engine.Input(B, r["state"], self.S, 0, r["img"], engine.IMG_ELEMS, 0, idx)
     return engine.Input(B, r["state"], self.S, 0, idx=idx)
 
-  def _minibatch(self, B):
+  def _minibatch(self, B, with_target=True):
     """The fixed kernel sequence of one PPO.update (reference ppo.py:125-153): critic first,
     then the actor on the encoder the critic just stepped."""
     ops, r, b = self.ops, self._roll, self._bufs(B)
@@ -365,7 +367,7 @@ class PPOUpdateEngine:
     if self.world > 1:
       self._allreduce_stats(b)
     if self.precision == "f16":
-      return self._minibatch_tc(B, b, idx, inv_local, inv_global)
+      return self._minibatch_tc(B, b, idx, inv_local, inv_global, with_target)
     inp = self._input(B, idx)
     # ---- critic
     self.plan_vf.forward(self.P_vf, inp, b["values"])
@@ -389,17 +391,22 @@ class PPOUpdateEngine:
                   self._slot, INFO_GRAD_NORM_PF)
     ops.slot_advance(self._slot, 0)
 
-  def _minibatch_tc(self, B, b, idx, inv_local, inv_global):
+  def _minibatch_tc(self, B, b, idx, inv_local, inv_global, with_target=True):
     """Same sequence on the tensor-core tier: fp16 activations, tcgen05 GEMMs; weights are
     re-packed to fp16 right before each network's forward (the critic step has just changed
     the shared encoder when the actor runs)."""
     ops, r = self.ops, self._roll
     imgs, st = r["imgs"], b["st"]
     ops.gather_rows_f16(r["state"], True, idx, st, B, self.S, self.S, self.plan_pf.Sp)
-    # the frozen target policy only depends on the minibatch rows: its forward runs on the side
-    # stream, concurrently with the whole critic phase (a parallel branch of the captured graph)
-    with ops.fork(1):
-      self.plan_t.forward(self.t_flat, imgs, idx, st, B, b["tmean"])
+    # The frozen target policy (copied once per update_per_epoch, ppo.py:34) only depends on the rollout
+    # row: its action mean is computed when a row is first visited (first opt-epoch), as a parallel
+    # branch of the captured graph next to the critic phase, written straight into a per-rollout
+    # [N, A] table (row map with the minibatch index list) and re-read by later opt-epochs — the values
+    # are bit-identical to recomputing them, 2/3 of the target forwards disappear.
+    if with_target:
+      with ops.fork(1):
+        self.plan_t.forward(self.t_flat, imgs, idx, st, B, r["tmean_all"],
+                            out_map=engine.RM(1, self.A, 0, 0, idx=idx))
     # ---- critic
     self.plan_vf.pack(self.vf_flat)
     self.plan_vf.forward(self.vf_flat, imgs, idx, st, B, b["values"])
@@ -413,10 +420,11 @@ class PPOUpdateEngine:
     # ---- actor
     self.plan_pf.pack(self.pf_flat)
     self.plan_pf.forward(self.pf_flat, imgs, idx, st, B, b["mean"])
-    ops.join(1)
-    ops.pf_loss(b["mean"], self.logstd, b["tmean"], self.t_logstd, r["acts"], r["advs"], idx, b["stats"],
+    if with_target:
+      ops.join(1)
+    ops.pf_loss(b["mean"], self.logstd, r["tmean_all"], self.t_logstd, r["acts"], r["advs"], idx, b["stats"],
                 b["d_mean"], self.G_pf["logstd"], B, self.A, inv_global, inv_local, self.clip_para,
-                self.entropy_coeff, self._info, self._slot)
+                self.entropy_coeff, self._info, self._slot, target_indexed=True)
     self.plan_pf.backward(self.g_pf, b["d_mean"])
     if self.world > 1:
       self._allreduce(self.g_pf)
@@ -478,7 +486,7 @@ class PPOUpdateEngine:
           # interleaved with the launches so the CPU never runs far behind the GPU
           ev = self._stream_chunk(pending[0], pending[1], perms[0][k * rows:(k + 1) * rows], E, k, rows)
           cur.wait_event(ev)               # rows of minibatch k (first opt-epoch) have landed
-        self._launch(B)
+        self._launch(B, with_target=k < n_full)
     else:
       if getattr(self, "_pending_obs", None) is not None:
         obs, D = self._pending_obs
@@ -494,27 +502,32 @@ class PPOUpdateEngine:
     self.d2h_bytes = info.nbytes
     return [dict(zip(INFO_KEYS, (float(x) for x in row))) for row in info]
 
-  def _launch(self, B):
+  def _launch(self, B, with_target=True):
+    """with_target: this minibatch visits its rows for the first time in this epoch (first opt-epoch):
+    the graph variant that also runs the frozen target policy's forward."""
+    if self.precision != "f16":
+      with_target = True                      # the exact tier recomputes the target forward every time
     if not self.use_cuda_graph:
-      self._minibatch(B)
+      self._minibatch(B, with_target)
       return
-    g = self._graphs.get(B)
+    key = (B, with_target)
+    g = self._graphs.get(key)
     if g is None:
       if not self._graphs.get(("warm", B)):
         # first minibatch at this size runs eagerly: allocates workspaces, loads modules
-        self._minibatch(B)
+        self._minibatch(B, with_target)
         self._graphs[("warm", B)] = True
         return
       torch.cuda.synchronize(self.device)
       g = torch.cuda.CUDAGraph()
       launches0 = self.ops.launches
       with torch.cuda.graph(g):
-        self._minibatch(B)
-      self._graph_launches = self.ops.launches - launches0
-      self._graphs[B] = g
+        self._minibatch(B, with_target)
+      self._graphs[key] = (g, self.ops.launches - launches0)
+      g = self._graphs[key]
     else:
-      self.ops.launches += self._graph_launches
-    g.replay()
+      self.ops.launches += g[1]
+    g[0].replay()
 
   def _run_ragged(self, flat, T, E, rows):
     """T not divisible by the minibatch rows: the reference yields a short last minibatch."""

@@ -279,7 +279,7 @@ pf_loss_kernel(const float* __restrict__ mean, const float* __restrict__ logstd,
                const float* __restrict__ acts, const float* __restrict__ adv,
                const int32_t* __restrict__ idx, const double* __restrict__ adv_stats,
                float* __restrict__ d_mean, int n, int A, float inv_global, float clip,
-               double* __restrict__ part) {
+               double* __restrict__ part, int t_indexed) {
   v4l_pdl_enter();
   __shared__ float s_ls[MAX_A], s_tls[MAX_A], s_ivar[MAX_A], s_tivar[MAX_A];
   __shared__ float s_dls[LOSS_THREADS / 32][MAX_A];
@@ -314,7 +314,7 @@ pf_loss_kernel(const float* __restrict__ mean, const float* __restrict__ logstd,
       for (int a = 0; a < A; ++a) {
         const float x = acts[(long long)r * A + a];
         const float dm = x - mean[(long long)i * A + a];
-        const float dt = x - tmean[(long long)i * A + a];
+        const float dt = x - tmean[(long long)(t_indexed ? r : i) * A + a];
         lp += -0.5f * dm * dm * s_ivar[a] - s_ls[a] - HALF_LOG_2PI;
         tlp += -0.5f * dt * dt * s_tivar[a] - s_tls[a] - HALF_LOG_2PI;
       }
@@ -585,7 +585,7 @@ extern "C" int v4l_pf_loss(v4l_ctx* ctx, void* stream, const float* mean, const 
                            const float* adv, const int32_t* idx, const double* adv_stats,
                            float* d_mean, float* d_logstd, int n, int A, float inv_global,
                            float inv_local, float clip_para, float entropy_coeff, float* info,
-                           const int32_t* slot) {
+                           const int32_t* slot, int target_indexed) {
   V4L_REQUIRE(ctx && mean && logstd && target_mean && target_logstd && acts && adv && adv_stats &&
               d_mean && d_logstd && info, "v4l_pf_loss: NULL argument");
   V4L_REQUIRE(n > 0 && A > 0 && A <= MAX_A, "v4l_pf_loss: bad shape n=%d A=%d (A <= %d)", n, A, MAX_A);
@@ -593,7 +593,8 @@ extern "C" int v4l_pf_loss(v4l_ctx* ctx, void* stream, const float* mean, const 
   const int ctas = min(v4l_cdiv(n, LOSS_THREADS), 2 * ctx->sm_count);
   double* part = reinterpret_cast<double*>(ctx->scratch);
   V4L_LAUNCH(pf_loss_kernel, ctas, LOSS_THREADS, 0, s, mean, logstd, target_mean, target_logstd, acts, adv, idx,
-                                               adv_stats, d_mean, n, A, inv_global, clip_para, part);
+                                               adv_stats, d_mean, n, A, inv_global, clip_para, part,
+                                               (target_indexed && idx) ? 1 : 0);
   V4L_CHECK_LAUNCH();
   V4L_LAUNCH(pf_loss_finalize_kernel, 1, 32, 0, s, part, ctas, logstd, adv_stats, d_logstd, n, A, inv_local,
                                            entropy_coeff, info, slot);

@@ -577,6 +577,22 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
 // partial[split][kp/128][kp%128][n]; dbias[n] = scale * sum_split partial[split][kin_tiles][0][n]
 struct ReduceJobs { v4l_reduce_job j[V4L_MAX_JOBS]; };
 
+// fixed-order sum over the split-K partials with 8 loads in flight (the adds stay sequential: the
+// result does not depend on the unrolling)
+__device__ __forceinline__ float sum_splits(const float* __restrict__ src, int splits, long long stride) {
+  float s = 0.f;
+  int z = 0;
+  for (; z + 8 <= splits; z += 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = src[(z + j) * stride];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+  }
+  for (; z < splits; ++z) s += src[z * stride];
+  return s;
+}
+
 __global__ void __launch_bounds__(256) tc_wgrad_reduce_kernel(const __grid_constant__ ReduceJobs jobs) {
   // partial[split][kp][n] (n contiguous) -> dw[index[n][kp]] (kp contiguous): 32x32 tiles through
   // shared memory so that both the split-sum reads and the scattered writes are coalesced
@@ -592,10 +608,7 @@ __global__ void __launch_bounds__(256) tc_wgrad_reduce_kernel(const __grid_const
     for (int i = 0; i < 4; ++i) {
       const int kp = kp0 + ty + 8 * i, n = n0 + tx;
       float s = 0.f;
-      if (kp < J.Kp && n < J.N_valid) {
-        const float* src = J.partial + (long long)kp * J.Nmma + n;
-        for (int z = 0; z < J.splits; ++z) s += src[z * split_stride];
-      }
+      if (kp < J.Kp && n < J.N_valid) s = sum_splits(J.partial + (long long)kp * J.Nmma + n, J.splits, split_stride);
       tile[ty + 8 * i][tx] = s;
     }
     __syncthreads();
@@ -613,9 +626,7 @@ __global__ void __launch_bounds__(256) tc_wgrad_reduce_kernel(const __grid_const
   if (J.has_bias && blockIdx.x == gridDim.x - 1) {
     const float* src0 = J.partial + (long long)J.kin_tiles * 128 * J.Nmma;
     for (int n = threadIdx.x; n < J.N_valid; n += blockDim.x) {
-      float s = 0.f;
-      for (int z = 0; z < J.splits; ++z) s += src0[z * split_stride + n];
-      J.dbias[n] = s * J.scale;
+      J.dbias[n] = sum_splits(src0 + n, J.splits, split_stride) * J.scale;
     }
   }
 }

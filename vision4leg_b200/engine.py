@@ -359,11 +359,11 @@ class Ops:
     self.launches += 2
 
   def pf_loss(self, mean, logstd, tmean, tlogstd, acts, adv, idx, stats, d_mean, d_logstd, n, A,
-              inv_global, inv_local, clip_para, entropy_coeff, info, slot):
+              inv_global, inv_local, clip_para, entropy_coeff, info, slot, target_indexed=False):
     check(self.lib.v4l_pf_loss(self.h, self.ctx.stream(), ptr(mean), ptr(logstd), ptr(tmean),
                                ptr(tlogstd), ptr(acts), ptr(adv), ptr(idx), ptr(stats), ptr(d_mean),
                                ptr(d_logstd), n, A, inv_global, inv_local, clip_para, entropy_coeff,
-                               ptr(info), ptr(slot)))
+                               ptr(info), ptr(slot), 1 if target_indexed else 0))
     self.launches += 2
 
   def clip_adam(self, param, grad, m, v, n, hyper, info, slot, norm_slot):

@@ -285,7 +285,7 @@ class LocoPlanTC(_PlanTC):
     self._diag = {}
 
   # ---- forward --------------------------------------------------------------------------------
-  def forward(self, flat, imgs, idx, st, B, out):
+  def forward(self, flat, imgs, idx, st, B, out, out_map=None):
     """imgs [N,16,16,64] fp16 (whole rollout), idx int32 [B] or None, st [B,Sp] fp16 proprio rows,
     out fp32 [B,out_dim].  `flat` = the fp32 bucket the layout offsets refer to (biases, LN)."""
     ops, T, d = self.ops, self.T, self.d
@@ -345,7 +345,7 @@ class LocoPlanTC(_PlanTC):
     h1 = self.buf("h1", (B, 256)); h2 = self.buf("h2", (B, 256))
     self._lin_fwd(flat, self.k_head[0], pooled, B, 2 * d, h1, RM.dense(256), True)
     self._lin_fwd(flat, self.k_head[1], h1, B, 256, h2, RM.dense(256), True)
-    self._lin_fwd(flat, self.k_head[2], h2, B, 256, out, RM.dense(self.out_dim), False, c_f32=True)
+    self._lin_fwd(flat, self.k_head[2], h2, B, 256, out, out_map or RM.dense(self.out_dim), False, c_f32=True)
     return out
 
   # ---- backward -------------------------------------------------------------------------------
@@ -464,7 +464,7 @@ class NaturePlanTC(_PlanTC):
     self.vd = layout[self.k_proj][1][0]
     self.sd = layout[self.k_base[-1]][1][0]
 
-  def forward(self, flat, imgs, idx, st, B, out):
+  def forward(self, flat, imgs, idx, st, B, out, out_map=None):
     self._flat, self._B, self._imgs, self._idx, self._st = flat, B, imgs, idx, st
     W = self.vd + self.sd
     a3 = self._trunk_fwd(flat, imgs, idx, B, "encoder.visual_base.layers.")
@@ -477,7 +477,7 @@ class NaturePlanTC(_PlanTC):
     h1 = self.buf("h1", (B, 256)); h2 = self.buf("h2", (B, 256))
     self._lin_fwd(flat, self.k_head[0], cat, B, W, h1, RM.dense(256), True)
     self._lin_fwd(flat, self.k_head[1], h1, B, 256, h2, RM.dense(256), True)
-    self._lin_fwd(flat, self.k_head[2], h2, B, 256, out, RM.dense(self.out_dim), False, c_f32=True)
+    self._lin_fwd(flat, self.k_head[2], h2, B, 256, out, out_map or RM.dense(self.out_dim), False, c_f32=True)
     return out
 
   def backward(self, gflat, d_out):
