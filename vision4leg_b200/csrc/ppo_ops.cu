@@ -454,7 +454,7 @@ sqnorm_kernel(const float* __restrict__ g, long long n, double* __restrict__ par
 __global__ void __launch_bounds__(ADAM_THREADS)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, long long n, const float* __restrict__ hyper,
-            const double* __restrict__ part, int nparts) {
+            const double* __restrict__ part, int nparts, int vec_ok) {
   v4l_pdl_enter();
   __shared__ float s_coef;
   if (threadIdx.x < 32) {
@@ -471,7 +471,27 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   const float bc1 = 1.f - powf(b1, step);
   const float bc2_sqrt = sqrtf(1.f - powf(b2, step));
   const float step_size = lr / bc1;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+  // four parameters per thread and iteration (the bucket base is 16-byte aligned); element-wise math
+  // identical to the scalar form
+  const long long n4 = vec_ok ? (n >> 2) : 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i], p4 = reinterpret_cast<float4*>(p)[i];
+    float* gm = reinterpret_cast<float*>(&m4); float* gv = reinterpret_cast<float*>(&v4); float* gp = reinterpret_cast<float*>(&p4);
+    const float* gg = reinterpret_cast<const float*>(&g4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gi = gg[j] * coef;
+      const float mi = b1 * gm[j] + (1.f - b1) * gi;
+      const float vi = b2 * gv[j] + (1.f - b2) * gi * gi;
+      gm[j] = mi; gv[j] = vi;
+      const float denom = sqrtf(vi) / bc2_sqrt + eps;
+      gp[j] -= step_size * (mi / denom);
+    }
+    reinterpret_cast<float4*>(m)[i] = m4; reinterpret_cast<float4*>(v)[i] = v4; reinterpret_cast<float4*>(p)[i] = p4;
+  }
+  for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * coef;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
@@ -612,7 +632,8 @@ extern "C" int v4l_clip_adam(v4l_ctx* ctx, void* stream, float* param, const flo
   double* part = reinterpret_cast<double*>(ctx->scratch);
   V4L_LAUNCH(sqnorm_kernel, ctas, ADAM_THREADS, 0, s, grad, n, part);
   V4L_CHECK_LAUNCH();
-  V4L_LAUNCH(adam_kernel, ctas, ADAM_THREADS, 0, s, param, grad, m, v, n, hyper, part, ctas);
+  const int vec_ok = (((uintptr_t)param | (uintptr_t)grad | (uintptr_t)m | (uintptr_t)v) & 15) == 0;
+  V4L_LAUNCH(adam_kernel, ctas, ADAM_THREADS, 0, s, param, grad, m, v, n, hyper, part, ctas, vec_ok);
   V4L_CHECK_LAUNCH();
   V4L_LAUNCH(adam_finish_kernel, 1, 32, 0, s, hyper, part, ctas, info, slot, norm_slot);
   V4L_CHECK_LAUNCH();

@@ -594,40 +594,40 @@ __device__ __forceinline__ float sum_splits(const float* __restrict__ src, int s
 }
 
 __global__ void __launch_bounds__(256) tc_wgrad_reduce_kernel(const __grid_constant__ ReduceJobs jobs) {
-  // partial[split][kp][n] (n contiguous) -> dw[index[n][kp]] (kp contiguous): 32x32 tiles through
-  // shared memory so that both the split-sum reads and the scattered writes are coalesced
+  // partial[split][kp][n] (n contiguous) -> dw[index[n][kp]] (kp contiguous).  One output per thread and
+  // tile (8 kp x 32 n): the split loop is a chain of dependent-latency loads, so short chains on many
+  // blocks beat long chains on few; the tile goes through shared memory so that the split-sum reads are
+  // coalesced along n and the scattered writes run along kp.
   v4l_pdl_enter();
-  __shared__ float tile[32][33];
+  __shared__ float tile[8][33];
   const v4l_reduce_job& J = jobs.j[blockIdx.y];
   const long long split_stride = (long long)(J.kin_tiles + J.has_bias) * 128 * J.Nmma;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int tk = (J.Kp + 31) >> 5, tn = (J.N_valid + 31) >> 5;
+  const int wk = threadIdx.x & 7, wn = threadIdx.x >> 3;
+  const int tk = (J.Kp + 7) >> 3, tn = (J.N_valid + 31) >> 5;
   for (int t = blockIdx.x; t < tk * tn; t += gridDim.x) {
-    const int kp0 = (t % tk) << 5, n0 = (t / tk) << 5;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int kp = kp0 + ty + 8 * i, n = n0 + tx;
+    const int kp0 = (t % tk) << 3, n0 = (t / tk) << 5;
+    {
+      const int kp = kp0 + ty, n = n0 + tx;
       float s = 0.f;
       if (kp < J.Kp && n < J.N_valid) s = sum_splits(J.partial + (long long)kp * J.Nmma + n, J.splits, split_stride);
-      tile[ty + 8 * i][tx] = s;
+      tile[ty][tx] = s;
     }
     __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int n = n0 + ty + 8 * i, kp = kp0 + tx;
+    {
+      const int n = n0 + wn, kp = kp0 + wk;
       if (kp < J.Kp && n < J.N_valid) {
         const long long e = (long long)n * J.Kp + kp;
         const long long d = J.index ? (long long)J.index[e] : e;
-        if (d >= 0) J.dw[d] = tile[tx][ty + 8 * i] * J.scale;
+        if (d >= 0) J.dw[d] = tile[wk][wn] * J.scale;
       }
     }
     __syncthreads();
   }
   if (J.has_bias && blockIdx.x == gridDim.x - 1) {
     const float* src0 = J.partial + (long long)J.kin_tiles * 128 * J.Nmma;
-    for (int n = threadIdx.x; n < J.N_valid; n += blockDim.x) {
+    for (int n = threadIdx.x; n < J.N_valid; n += blockDim.x)
       J.dbias[n] = sum_splits(src0 + n, J.splits, split_stride) * J.scale;
-    }
   }
 }
 
@@ -787,7 +787,7 @@ extern "C" int v4l_tc_wgrad_flush(v4l_ctx* ctx, void* stream) {
   ReduceJobs all;
   memset(&all, 0, sizeof(all));
   for (int i = 0; i < ctx->n_jobs; ++i) all.j[i] = ctx->jobs[i];
-  V4L_LAUNCH(tc_wgrad_reduce_kernel, dim3(32, ctx->n_jobs), 256, 0, (cudaStream_t)stream, all);
+  V4L_LAUNCH(tc_wgrad_reduce_kernel, dim3(64, ctx->n_jobs), 256, 0, (cudaStream_t)stream, all);
   ctx->n_jobs = 0;
   ctx->defer_cursor = 0;
   V4L_CHECK_LAUNCH();
