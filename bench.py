@@ -73,12 +73,12 @@ class ClockSampler:
        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
   def __init__(self, index=0):
-    self.index, self.rows, self.proc = index, [], None
+    self.index, self.rows, self.stamps, self.proc = index, [], [], None
 
   def start(self):
     try:
       self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                    "--format=csv,noheader,nounits", "-lms", "100"],
+                                    "--format=csv,noheader,nounits", "-lms", "20"],
                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
       self.t = threading.Thread(target=self._read, daemon=True)
       self.t.start()
@@ -87,17 +87,24 @@ class ClockSampler:
 
   def _read(self):
     for line in self.proc.stdout:
+      self.stamps.append(time.perf_counter())
       self.rows.append([c.strip() for c in line.split(",")])
 
-  def stop(self):
+  def stop(self, window=None):
+    """window = (t0, t1) in time.perf_counter() seconds: keep the samples taken inside the timed region
+    (the sampler is started one warm-up step early so that nvidia-smi is already running by then)."""
     if self.proc is None:
       return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-    time.sleep(0.15)
+    time.sleep(0.05)
     self.proc.terminate()
     try:
       self.proc.wait(timeout=2)
     except Exception:
       self.proc.kill()
+    if window is not None:
+      keep = [r for t, r in zip(self.stamps, self.rows) if window[0] <= t <= window[1] + 0.02]
+      if keep:
+        self.rows = keep
     sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
     mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
     reasons = set()
@@ -302,22 +309,26 @@ def main():
     eng.sync_target()
     return eng.run_epoch(agent._draw_perms(T), args.batch)
 
-  for w in range(args.warmup):
-    resident_step(w)
-  barrier()
   sampler = ClockSampler(local)
-  if rank == 0:
+  for w in range(args.warmup):
+    if rank == 0 and w == args.warmup - 1:
+      sampler.start()                       # nvidia-smi needs ~100 ms to come up: start one warm-up step early
+    resident_step(w)
+  if rank == 0 and args.warmup == 0:
     sampler.start()
+  barrier()
   launches0 = eng.ops.launches
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  t_w0 = time.perf_counter()
   ev0.record()
   for k in range(args.steps):
     resident_step(args.warmup + k)
   ev1.record()
   barrier()
+  t_w1 = time.perf_counter()
   ms = max_over_ranks(ev0.elapsed_time(ev1))
   launches = eng.ops.launches - launches0
-  clocks = sampler.stop() if rank == 0 else None
+  clocks = sampler.stop((t_w0, t_w1)) if rank == 0 else None
   value = samples_per_step * args.steps / (ms / 1e3)
 
   # ---- end-to-end step through the public API with HOST buffers
