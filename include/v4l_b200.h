@@ -225,7 +225,9 @@ int v4l_adv_stats(v4l_ctx* ctx, void* stream, const float* adv, const int32_t* i
 int v4l_vf_loss(v4l_ctx* ctx, void* stream, const float* values, const float* returns,
                 const float* old_values, const int32_t* idx, float* d_values, int n,
                 float inv_global, float inv_local, int clipped, float clip_para,
-                float* info, const int32_t* slot);
+                float* info, const int32_t* slot,
+                void* d_values_f16 /* optional f16 [n,16]: scale_f16 * d_values in column 0, zero padded:
+                                      the tensor-core tier's backward starts from it */, float scale_f16);
 /* actor loss: log-prob, ratio, clipped surrogate, entropy bonus and their gradients w.r.t.
  * mean [n,A] and logstd [A]  (ppo.py:42-92).  target_mean/target_logstd come from the frozen
  * target policy; adv is normalised with the (possibly all-reduced) stats of v4l_adv_stats.
@@ -236,7 +238,8 @@ int v4l_pf_loss(v4l_ctx* ctx, void* stream, const float* mean, const float* logs
                 const float* adv, const int32_t* idx, const double* adv_stats,
                 float* d_mean, float* d_logstd, int n, int A, float inv_global, float inv_local,
                 float clip_para, float entropy_coeff, float* info, const int32_t* slot,
-                int target_indexed /* 0: target_mean is [n,A] (row i); 1: a per-rollout table read at row idx[i] */);
+                int target_indexed /* 0: target_mean is [n,A] (row i); 1: a per-rollout table read at row idx[i] */,
+                void* d_mean_f16 /* optional f16 [n,16] = scale_f16 * d_mean, zero padded (A <= 16) */, float scale_f16);
 
 /* ---- clip_grad_norm_(0.5) + Adam(eps=1e-5) over a flat bucket
  *      (reference ppo.py:71-75,116-120; a2c.py:30-40).
@@ -297,9 +300,37 @@ typedef struct {
                                     (an extra K slice whose X operand is the constant 1)         */
   int32_t defer;                 /* 1: leave the split partials in the context and sum them in
                                     the next v4l_tc_wgrad_flush (one launch for a whole backward) */
+  int32_t accumulate;            /* 1: dw += (gradient accumulation over micro-batches) */
 } v4l_tc_wgrad_args;
 int v4l_tc_wgrad(v4l_ctx* ctx, void* stream, const v4l_tc_wgrad_args* args);
 int v4l_tc_wgrad_flush(v4l_ctx* ctx, void* stream);
+
+/* ---- fused optimiser tail of one network pass (tensor-core tier; csrc/step_ops.cu):
+ * phase 1  split-K reduction of all deferred weight-gradient partials into the fp32 gradient bucket;
+ * phase 2  clip_grad_norm_(max_norm) + Adam over the flat bucket (same arithmetic as v4l_clip_adam,
+ *          reference ppo.py:71-75,116-120; a2c.py:30-40), pre-clip norm into info[norm_slot];
+ * phase 4  fp16 re-pack (v4l_pack_f16 semantics) of the weights the NEXT forward reads from the
+ *          updated bucket, Adam step counter + optional minibatch slot advance.
+ * `phases` is a bit mask; consecutive phases are separated by a device-wide barrier inside ONE
+ * kernel (grid = one CTA per SM).  Data-parallel runs launch phase 1, all-reduce the bucket, then
+ * launch phases 2|4.                                                                              */
+typedef struct {
+  int32_t phases;
+  float* param; float* grad; float* m; float* v; int64_t n;
+  float* hyper;                 /* as v4l_clip_adam */
+  float* info; const int32_t* slot; int32_t norm_slot;
+  const float* pack_src; const int32_t* pack_table; void* packed; int64_t n_pack;   /* or NULL */
+  int32_t* slot_advance;        /* optional: incremented by 1 at the very end */
+} v4l_opt_tail_args;
+int v4l_opt_tail(v4l_ctx* ctx, void* stream, const v4l_opt_tail_args* args);
+/* 1 if a device-wide barrier of v4l_opt_tail ever timed out (synchronises the device)           */
+int v4l_opt_tail_error(v4l_ctx* ctx);
+/* minibatch prologue in one launch: cur_idx[i] = flat_idx[(*slot)*n + i] (v4l_select_rows), the
+ * advantage statistics of those rows (v4l_adv_stats) and, if state_f16 != NULL, the proprio rows
+ * state[cur_idx[i], :S] converted to f16 and zero padded to Sp columns                           */
+int v4l_mb_begin(v4l_ctx* ctx, void* stream, const int32_t* flat_idx, const int32_t* slot,
+                 int32_t* cur_idx, int n, const float* adv, double* stats, const float* state,
+                 int S, void* state_f16, int Sp);
 /* out[n] = sum_m sum_f dy(m, f*N + n) for a row-mapped f16 [M, N*fold <= 256] view (bias
  * gradients; fold > 1 sums the sub-positions of a space-to-depth cell)                         */
 int v4l_colsum_f16(v4l_ctx* ctx, void* stream, const void* dy, const v4l_rowmap* map, int M, int N,

@@ -238,7 +238,7 @@ def test_tc_tier_update_matches_oracle(B, family):
   m_err = rel(eng._bufs(B)["mean"], orc._last["mean"])
   print("B=%d value err %.3e mean err %.3e" % (B, v_err, m_err))
   assert v_err < 1e-2
-  assert m_err < 3e-2   # the actor forward runs on an encoder already stepped by (fp16) critic grads
+  assert m_err < 1e-2   # north-star bound of the reduced-precision tier on action means
   for k in ("Training/vf_loss", "logprob/mean", "advs/mean", "advs/std", "log_std/mean"):
     assert abs(info[k] - ref[k]) <= 1e-2 * abs(ref[k]) + 1e-4, (k, info[k], ref[k])
   assert abs(info["grad_norm/vf"] - ref["grad_norm/vf"]) <= 3e-2 * ref["grad_norm/vf"]

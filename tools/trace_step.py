@@ -58,7 +58,10 @@ def main():
     last_end[st] = e_
     if st == main_stream:
       busy += e_ - s_
-    short = n_.split("::")[-1].split("(")[0][:28]
+    import re as _re
+    _m = _re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\s*(?:<[^()]*>)?\s*\(", n_)
+    _m = [x for x in _m if x not in ("void", "namespace")]
+    short = (_m[0] if _m else n_)[:28]
     print("%8.1f  s%-4s %-28s dur %6.1f  gap %6.1f" % (s_ - t0, st, short, e_ - s_, gap))
   print("main stream busy %.1f us of %.1f" % (busy, ks[b][0] - t0))
 

@@ -73,7 +73,15 @@ class TcWgradArgs(C.Structure):
               ("bw", C.c_int32), ("bh", C.c_int32), ("bb", C.c_int32),
               ("n_taps", C.c_int32), ("tap_dw", C.c_int32 * 16), ("tap_dh", C.c_int32 * 16),
               ("N_valid", C.c_int32), ("index", C.c_void_p), ("dw", C.c_void_p), ("out_scale", C.c_float),
-              ("dbias", C.c_void_p), ("defer", C.c_int32)]
+              ("dbias", C.c_void_p), ("defer", C.c_int32), ("accumulate", C.c_int32)]
+
+
+class OptTailArgs(C.Structure):
+  _fields_ = [("phases", C.c_int32), ("param", C.c_void_p), ("grad", C.c_void_p), ("m", C.c_void_p),
+              ("v", C.c_void_p), ("n", C.c_int64), ("hyper", C.c_void_p), ("info", C.c_void_p),
+              ("slot", C.c_void_p), ("norm_slot", C.c_int32), ("pack_src", C.c_void_p),
+              ("pack_table", C.c_void_p), ("packed", C.c_void_p), ("n_pack", C.c_int64),
+              ("slot_advance", C.c_void_p)]
 
 
 class TcConvFlatArgs(C.Structure):
@@ -132,13 +140,16 @@ SIGNATURES = {
   "v4l_select_rows": [_vp, _vp, _vp, _vp, _vp, _i],
   "v4l_slot_advance": [_vp, _vp, _vp, C.c_int32],
   "v4l_adv_stats": [_vp, _vp, _vp, _vp, _i, _vp],
-  "v4l_vf_loss": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _i, _f, _vp, _vp],
+  "v4l_vf_loss": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _i, _f, _vp, _vp, _vp, _f],
   "v4l_pf_loss": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _f,
-                  _f, _vp, _vp, _i],
+                  _f, _vp, _vp, _i, _vp, _f],
   "v4l_clip_adam": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i],
   "v4l_tc_gemm": [_vp, _vp, C.POINTER(TcGemmArgs)],
   "v4l_tc_wgrad": [_vp, _vp, C.POINTER(TcWgradArgs)],
   "v4l_tc_wgrad_flush": [_vp, _vp],
+  "v4l_opt_tail": [_vp, _vp, C.POINTER(OptTailArgs)],
+  "v4l_opt_tail_error": [_vp],
+  "v4l_mb_begin": [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i],
   "v4l_colsum_f16": [_vp, _vp, _vp, C.POINTER(RowMap), _i, _i, _i, _f, _vp],
   "v4l_ingest_img": [_vp, _vp, _vp, _vp, _i64, _vp],
   "v4l_ingest_img_f16": [_vp, _vp, _vp, _vp, _i64, _vp],

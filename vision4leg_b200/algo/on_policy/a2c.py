@@ -41,12 +41,25 @@ class A2C(OnRLAlgo):
     policy_loss = (-log_probs * advs).mean() - self.entropy_coeff * ent.mean()
     values = self.vf(obs)
     vf_loss = self.vf_criterion(values, est_rets)
+    # Both backward passes run BEFORE either optimiser step: with a shared encoder the actor's step
+    # changes weights the critic's saved activations were computed with (the reference's order,
+    # a2c.py:66-76, makes torch raise an in-place-modification error in that case; with separate
+    # networks the two orders give identical results).  Gradients of shared parameters are kept apart.
+    shared = {id(p) for p in self.pf.parameters()} & {id(p) for p in self.vf.parameters()}
     self.pf_optimizer.zero_grad()
     policy_loss.backward()
-    torch.nn.utils.clip_grad_norm_(self.pf.parameters(), 0.5)
-    self.pf_optimizer.step()
+    pf_grads = {id(p): p.grad.clone() for p in self.pf.parameters() if id(p) in shared and p.grad is not None}
     self.vf_optimizer.zero_grad()
     vf_loss.backward()
+    vf_grads = {id(p): p.grad.clone() for p in self.vf.parameters() if id(p) in shared and p.grad is not None}
+    for p in self.pf.parameters():
+      if id(p) in pf_grads:
+        p.grad.copy_(pf_grads[id(p)])
+    torch.nn.utils.clip_grad_norm_(self.pf.parameters(), 0.5)
+    self.pf_optimizer.step()
+    for p in self.vf.parameters():
+      if id(p) in vf_grads:
+        p.grad.copy_(vf_grads[id(p)])
     torch.nn.utils.clip_grad_norm_(self.vf.parameters(), 0.5)
     self.vf_optimizer.step()
 

@@ -28,13 +28,15 @@ class PPO(A2C):
     self.sample_key = ["obs", "acts", "advs", "estimate_returns", "values"]
     self.process_group = None       # set to a torch.distributed group for data-parallel updates
     self.use_cuda_graph = True
-    self.precision = "fp32"         # "fp32": exact CUDA-core tier; "fp16": tcgen05 tensor-core tier
+    self.precision = "fp32"         # "fp32": exact CUDA-core tier; "f16" (or "fp16"): tcgen05 tensor-core tier
     self.half_image_staging = True  # f16 tier: stream the buffer's fp16 copy of the depth stack (same values)
     self._engine = None
 
   @property
   def engine(self):
     if self._engine is None:
+      if self.precision == "fp16":
+        self.precision = "f16"
       self._engine = PPOUpdateEngine(self.pf, self.vf, self.target_pf, self.device, self.clip_para,
                                      self.entropy_coeff, self.clipped_value_loss,
                                      use_cuda_graph=self.use_cuda_graph,

@@ -88,6 +88,8 @@ class PPOUpdateEngine:
       self.world = dist.get_world_size(process_group)
     self._build_buckets()
     kw = getattr(pf, "_plan_kwargs", {})
+    if precision == "fp16":
+      precision = "f16"
     if precision not in ("fp32", "f16"):
       raise ValueError("precision must be 'fp32' (exact CUDA-core tier) or 'f16' (tcgen05 tier)")
     self.precision = precision
@@ -101,6 +103,7 @@ class PPOUpdateEngine:
       self.plan_vf = Plan(self.ops, self.S, 1, self.vf_layout, nh)
       self.plan_t = Plan(self.ops, self.S, self.A, self.pf_layout, nh, with_backward=False)
       self.plan_t.pack(self.t_flat)
+      self.plan_pf.world = self.plan_vf.world = self.world
     else:
       self.plan_pf = engine.make_plan(self.family, self.ops, self.S, self.A, **kw)
       self.plan_vf = engine.make_plan(self.family, self.ops, self.S, 1, **kw)
@@ -308,18 +311,46 @@ class PPOUpdateEngine:
                  r["advs"], r["rets"], T, E, float(gamma), float(tau if use_gae else 1.0), use_tl,
                  0 if use_gae else 1)
 
-  def _aux_plan(self, B):
-    key = ("aux", B)
+  def _aux_plan(self, B, which="vf"):
+    """forward-only plan for `B` rows of the critic ("vf") or the actor ("pf")"""
+    key = ("aux", B, which)
     p = self._mb_bufs.get(key)
     if p is None:
       kw = getattr(self.pf, "_plan_kwargs", {})
+      out_dim, layout = (1, self.vf_layout) if which == "vf" else (self.A, self.pf_layout)
       if self.precision == "f16":
-        p = engine_tc.PLANS[self.family](self.ops, self.S, 1, self.vf_layout, kw.get("n_heads", (1, 1)),
+        p = engine_tc.PLANS[self.family](self.ops, self.S, out_dim, layout, kw.get("n_heads", (1, 1)),
                                          with_backward=False)
       else:
-        p = engine.make_plan(self.family, self.ops, self.S, 1, **kw)
+        p = engine.make_plan(self.family, self.ops, self.S, out_dim, **kw)
       self._mb_bufs[key] = p
     return p
+
+  def infer(self, obs):
+    """Action means and values of `obs` [n, D] (fp32 host array or device tensor) on the engine's
+    precision tier with the CURRENT parameters: what the collector's `pf.explore` + `vf` evaluate
+    (reference collector/on_policy.py:90-100), one call for both networks.  Returns device tensors
+    (mean [n, A], value [n, 1])."""
+    x = torch.as_tensor(np.ascontiguousarray(obs, dtype=np.float32) if not torch.is_tensor(obs) else obs)
+    x = x.to(self.device, torch.float32).reshape(-1, self.S + (engine.IMG_ELEMS if self.has_img else 0)).contiguous()
+    n = x.shape[0]
+    mean = torch.empty((n, self.A), device=self.device, dtype=torch.float32)
+    value = torch.empty((n, 1), device=self.device, dtype=torch.float32)
+    ppf, pvf = self._aux_plan(n, "pf"), self._aux_plan(n, "vf")
+    if self.precision == "f16":
+      imgs = torch.empty((n, 16, 16, 64), device=self.device, dtype=torch.float16)
+      self.ops.ingest_img(x[:, self.S:].contiguous(), imgs, n)
+      st = torch.zeros((n, ppf.Sp), device=self.device, dtype=torch.float16)
+      self.ops.gather_rows_f16(x, True, None, st, n, self.S, x.shape[1], ppf.Sp)
+      ppf.pack(self.pf_flat)
+      ppf.forward(self.pf_flat, imgs, None, st, n, mean)
+      pvf.pack(self.vf_flat)
+      pvf.forward(self.vf_flat, imgs, None, st, n, value)
+    else:
+      inp = engine.Input.from_flat(x, self.S, self.has_img)
+      ppf.forward(self.P_pf, inp, mean)
+      pvf.forward(self.P_vf, inp, value)
+    return mean, value
 
   # ---------------------------------------------------------------------------------------------
   # one epoch
@@ -362,12 +393,12 @@ class PPOUpdateEngine:
     idx = b["cur_idx"]
     inv_local = 1.0 / B
     inv_global = 1.0 / (B * self.world)
+    if self.precision == "f16":
+      return self._minibatch_tc(B, b, idx, inv_local, inv_global, with_target)
     ops.select_rows(self._flat_idx, self._slot, idx, B)
     ops.adv_stats(r["advs"], idx, B, b["stats"])
     if self.world > 1:
       self._allreduce_stats(b)
-    if self.precision == "f16":
-      return self._minibatch_tc(B, b, idx, inv_local, inv_global, with_target)
     inp = self._input(B, idx)
     # ---- critic
     self.plan_vf.forward(self.P_vf, inp, b["values"])
@@ -392,12 +423,18 @@ class PPOUpdateEngine:
     ops.slot_advance(self._slot, 0)
 
   def _minibatch_tc(self, B, b, idx, inv_local, inv_global, with_target=True):
-    """Same sequence on the tensor-core tier: fp16 activations, tcgen05 GEMMs; weights are
-    re-packed to fp16 right before each network's forward (the critic step has just changed
-    the shared encoder when the actor runs)."""
+    """Same sequence on the tensor-core tier: fp16 activations, tcgen05 GEMMs.  The chain is kept short:
+    one prologue launch, each loss kernel writes the loss-scaled fp16 gradient the backward starts from,
+    and ONE optimiser-tail launch per network (split-K reduction of the weight gradients -> clip + Adam ->
+    fp16 re-pack of the weights the NEXT forward reads: the critic's tail re-packs the actor's weights,
+    whose shared encoder it has just stepped, the actor's tail the critic's)."""
     ops, r = self.ops, self._roll
     imgs, st = r["imgs"], b["st"]
-    ops.gather_rows_f16(r["state"], True, idx, st, B, self.S, self.S, self.plan_pf.Sp)
+    ppf, pvf = self.plan_pf, self.plan_vf
+    ops.mb_begin(self._flat_idx, self._slot, idx, B, r["advs"], b["stats"], r["state"] if self.S else None,
+                 self.S, st, ppf.Sp)
+    if self.world > 1:
+      self._allreduce_stats(b)
     # The frozen target policy (copied once per update_per_epoch, ppo.py:34) only depends on the rollout
     # row: its action mean is computed when a row is first visited (first opt-epoch), as a parallel
     # branch of the captured graph next to the critic phase, written straight into a per-rollout
@@ -407,30 +444,37 @@ class PPOUpdateEngine:
       with ops.fork(1):
         self.plan_t.forward(self.t_flat, imgs, idx, st, B, r["tmean_all"],
                             out_map=engine.RM(1, self.A, 0, 0, idx=idx))
-    # ---- critic
-    self.plan_vf.pack(self.vf_flat)
-    self.plan_vf.forward(self.vf_flat, imgs, idx, st, B, b["values"])
+    # ---- critic (weights were packed by the previous actor tail / run_epoch)
+    pvf.forward(self.vf_flat, imgs, idx, st, B, b["values"])
     ops.vf_loss(b["values"], r["rets"], r["values"], idx, b["d_values"], B, inv_global, inv_local,
-                self.clipped_value_loss, self.clip_para, self._info, self._slot)
-    self.plan_vf.backward(self.g_vf, b["d_values"])
-    if self.world > 1:
-      self._allreduce(self.g_vf)
-    ops.clip_adam(self.vf_flat, self.g_vf, self.m_vf, self.v_vf, self.n_vf, self.hyper_vf, self._info,
-                  self._slot, INFO_GRAD_NORM_VF)
+                self.clipped_value_loss, self.clip_para, self._info, self._slot,
+                d_f16=pvf.grad_in(B), scale_f16=pvf.loss_scale(B))
+    pvf.backward(self.g_vf, None, flush=False)
+    self._tail(self.vf_flat, self.g_vf, self.m_vf, self.v_vf, self.n_vf, self.hyper_vf, INFO_GRAD_NORM_VF,
+               self.pf_flat, ppf.W, None)
     # ---- actor
-    self.plan_pf.pack(self.pf_flat)
-    self.plan_pf.forward(self.pf_flat, imgs, idx, st, B, b["mean"])
+    ppf.forward(self.pf_flat, imgs, idx, st, B, b["mean"])
     if with_target:
       ops.join(1)
     ops.pf_loss(b["mean"], self.logstd, r["tmean_all"], self.t_logstd, r["acts"], r["advs"], idx, b["stats"],
                 b["d_mean"], self.G_pf["logstd"], B, self.A, inv_global, inv_local, self.clip_para,
-                self.entropy_coeff, self._info, self._slot, target_indexed=True)
-    self.plan_pf.backward(self.g_pf, b["d_mean"])
+                self.entropy_coeff, self._info, self._slot, target_indexed=True,
+                d_f16=ppf.grad_in(B), scale_f16=ppf.loss_scale(B))
+    ppf.backward(self.g_pf, None, flush=False)
+    self._tail(self.pf_flat, self.g_pf, self.m_pf, self.v_pf, self.n_pf, self.hyper_pf, INFO_GRAD_NORM_PF,
+               self.vf_flat, pvf.W, self._slot)
+
+  def _tail(self, flat, g, m, v, n, hyper, norm_slot, pack_src, W, slot_advance):
+    """reduce -> (all-reduce) -> clip + Adam -> re-pack `W` from `pack_src` -> counters"""
+    kw = dict(param=flat, grad=g, m=m, v=v, n=n, hyper=hyper, info=self._info, slot=self._slot,
+              norm_slot=norm_slot, pack_src=pack_src, pack_table=W.table, packed=W.packed, n_pack=W.size,
+              slot_advance=slot_advance)
     if self.world > 1:
-      self._allreduce(self.g_pf)
-    ops.clip_adam(self.pf_flat, self.g_pf, self.m_pf, self.v_pf, self.n_pf, self.hyper_pf, self._info,
-                  self._slot, INFO_GRAD_NORM_PF)
-    ops.slot_advance(self._slot, 0)
+      self.ops.opt_tail(1)
+      self._allreduce(g)
+      self.ops.opt_tail(6, **kw)
+    else:
+      self.ops.opt_tail(7, **kw)
 
   def _allreduce(self, t):
     import torch.distributed as dist
@@ -467,6 +511,8 @@ class PPOUpdateEngine:
       self._info = torch.zeros((n_mb, INFO_STRIDE), device=dev, dtype=torch.float32)
       self._graphs.clear()
     B = rows * E
+    if self.precision == "f16":
+      self.plan_vf.pack(self.vf_flat)       # later re-packs ride on the optimiser tails (_minibatch_tc)
     if tail == 0 and len(perms) > 0:
       # uniform minibatches: flat_idx is [n_mb, B] and the device slot counter indexes it
       if getattr(self, "_flat_idx_static", None) is None or self._flat_idx_static.numel() != flat.size:

@@ -69,7 +69,10 @@ class RLAlgo:
       with open(os.path.join(prefix, "_obs_normalizer_{}.pkl".format(epoch)), "wb") as f:
         pickle.dump(normalizer, f)
     for name, network in self.snapshot_networks:
-      torch.save(network.state_dict(), os.path.join(prefix, "model_{}_{}.pth".format(name, epoch)))
+      # parameters may be views into one flat bucket (PPO engine): clone so that each file holds only
+      # its own tensors, with independent storages, like the reference's checkpoints (rl_algo.py:84-95)
+      sd = {k: v.detach().clone() for k, v in network.state_dict().items()}
+      torch.save(sd, os.path.join(prefix, "model_{}_{}.pth".format(name, epoch)))
 
   def train(self):
     self.pretrain()

@@ -60,6 +60,15 @@ extern "C" int v4l_ctx_create(v4l_ctx** out, int device, size_t scratch_bytes) {
     return -2;
   }
   c->defer_base = c->scratch + c->scratch_elems;
+  c->counters = nullptr;
+  e = cudaMalloc(&c->counters, V4L_N_COUNTERS * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(c->counters, 0, V4L_N_COUNTERS * sizeof(unsigned int));
+  if (e != cudaSuccess) {
+    v4l_set_error("v4l_ctx_create: counters -> %s", cudaGetErrorString(e));
+    cudaFree(c->scratch);
+    delete c;
+    return -2;
+  }
   *out = c;
   return 0;
 }
@@ -67,6 +76,7 @@ extern "C" int v4l_ctx_create(v4l_ctx** out, int device, size_t scratch_bytes) {
 extern "C" int v4l_ctx_destroy(v4l_ctx* ctx) {
   if (!ctx) return 0;
   cudaFree(ctx->scratch);
+  cudaFree(ctx->counters);
   delete ctx;
   return 0;
 }

@@ -8,13 +8,13 @@
 
 // one deferred weight-gradient reduction (see tc_gemm.cu: v4l_tc_wgrad with defer = 1)
 struct v4l_reduce_job {
-  const float* partial;      // [splits][kin_tiles + has_bias][128][Nmma]
+  const float* partial;      // [splits][kin_tiles + has_bias][Nmma][128]  (packed-K lane fastest)
   const int32_t* index;      // packing table or NULL
   float* dw;
   float* dbias;              // or NULL
   int splits, kin_tiles, has_bias, Nmma, N_valid, Kp;
   float scale;
-  int pad_;
+  int accumulate;            // dw += instead of dw = (gradient accumulation over micro-batches)
 };
 constexpr int V4L_MAX_JOBS = 48;
 
@@ -28,7 +28,10 @@ struct v4l_ctx {
   size_t defer_elems, defer_cursor;
   v4l_reduce_job jobs[V4L_MAX_JOBS];
   int n_jobs;
+  unsigned int* counters;   // V4L_N_COUNTERS zero-initialised device words: last-CTA arrival counters and
+                            // the grid barrier of the fused optimiser tail (each user re-arms its own)
 };
+constexpr int V4L_N_COUNTERS = 64;
 
 void v4l_set_error(const char* fmt, ...);
 

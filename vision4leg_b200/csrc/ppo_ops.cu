@@ -5,6 +5,7 @@
 // keep all reductions on-chip (warp shuffles) and never sync with the host: the 18 logged
 // statistics of a minibatch (reference ppo.py:77-92,122-123,142-145) land in a device-side
 // info row that the host reads once per epoch.
+#include <cuda_fp16.h>
 #include <float.h>
 #include <math.h>
 
@@ -219,11 +220,29 @@ __global__ void __launch_bounds__(1024) adv_stats_kernel(const float* __restrict
 // =============================================================================================
 constexpr int LOSS_THREADS = 256;
 
+// The CTA that finishes last (device-wide arrival counter, reset by it for the next launch) sums the
+// per-CTA partials in CTA order: one launch, same fixed summation order as a separate finalize pass.
+__device__ __forceinline__ bool last_block_arrives(unsigned int* counter) {
+  __shared__ bool s_last;
+  __threadfence();                                   // this CTA's partials are visible device-wide
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(counter, 1u);
+    s_last = (t == gridDim.x - 1);
+    if (s_last) *counter = 0u;                       // every CTA has arrived: safe to re-arm
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last;
+}
+
 __global__ void __launch_bounds__(LOSS_THREADS)
 vf_loss_kernel(const float* __restrict__ values, const float* __restrict__ returns,
                const float* __restrict__ old_values, const int32_t* __restrict__ idx,
-               float* __restrict__ d_values, int n, float inv_global, int clipped, float clip,
-               double* __restrict__ part) {
+               float* __restrict__ d_values, __half* __restrict__ d_f16, float scale_f16, int n,
+               float inv_global, float inv_local, int clipped, float clip,
+               double* part, unsigned int* counter, float* __restrict__ info,
+               const int32_t* __restrict__ slot) {
   v4l_pdl_enter();
   __shared__ double shd[32];
   double acc = 0.0;
@@ -248,18 +267,22 @@ vf_loss_kernel(const float* __restrict__ values, const float* __restrict__ retur
       else              { l = 0.5f * l1; g = 0.5f * (e1 + e2 * inside) * inv_global; }
     }
     d_values[i] = g;
+    if (d_f16) {
+      // tensor-core tier: the backward pass starts from the loss-scaled fp16 gradient, padded to 16 columns
+      uint4 z = make_uint4(0, 0, 0, 0);
+      uint4 f = z;
+      f.x = (uint32_t)__half_as_ushort(__float2half(g * scale_f16));
+      reinterpret_cast<uint4*>(d_f16 + (long long)i * 16)[0] = f;
+      reinterpret_cast<uint4*>(d_f16 + (long long)i * 16)[1] = z;
+    }
     acc += l;
   }
   acc = block_reduce(acc, OpAddD(), 0.0, shd);
   if (threadIdx.x == 0) part[blockIdx.x] = acc;
-}
-
-__global__ void vf_loss_finalize_kernel(const double* __restrict__ part, int nparts, float inv_local,
-                                        float* __restrict__ info, const int32_t* __restrict__ slot) {
-  v4l_pdl_enter();
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
+  if (!last_block_arrives(counter)) return;
+  if (threadIdx.x == 0) {
     double s = 0.0;
-    for (int i = 0; i < nparts; ++i) s += part[i];
+    for (int i = 0; i < (int)gridDim.x; ++i) s += reinterpret_cast<volatile double*>(part)[i];
     float* row = info + (long long)(slot ? *slot : 0) * V4L_INFO_STRIDE;
     row[V4L_INFO_VF_LOSS] = (float)(s * inv_local);
   }
@@ -278,8 +301,10 @@ pf_loss_kernel(const float* __restrict__ mean, const float* __restrict__ logstd,
                const float* __restrict__ tmean, const float* __restrict__ tlogstd,
                const float* __restrict__ acts, const float* __restrict__ adv,
                const int32_t* __restrict__ idx, const double* __restrict__ adv_stats,
-               float* __restrict__ d_mean, int n, int A, float inv_global, float clip,
-               double* __restrict__ part, int t_indexed) {
+               float* __restrict__ d_mean, __half* __restrict__ d_f16, float scale_f16, int n, int A,
+               float inv_global, float inv_local, float clip, float entropy_coeff, double* part, int t_indexed,
+               float* __restrict__ d_logstd, unsigned int* counter, float* __restrict__ info,
+               const int32_t* __restrict__ slot) {
   v4l_pdl_enter();
   __shared__ float s_ls[MAX_A], s_tls[MAX_A], s_ivar[MAX_A], s_tivar[MAX_A];
   __shared__ float s_dls[LOSS_THREADS / 32][MAX_A];
@@ -339,13 +364,17 @@ pf_loss_kernel(const float* __restrict__ mean, const float* __restrict__ logstd,
       float g = 0.f;
       if (live) {
         const float dm = acts[(long long)r * A + a] - mean[(long long)i * A + a];
-        d_mean[(long long)i * A + a] = coef * dm * s_ivar[a];
+        const float gm = coef * dm * s_ivar[a];
+        d_mean[(long long)i * A + a] = gm;
+        if (d_f16) d_f16[(long long)i * 16 + a] = __float2half(gm * scale_f16);
         g = coef * (dm * dm * s_ivar[a] - 1.f);           // d lp / d logstd_a
       }
 #pragma unroll
       for (int o = 16; o; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
       if (lane == 0) s_dls[warp][a] += g;
     }
+    if (d_f16 && live)                                     // zero padding of the 16-column fp16 row
+      for (int a = A; a < 16; ++a) d_f16[(long long)i * 16 + a] = __float2half(0.f);
   }
   a_loss = block_reduce(a_loss, OpAddD(), 0.0, shd);
   a_lp = block_reduce(a_lp, OpAddD(), 0.0, shd);
@@ -364,30 +393,27 @@ pf_loss_kernel(const float* __restrict__ mean, const float* __restrict__ logstd,
     for (int w = 0; w < LOSS_THREADS / 32; ++w) s += s_dls[w][threadIdx.x];
     p[8 + threadIdx.x] = s;
   }
-}
-
-__global__ void pf_loss_finalize_kernel(const double* __restrict__ part, int nparts,
-                                        const float* __restrict__ logstd,
-                                        const double* __restrict__ adv_stats, float* __restrict__ d_logstd,
-                                        int n, int A, float inv_local, float entropy_coeff,
-                                        float* __restrict__ info, const int32_t* __restrict__ slot) {
-  v4l_pdl_enter();
-  // one warp; lane a < A reduces d_logstd[a]; lane 0 writes the info row
-  const int lane = threadIdx.x;
+  if (!last_block_arrives(counter)) return;
+  if (threadIdx.x >= 32) return;
+  // ---- finalize (last CTA, one warp): lane a < A reduces d_logstd[a]; lane 0 writes the info row
+  const int nparts = (int)gridDim.x;
+  const volatile double* partv = part;
   float* row = info + (long long)(slot ? *slot : 0) * V4L_INFO_STRIDE;
   for (int a = lane; a < A; a += 32) {
     double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += part[(long long)p * PF_PART + 8 + a];
+    for (int q = 0; q < nparts; ++q) s += partv[(long long)q * PF_PART + 8 + a];
     const float raw = logstd[a];
     const float pass = (raw >= -5.f && raw <= 2.f) ? 1.f : 0.f;      // clamp backward
-    // entropy = sum_a (0.5 + 0.5 log 2pi + logstd_a): d(-c * mean ent)/d logstd_a = -c
-    d_logstd[a] = pass * ((float)s - entropy_coeff);
+    // entropy = sum_a (0.5 + 0.5 log 2pi + logstd_a): d(-c * mean ent)/d logstd_a = -c over the GLOBAL
+    // minibatch; this rank contributes its share n / (n * world) of it (the gradient buckets are
+    // SUM-all-reduced across ranks, like the surrogate part which already carries inv_global)
+    d_logstd[a] = pass * ((float)s - entropy_coeff * ((float)n * inv_global));
   }
   if (lane == 0) {
     double loss = 0.0, slp = 0.0, slp2 = 0.0;
     float lpmax = -FLT_MAX, lpmin = FLT_MAX, rmax = -FLT_MAX, rmin = FLT_MAX;
-    for (int p = 0; p < nparts; ++p) {
-      const double* q = part + (long long)p * PF_PART;
+    for (int pi = 0; pi < nparts; ++pi) {
+      const volatile double* q = partv + (long long)pi * PF_PART;
       loss += q[0]; slp += q[1]; slp2 += q[2];
       lpmax = fmaxf(lpmax, (float)q[3]); lpmin = fminf(lpmin, (float)q[4]);
       rmax = fmaxf(rmax, (float)q[5]); rmin = fminf(rmin, (float)q[6]);
@@ -461,11 +487,14 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     const double s = sum_parts(part, nparts);             // same order in every CTA
     if (threadIdx.x == 0) {
       const float total = (float)sqrt(s);
-      s_coef = fminf(hyper[4] / (total + 1e-6f), 1.f);    // clip_grad_norm_
+      // a non-finite gradient norm (fp16 overflow in the tensor-core tier) would poison the Adam
+      // moments for good: skip this step instead (coef < 0 marks it; the norm is still logged)
+      s_coef = isfinite(total) ? fminf(hyper[4] / (total + 1e-6f), 1.f) : -1.f;    // clip_grad_norm_
     }
   }
   __syncthreads();
   const float coef = s_coef;
+  if (coef < 0.f) return;
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3];
   const float step = hyper[5] + 1.f;
   const float bc1 = 1.f - powf(b1, step);
@@ -508,7 +537,7 @@ __global__ void adam_finish_kernel(float* hyper, const double* __restrict__ part
   if (blockIdx.x == 0 && threadIdx.x < 32) {
     const double s = sum_parts(part, nparts);
     if (threadIdx.x == 0) {
-      hyper[5] += 1.f;
+      if (isfinite((float)sqrt(s))) hyper[5] += 1.f;
       if (info && norm_slot >= 0)
         info[(long long)(slot ? *slot : 0) * V4L_INFO_STRIDE + norm_slot] = (float)sqrt(s);
     }
@@ -586,16 +615,15 @@ extern "C" int v4l_adv_stats(v4l_ctx* ctx, void* stream, const float* adv, const
 extern "C" int v4l_vf_loss(v4l_ctx* ctx, void* stream, const float* values, const float* returns,
                            const float* old_values, const int32_t* idx, float* d_values, int n,
                            float inv_global, float inv_local, int clipped, float clip_para,
-                           float* info, const int32_t* slot) {
+                           float* info, const int32_t* slot, void* d_values_f16, float scale_f16) {
   V4L_REQUIRE(ctx && values && returns && d_values && info && n > 0, "v4l_vf_loss: bad argument");
   V4L_REQUIRE(!clipped || old_values, "v4l_vf_loss: clipped loss needs old_values");
   cudaStream_t s = (cudaStream_t)stream;
   const int ctas = min(v4l_cdiv(n, LOSS_THREADS), 2 * ctx->sm_count);
   double* part = reinterpret_cast<double*>(ctx->scratch);
-  V4L_LAUNCH(vf_loss_kernel, ctas, LOSS_THREADS, 0, s, values, returns, old_values, idx, d_values, n, inv_global,
-                                               clipped, clip_para, part);
-  V4L_CHECK_LAUNCH();
-  V4L_LAUNCH(vf_loss_finalize_kernel, 1, 32, 0, s, part, ctas, inv_local, info, slot);
+  V4L_LAUNCH(vf_loss_kernel, ctas, LOSS_THREADS, 0, s, values, returns, old_values, idx, d_values,
+             reinterpret_cast<__half*>(d_values_f16), scale_f16, n, inv_global, inv_local, clipped, clip_para, part,
+             ctx->counters + 0, info, slot);
   V4L_CHECK_LAUNCH();
   return 0;
 }
@@ -605,19 +633,17 @@ extern "C" int v4l_pf_loss(v4l_ctx* ctx, void* stream, const float* mean, const 
                            const float* adv, const int32_t* idx, const double* adv_stats,
                            float* d_mean, float* d_logstd, int n, int A, float inv_global,
                            float inv_local, float clip_para, float entropy_coeff, float* info,
-                           const int32_t* slot, int target_indexed) {
+                           const int32_t* slot, int target_indexed, void* d_mean_f16, float scale_f16) {
   V4L_REQUIRE(ctx && mean && logstd && target_mean && target_logstd && acts && adv && adv_stats &&
               d_mean && d_logstd && info, "v4l_pf_loss: NULL argument");
   V4L_REQUIRE(n > 0 && A > 0 && A <= MAX_A, "v4l_pf_loss: bad shape n=%d A=%d (A <= %d)", n, A, MAX_A);
   cudaStream_t s = (cudaStream_t)stream;
   const int ctas = min(v4l_cdiv(n, LOSS_THREADS), 2 * ctx->sm_count);
   double* part = reinterpret_cast<double*>(ctx->scratch);
+  V4L_REQUIRE(!d_mean_f16 || A <= 16, "v4l_pf_loss: the fp16 gradient row holds 16 columns (A = %d)", A);
   V4L_LAUNCH(pf_loss_kernel, ctas, LOSS_THREADS, 0, s, mean, logstd, target_mean, target_logstd, acts, adv, idx,
-                                               adv_stats, d_mean, n, A, inv_global, clip_para, part,
-                                               (target_indexed && idx) ? 1 : 0);
-  V4L_CHECK_LAUNCH();
-  V4L_LAUNCH(pf_loss_finalize_kernel, 1, 32, 0, s, part, ctas, logstd, adv_stats, d_logstd, n, A, inv_local,
-                                           entropy_coeff, info, slot);
+             adv_stats, d_mean, reinterpret_cast<__half*>(d_mean_f16), scale_f16, n, A, inv_global, inv_local,
+             clip_para, entropy_coeff, part, (target_indexed && idx) ? 1 : 0, d_logstd, ctx->counters + 1, info, slot);
   V4L_CHECK_LAUNCH();
   return 0;
 }

@@ -1,0 +1,373 @@
+// Minibatch prologue and the fused optimiser tail of the tensor-core tier.
+//
+// One PPO minibatch (reference torchrl/algo/on_policy/ppo.py:125-153) is a strictly serial chain:
+// critic forward -> loss -> backward -> clip + Adam -> actor forward (on the encoder the critic just
+// stepped) -> loss -> backward -> clip + Adam.  At the benchmark's minibatch of 1024 the step is bound
+// by the LENGTH of that chain, so the small HBM/latency-bound links are merged:
+//
+//   v4l_mb_begin   row-index selection + advantage statistics + proprio rows -> fp16 (was 3 launches)
+//   v4l_opt_tail   split-K reduction of the weight-gradient partials -> squared norm -> global-norm
+//                  clip + Adam -> fp16 re-pack of the weights the NEXT forward reads -> slot advance
+//                  (was 5-6 launches); phases are separated by a device-wide barrier.
+//
+// The device-wide barrier needs all CTAs of the grid co-resident: the grid is one CTA per SM, the
+// kernel uses no dynamic shared memory and <= 64 registers, so a CTA always finds a slot as soon as
+// concurrently running kernels (which never depend on this one) drain.
+#include <cuda_fp16.h>
+#include <float.h>
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace {
+
+template <typename T, typename Op>
+__device__ __forceinline__ T block_reduce_t(T v, Op op, T ident, T* sh /* [32] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? sh[threadIdx.x] : ident;
+  if (warp == 0) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) sh[0] = v;
+  }
+  __syncthreads();
+  v = sh[0];
+  return v;
+}
+struct AddD { __device__ double operator()(double a, double b) const { return a + b; } };
+struct MaxF { __device__ float operator()(float a, float b) const { return fmaxf(a, b); } };
+struct MinF { __device__ float operator()(float a, float b) const { return fminf(a, b); } };
+
+// =================================================================================================
+// minibatch prologue
+// =================================================================================================
+constexpr int MB_THREADS = 256;
+
+__global__ void __launch_bounds__(MB_THREADS)
+mb_begin_kernel(const int32_t* __restrict__ flat_idx, const int32_t* __restrict__ slot, int32_t* __restrict__ cur,
+                int n, const float* __restrict__ adv, double* __restrict__ stats, double* part,
+                unsigned int* counter, const float* __restrict__ state, int S, __half* __restrict__ st16, int Sp) {
+  v4l_pdl_enter();
+  __shared__ double shd[32];
+  __shared__ float shf[32];
+  __shared__ bool s_last;
+  const long long base = (long long)(*slot) * n;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+  // (1) this minibatch's row list (reference replay_buffers/on_policy.py:76-89) + advantage partials
+  double s = 0.0, s2 = 0.0;
+  float mx = -FLT_MAX, mn = FLT_MAX;
+  for (int i = gtid; i < n; i += gsz) {
+    const int r = flat_idx[base + i];
+    cur[i] = r;
+    const float a = adv[r];
+    s += a; s2 += (double)a * a;
+    mx = fmaxf(mx, a); mn = fminf(mn, a);
+  }
+  // (2) proprio rows -> fp16, zero padded to Sp columns (the first Linear's K is a multiple of 64)
+  if (st16) {
+    const long long total = (long long)n * Sp;
+    for (long long e = gtid; e < total; e += gsz) {
+      const int r = (int)(e / Sp), c = (int)(e - (long long)r * Sp);
+      float v = 0.f;
+      if (c < S) v = state[(long long)flat_idx[base + r] * S + c];
+      st16[e] = __float2half(v);
+    }
+  }
+  // (3) advantage statistics {sum, sumsq, n, max, min}: per-CTA partials, summed in CTA order by the
+  //     last CTA to arrive (deterministic)
+  s = block_reduce_t(s, AddD(), 0.0, shd);
+  s2 = block_reduce_t(s2, AddD(), 0.0, shd);
+  mx = block_reduce_t(mx, MaxF(), -FLT_MAX, shf);
+  mn = block_reduce_t(mn, MinF(), FLT_MAX, shf);
+  if (threadIdx.x == 0) {
+    double* p = part + 4 * blockIdx.x;
+    p[0] = s; p[1] = s2; p[2] = mx; p[3] = mn;
+    __threadfence();
+    const unsigned int t = atomicAdd(counter, 1u);
+    s_last = (t == gridDim.x - 1);
+    if (s_last) *counter = 0u;
+  }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  const volatile double* pv = part;
+  double S1 = 0.0, S2 = 0.0;
+  float MX = -FLT_MAX, MN = FLT_MAX;
+  for (int b = 0; b < (int)gridDim.x; ++b) {
+    S1 += pv[4 * b]; S2 += pv[4 * b + 1];
+    MX = fmaxf(MX, (float)pv[4 * b + 2]); MN = fminf(MN, (float)pv[4 * b + 3]);
+  }
+  stats[0] = S1; stats[1] = S2; stats[2] = (double)n; stats[3] = MX; stats[4] = MN;
+}
+
+// =================================================================================================
+// fused optimiser tail
+// =================================================================================================
+constexpr int TAIL_THREADS = 512;
+
+struct TailParams {
+  v4l_reduce_job jobs[V4L_MAX_JOBS];
+  int job_first[V4L_MAX_JOBS + 1];   // prefix sums of lane-items (outputs x lanes) per job
+  int job_lanes_log2[V4L_MAX_JOBS];  // log2 of the lanes that share one output's split sum
+  int n_jobs;
+  int phases;                        // bit 0: reduce, bit 1: norm + clip + Adam, bit 2: re-pack + finish
+  float* p; float* g; float* m; float* v; long long n;
+  float* hyper;                      // {lr, b1, b2, eps, max_norm, step, ...}
+  float* info; const int32_t* slot; int norm_slot;
+  const float* pack_src; const int32_t* pack_table; __half* packed; long long n_pack;
+  int32_t* slot_advance;             // optional: minibatch slot counter to increment at the very end
+  double* part;                      // [gridDim.x] squared-norm partials
+  unsigned int* bar;                 // [2] barrier arrival counter, exit counter
+  unsigned int* err;                 // set to 1 if the barrier timed out
+};
+
+// Device-wide barrier (all CTAs co-resident).  `bar[0]` counts arrivals monotonically within the launch;
+// the kernel's last act is an exit count whose last arriver re-arms both words for the next launch.
+__device__ __forceinline__ void grid_barrier(const TailParams& P, unsigned int& generation) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(P.bar, 1u);
+    const unsigned int target = (generation + 1) * gridDim.x;
+    unsigned int spins = 0;
+    while (*reinterpret_cast<volatile unsigned int*>(P.bar) < target) {
+      if (++spins > (1u << 27)) { *P.err = 1u; break; }     // never hang the GPU on a logic error
+    }
+    __threadfence();
+  }
+  ++generation;
+  __syncthreads();
+}
+
+// dw[index[n*Kp + kp]] = scale * sum_split partial[split][kp / 128][n][kp % 128]  (+ bias rows), one
+// output per group of 2^lanes_log2 lanes: each lane sums a strided subset of the splits, then a fixed
+// shuffle tree combines them.  partial is kp-fastest, so reads AND (for Linear layers) writes coalesce.
+__device__ __forceinline__ void reduce_phase(const TailParams& P) {
+  const int total = P.job_first[P.n_jobs];
+  const int lane = threadIdx.x & 31;
+  for (int base = blockIdx.x * TAIL_THREADS; base < total; base += gridDim.x * TAIL_THREADS) {
+    const int item = base + threadIdx.x;
+    // the job of this item (items of one warp may straddle two jobs: lanes are masked, not the warp)
+    int j = 0;
+    bool live = item < total;
+    if (live) {
+      int lo = 0, hi = P.n_jobs;                // job_first[lo] <= item < job_first[hi]
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (P.job_first[mid] <= item) lo = mid; else hi = mid; }
+      j = lo;
+    }
+    const v4l_reduce_job& J = P.jobs[j];
+    const int ll = P.job_lanes_log2[j];
+    const int L = 1 << ll;
+    const int rel = live ? item - P.job_first[j] : 0;
+    const int o = rel >> ll, l = rel & (L - 1);
+    const long long n_w = (long long)J.N_valid * J.Kp;
+    live = live && o < n_w + (J.has_bias ? J.N_valid : 0);      // a job's items are padded to whole warps
+    const long long split_stride = (long long)(J.kin_tiles + J.has_bias) * 128 * J.Nmma;
+    const float* src;
+    long long dst = -1;
+    float* out = J.dw;
+    if (o < n_w) {
+      const int n = o / J.Kp, kp = o - n * J.Kp;
+      src = J.partial + ((long long)(kp >> 7) * J.Nmma + n) * 128 + (kp & 127);
+      dst = J.index ? (long long)J.index[o] : (long long)o;
+    } else {                                    // bias gradient: K slice `kin_tiles`, lane 0
+      const int n = (int)(o - n_w);
+      src = J.partial + ((long long)J.kin_tiles * J.Nmma + n) * 128;
+      dst = n; out = J.dbias;
+    }
+    float s = 0.f;
+    if (live) {
+      int z = l;
+      for (; z + 3 * L < J.splits; z += 4 * L) {
+        const float a0 = src[(long long)z * split_stride], a1 = src[(long long)(z + L) * split_stride];
+        const float a2 = src[(long long)(z + 2 * L) * split_stride], a3 = src[(long long)(z + 3 * L) * split_stride];
+        s += a0; s += a1; s += a2; s += a3;
+      }
+      for (; z < J.splits; z += L) s += src[(long long)z * split_stride];
+    }
+    // combine the L lanes of an output (L <= 32 divides the warp; same tree for every output)
+    for (int off = 1; off < L; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (live && l == 0 && dst >= 0) {
+      const float r = s * J.scale;
+      out[dst] = J.accumulate ? out[dst] + r : r;
+    }
+  }
+  (void)lane;
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1) opt_tail_kernel(const __grid_constant__ TailParams P) {
+  v4l_pdl_enter();
+  __shared__ double shd[32];
+  __shared__ float s_coef;
+  unsigned int generation = 0;
+  const long long gtid = blockIdx.x * (long long)TAIL_THREADS + threadIdx.x;
+  const long long gsz = (long long)gridDim.x * TAIL_THREADS;
+
+  if (P.phases & 1) reduce_phase(P);
+  if (P.phases & 2) {
+    if (P.phases & 1) grid_barrier(P, generation);
+    // ---- squared norm of the whole gradient bucket (clip_grad_norm_, reference ppo.py:73-74,118-119)
+    double s = 0.0;
+    for (long long i = gtid; i < P.n; i += gsz) { const double x = __ldcg(P.g + i); s += x * x; }
+    s = block_reduce_t(s, AddD(), 0.0, shd);
+    if (threadIdx.x == 0) P.part[blockIdx.x] = s;
+    grid_barrier(P, generation);
+    // ---- every CTA derives the same clip factor from the partials, summed in the same order
+    if (threadIdx.x < 32) {
+      const volatile double* pv = P.part;
+      double t = 0.0;
+      for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) t += pv[i];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (threadIdx.x == 0) {
+        const float total = (float)sqrt(t);
+        s_coef = isfinite(total) ? fminf(P.hyper[4] / (total + 1e-6f), 1.f) : -1.f;
+        if (blockIdx.x == 0 && P.info && P.norm_slot >= 0)
+          P.info[(long long)(P.slot ? *P.slot : 0) * V4L_INFO_STRIDE + P.norm_slot] = total;
+      }
+    }
+    __syncthreads();
+    const float coef = s_coef;
+    if (coef >= 0.f) {                       // a non-finite norm skips the step (moments stay clean)
+      const float lr = P.hyper[0], b1 = P.hyper[1], b2 = P.hyper[2], eps = P.hyper[3];
+      const float step = P.hyper[5] + 1.f;
+      const float bc1 = 1.f - powf(b1, step);
+      const float bc2_sqrt = sqrtf(1.f - powf(b2, step));
+      const float step_size = lr / bc1;
+      const long long n4 = P.n >> 2;         // buckets are 16-byte aligned and padded to 4 floats
+      for (long long i = gtid; i < n4; i += gsz) {
+        const float4 g4 = __ldcg(reinterpret_cast<const float4*>(P.g) + i);
+        float4 m4 = reinterpret_cast<float4*>(P.m)[i], v4 = reinterpret_cast<float4*>(P.v)[i];
+        float4 p4 = reinterpret_cast<float4*>(P.p)[i];
+        float* gm = reinterpret_cast<float*>(&m4); float* gv = reinterpret_cast<float*>(&v4);
+        float* gp = reinterpret_cast<float*>(&p4);
+        const float* gg = reinterpret_cast<const float*>(&g4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float gi = gg[q] * coef;
+          const float mi = b1 * gm[q] + (1.f - b1) * gi;
+          const float vi = b2 * gv[q] + (1.f - b2) * gi * gi;
+          gm[q] = mi; gv[q] = vi;
+          const float denom = sqrtf(vi) / bc2_sqrt + eps;
+          gp[q] -= step_size * (mi / denom);
+        }
+        reinterpret_cast<float4*>(P.m)[i] = m4; reinterpret_cast<float4*>(P.v)[i] = v4;
+        reinterpret_cast<float4*>(P.p)[i] = p4;
+      }
+      for (long long i = (n4 << 2) + gtid; i < P.n; i += gsz) {
+        const float gi = __ldcg(P.g + i) * coef;
+        const float mi = b1 * P.m[i] + (1.f - b1) * gi;
+        const float vi = b2 * P.v[i] + (1.f - b2) * gi * gi;
+        P.m[i] = mi; P.v[i] = vi;
+        P.p[i] -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+      }
+    }
+  }
+  if (P.phases & 4) {
+    if (P.phases & 3) grid_barrier(P, generation);
+    // ---- the step counter moves only after every CTA has used it (barrier above)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      if ((P.phases & 2) && s_coef >= 0.f) P.hyper[5] += 1.f;
+      if (P.slot_advance) *P.slot_advance += 1;
+    }
+    // ---- fp16 re-pack (tap-major, forward + data-gradient orientations) of the weights the next
+    //      forward pass reads; the bucket was just updated by all CTAs
+    if (P.packed)
+      for (long long i = gtid; i < P.n_pack; i += gsz) {
+        const int sidx = P.pack_table[i];
+        P.packed[i] = __float2half(sidx >= 0 ? __ldcg(P.pack_src + sidx) : 0.f);
+      }
+  }
+  // ---- re-arm the barrier words for the next launch
+  if (generation > 0) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int t = atomicAdd(P.bar + 1, 1u);
+      if (t == gridDim.x - 1) { P.bar[0] = 0u; P.bar[1] = 0u; __threadfence(); }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int v4l_mb_begin(v4l_ctx* ctx, void* stream, const int32_t* flat_idx, const int32_t* slot,
+                            int32_t* cur_idx, int n, const float* adv, double* stats, const float* state,
+                            int S, void* state_f16, int Sp) {
+  V4L_REQUIRE(ctx && flat_idx && slot && cur_idx && adv && stats && n > 0, "v4l_mb_begin: bad argument");
+  V4L_REQUIRE(!state_f16 || (S >= 0 && Sp >= S && (S == 0 || state)), "v4l_mb_begin: bad proprio arguments");
+  const long long work = max((long long)n, state_f16 ? (long long)n * Sp / 8 : 0LL);
+  const int ctas = max(1, min(ctx->sm_count, v4l_cdiv(work, MB_THREADS)));
+  double* part = reinterpret_cast<double*>(ctx->scratch);
+  V4L_LAUNCH(mb_begin_kernel, ctas, MB_THREADS, 0, (cudaStream_t)stream, flat_idx, slot, cur_idx, n, adv, stats, part,
+             ctx->counters + 2, state, S, reinterpret_cast<__half*>(state_f16), Sp);
+  V4L_CHECK_LAUNCH();
+  return 0;
+}
+
+// lanes sharing one output's split sum: ~<= 8 splits per lane
+static int lanes_log2_for(int splits) {
+  int ll = 0;
+  while ((1 << ll) < 32 && (splits >> ll) > 8) ++ll;
+  return ll;
+}
+
+extern "C" int v4l_opt_tail(v4l_ctx* ctx, void* stream, const v4l_opt_tail_args* a) {
+  V4L_REQUIRE(ctx && a, "v4l_opt_tail: NULL argument");
+  const int phases = a->phases;
+  V4L_REQUIRE(phases > 0 && phases < 8, "v4l_opt_tail: bad phases %d", phases);
+  V4L_REQUIRE(!(phases & 2) || (a->param && a->grad && a->m && a->v && a->hyper && a->n > 0),
+              "v4l_opt_tail: the optimiser phase needs param/grad/m/v/hyper");
+  V4L_REQUIRE(!(phases & 2) || ((((uintptr_t)a->param | (uintptr_t)a->grad | (uintptr_t)a->m | (uintptr_t)a->v) & 15) == 0),
+              "v4l_opt_tail: buckets must be 16-byte aligned");
+  V4L_REQUIRE(a->norm_slot < V4L_INFO_STRIDE, "v4l_opt_tail: bad norm_slot");
+  V4L_REQUIRE(!a->packed || (a->pack_src && a->pack_table && a->n_pack > 0), "v4l_opt_tail: bad pack arguments");
+  static TailParams P;               // large: keep it off the stack (single host thread per context)
+  memset(&P, 0, sizeof(P));
+  int total = 0;
+  if (phases & 1) {
+    for (int i = 0; i < ctx->n_jobs; ++i) {
+      const v4l_reduce_job& J = ctx->jobs[i];
+      P.jobs[i] = J;
+      P.job_first[i] = total;
+      const int ll = lanes_log2_for(J.splits);
+      P.job_lanes_log2[i] = ll;
+      const long long outs = (long long)J.N_valid * J.Kp + (J.has_bias ? J.N_valid : 0);
+      V4L_REQUIRE(((outs << ll) + total + 32) < (1LL << 31), "v4l_opt_tail: too many reduction items");
+      total += (int)((((outs << ll) + 31) >> 5) << 5);     // whole warps per job: a warp never straddles two jobs
+    }
+    P.n_jobs = ctx->n_jobs;
+    P.job_first[P.n_jobs] = total;
+    ctx->n_jobs = 0;
+    ctx->defer_cursor = 0;
+  }
+  P.phases = phases;
+  P.p = a->param; P.g = a->grad; P.m = a->m; P.v = a->v; P.n = a->n;
+  P.hyper = a->hyper; P.info = a->info; P.slot = a->slot; P.norm_slot = a->norm_slot;
+  P.pack_src = a->pack_src; P.pack_table = a->pack_table; P.packed = reinterpret_cast<__half*>(a->packed);
+  P.n_pack = a->n_pack;
+  P.slot_advance = a->slot_advance;
+  P.part = reinterpret_cast<double*>(ctx->scratch);
+  P.bar = ctx->counters + 4;
+  P.err = ctx->counters + 6;
+  // one CTA per SM when a barrier is needed (co-residency); a pure reduction may use more
+  const bool needs_barrier = (phases & (phases - 1)) != 0;
+  int grid = ctx->sm_count;
+  if (!needs_barrier && phases == 1) grid = max(1, min(4 * ctx->sm_count, v4l_cdiv(total, TAIL_THREADS)));
+  V4L_LAUNCH(opt_tail_kernel, grid, TAIL_THREADS, 0, (cudaStream_t)stream, P);
+  V4L_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int v4l_opt_tail_error(v4l_ctx* ctx) {
+  V4L_REQUIRE(ctx, "v4l_opt_tail_error: NULL ctx");
+  unsigned int e = 0;
+  V4L_CHECK_CUDA(cudaMemcpy(&e, ctx->counters + 6, sizeof(e), cudaMemcpyDeviceToHost));
+  return (int)e;
+}

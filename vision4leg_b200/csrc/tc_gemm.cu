@@ -548,7 +548,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
   } else {
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
-    float* out = p.partial + ((static_cast<long long>(split) * gridDim.y + kt) * 128 + r) * Nmma;
+    // partial[split][kt][n][r]: the packed-K lane r is the fastest index, so a warp writes 128 contiguous
+    // bytes per column and the reduction reads / scatters along kp (contiguous in the reference layout
+    // of Linear weights)
+    float* out = p.partial + (static_cast<long long>(split) * gridDim.y + kt) * 128 * Nmma + r;
     if (tile_hi > tile_lo) {
       tc::mbar_wait(&tmem_full, 0);
       tc::tc_fence_after();
@@ -558,11 +561,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
         tc::tmem_ld_32x32(taddr + c0, v);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<uint4*>(out + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        for (int j = 0; j < 32; ++j) out[(c0 + j) * 128] = __uint_as_float(v[j]);
       }
     } else {
-      for (int c = 0; c < Nmma; c += 4) *reinterpret_cast<uint4*>(out + c) = make_uint4(0, 0, 0, 0);
+      for (int c = 0; c < Nmma; ++c) out[c * 128] = 0.f;
     }
     tc::tc_fence_before();
   }
@@ -573,63 +575,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
   }
 }
 
-// All pending reductions in ONE launch (blockIdx.y = job): dw[index[n*Kp + kp]] = scale * sum_split
-// partial[split][kp/128][kp%128][n]; dbias[n] = scale * sum_split partial[split][kin_tiles][0][n]
-struct ReduceJobs { v4l_reduce_job j[V4L_MAX_JOBS]; };
-
-// fixed-order sum over the split-K partials with 8 loads in flight (the adds stay sequential: the
-// result does not depend on the unrolling)
-__device__ __forceinline__ float sum_splits(const float* __restrict__ src, int splits, long long stride) {
-  float s = 0.f;
-  int z = 0;
-  for (; z + 8 <= splits; z += 8) {
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = src[(z + j) * stride];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s += v[j];
-  }
-  for (; z < splits; ++z) s += src[z * stride];
-  return s;
-}
-
-__global__ void __launch_bounds__(256) tc_wgrad_reduce_kernel(const __grid_constant__ ReduceJobs jobs) {
-  // partial[split][kp][n] (n contiguous) -> dw[index[n][kp]] (kp contiguous).  One output per thread and
-  // tile (8 kp x 32 n): the split loop is a chain of dependent-latency loads, so short chains on many
-  // blocks beat long chains on few; the tile goes through shared memory so that the split-sum reads are
-  // coalesced along n and the scattered writes run along kp.
-  v4l_pdl_enter();
-  __shared__ float tile[8][33];
-  const v4l_reduce_job& J = jobs.j[blockIdx.y];
-  const long long split_stride = (long long)(J.kin_tiles + J.has_bias) * 128 * J.Nmma;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int wk = threadIdx.x & 7, wn = threadIdx.x >> 3;
-  const int tk = (J.Kp + 7) >> 3, tn = (J.N_valid + 31) >> 5;
-  for (int t = blockIdx.x; t < tk * tn; t += gridDim.x) {
-    const int kp0 = (t % tk) << 3, n0 = (t / tk) << 5;
-    {
-      const int kp = kp0 + ty, n = n0 + tx;
-      float s = 0.f;
-      if (kp < J.Kp && n < J.N_valid) s = sum_splits(J.partial + (long long)kp * J.Nmma + n, J.splits, split_stride);
-      tile[ty][tx] = s;
-    }
-    __syncthreads();
-    {
-      const int n = n0 + wn, kp = kp0 + wk;
-      if (kp < J.Kp && n < J.N_valid) {
-        const long long e = (long long)n * J.Kp + kp;
-        const long long d = J.index ? (long long)J.index[e] : e;
-        if (d >= 0) J.dw[d] = tile[wk][wn] * J.scale;
-      }
-    }
-    __syncthreads();
-  }
-  if (J.has_bias && blockIdx.x == gridDim.x - 1) {
-    const float* src0 = J.partial + (long long)J.kin_tiles * 128 * J.Nmma;
-    for (int n = threadIdx.x; n < J.N_valid; n += blockDim.x)
-      J.dbias[n] = sum_splits(src0 + n, J.splits, split_stride) * J.scale;
-  }
-}
+// The split-K reduction of these partials lives in step_ops.cu (opt_tail_kernel, phase 1): on its own
+// (v4l_tc_wgrad_flush) or fused with clip + Adam + weight re-pack (v4l_opt_tail).
 
 // column sums of a row-mapped f16 [M, N] matrix (bias gradients), two deterministic stages
 __global__ void __launch_bounds__(256) colsum_f16_kernel(const __half* __restrict__ dy,
@@ -766,32 +713,35 @@ extern "C" int v4l_tc_wgrad(v4l_ctx* ctx, void* stream, const v4l_tc_wgrad_args*
   v4l_reduce_job job;
   job.partial = region; job.index = a->index; job.dw = a->dw; job.dbias = a->dbias;
   job.splits = splits; job.kin_tiles = kin_tiles; job.has_bias = has_bias; job.Nmma = Nmma;
-  job.N_valid = a->N_valid; job.Kp = Kp; job.scale = a->out_scale != 0.f ? a->out_scale : 1.f; job.pad_ = 0;
+  job.N_valid = a->N_valid; job.Kp = Kp; job.scale = a->out_scale != 0.f ? a->out_scale : 1.f;
+  job.accumulate = a->accumulate ? 1 : 0;
   if (a->defer) {
     ctx->jobs[ctx->n_jobs++] = job;
     ctx->defer_cursor += (((size_t)splits * ytiles * 128 * Nmma) + 63) / 64 * 64;
     return 0;
   }
-  ReduceJobs one;
-  one.j[0] = job;
-  const long long total = (long long)a->N_valid * (Kp + has_bias);
-  const int rblocks = (int)min((long long)2 * ctx->sm_count, (total + 255) / 256);
-  V4L_LAUNCH(tc_wgrad_reduce_kernel, dim3(rblocks, 1), 256, 0, s, one);
-  V4L_CHECK_LAUNCH();
-  return 0;
+  // immediate reduction: the pending deferred jobs (if any) are set aside around the one-job pass
+  v4l_reduce_job saved[V4L_MAX_JOBS];
+  const int n_saved = ctx->n_jobs;
+  const size_t cursor = ctx->defer_cursor;
+  for (int i = 0; i < n_saved; ++i) saved[i] = ctx->jobs[i];
+  ctx->jobs[0] = job; ctx->n_jobs = 1;
+  const int rc = v4l_tc_wgrad_flush(ctx, stream);
+  for (int i = 0; i < n_saved; ++i) ctx->jobs[i] = saved[i];
+  ctx->n_jobs = n_saved; ctx->defer_cursor = cursor;
+  return rc;
 }
 
+// split-K reduction of every pending (deferred) weight-gradient job in one launch: phase 1 of the
+// optimiser tail kernel (step_ops.cu) on its own
 extern "C" int v4l_tc_wgrad_flush(v4l_ctx* ctx, void* stream) {
   V4L_REQUIRE(ctx, "v4l_tc_wgrad_flush: NULL ctx");
   if (ctx->n_jobs == 0) return 0;
-  ReduceJobs all;
-  memset(&all, 0, sizeof(all));
-  for (int i = 0; i < ctx->n_jobs; ++i) all.j[i] = ctx->jobs[i];
-  V4L_LAUNCH(tc_wgrad_reduce_kernel, dim3(64, ctx->n_jobs), 256, 0, (cudaStream_t)stream, all);
-  ctx->n_jobs = 0;
-  ctx->defer_cursor = 0;
-  V4L_CHECK_LAUNCH();
-  return 0;
+  v4l_opt_tail_args t;
+  memset(&t, 0, sizeof(t));
+  t.phases = 1;
+  t.norm_slot = -1;
+  return v4l_opt_tail(ctx, stream, &t);
 }
 
 extern "C" int v4l_colsum_f16(v4l_ctx* ctx, void* stream, const void* dy, const v4l_rowmap* map, int M, int N,

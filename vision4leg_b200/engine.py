@@ -352,19 +352,43 @@ class Ops:
     self.launches += 1
 
   def vf_loss(self, values, returns, old_values, idx, d_values, n, inv_global, inv_local, clipped,
-              clip_para, info, slot):
+              clip_para, info, slot, d_f16=None, scale_f16=1.0):
+    """one launch: loss, gradient (fp32 and, optionally, loss-scaled fp16 [n,16]) and the logged value"""
     check(self.lib.v4l_vf_loss(self.h, self.ctx.stream(), ptr(values), ptr(returns), ptr(old_values),
                                ptr(idx), ptr(d_values), n, inv_global, inv_local, 1 if clipped else 0,
-                               clip_para, ptr(info), ptr(slot)))
-    self.launches += 2
+                               clip_para, ptr(info), ptr(slot), ptr(d_f16), scale_f16))
+    self.launches += 1
 
   def pf_loss(self, mean, logstd, tmean, tlogstd, acts, adv, idx, stats, d_mean, d_logstd, n, A,
-              inv_global, inv_local, clip_para, entropy_coeff, info, slot, target_indexed=False):
+              inv_global, inv_local, clip_para, entropy_coeff, info, slot, target_indexed=False,
+              d_f16=None, scale_f16=1.0):
     check(self.lib.v4l_pf_loss(self.h, self.ctx.stream(), ptr(mean), ptr(logstd), ptr(tmean),
                                ptr(tlogstd), ptr(acts), ptr(adv), ptr(idx), ptr(stats), ptr(d_mean),
                                ptr(d_logstd), n, A, inv_global, inv_local, clip_para, entropy_coeff,
-                               ptr(info), ptr(slot), 1 if target_indexed else 0))
-    self.launches += 2
+                               ptr(info), ptr(slot), 1 if target_indexed else 0, ptr(d_f16), scale_f16))
+    self.launches += 1
+
+  def mb_begin(self, flat_idx, slot, cur_idx, n, adv, stats, state=None, S=0, state_f16=None, Sp=0):
+    """minibatch prologue: row selection + advantage statistics (+ proprio rows -> fp16), one launch"""
+    check(self.lib.v4l_mb_begin(self.h, self.ctx.stream(), ptr(flat_idx), ptr(slot), ptr(cur_idx), n, ptr(adv),
+                                ptr(stats), ptr(state), S, ptr(state_f16), Sp))
+    self.launches += 1
+
+  def opt_tail(self, phases, param=None, grad=None, m=None, v=None, n=0, hyper=None, info=None, slot=None,
+               norm_slot=-1, pack_src=None, pack_table=None, packed=None, n_pack=0, slot_advance=None):
+    """fused optimiser tail (v4l_opt_tail): phases bit 0 = split-K reduction of the deferred weight-
+    gradient partials, bit 1 = clip + Adam, bit 2 = fp16 re-pack + step / slot counters"""
+    a = _lib.OptTailArgs()
+    a.phases = phases
+    a.param, a.grad, a.m, a.v, a.n = ptr(param), ptr(grad), ptr(m), ptr(v), n
+    a.hyper, a.info, a.slot, a.norm_slot = ptr(hyper), ptr(info), ptr(slot), norm_slot
+    a.pack_src, a.pack_table, a.packed, a.n_pack = ptr(pack_src), ptr(pack_table), ptr(packed), n_pack
+    a.slot_advance = ptr(slot_advance)
+    check(self.lib.v4l_opt_tail(self.h, self.ctx.stream(), C.byref(a)))
+    self.launches += 1
+
+  def opt_tail_error(self):
+    return self.lib.v4l_opt_tail_error(self.h)
 
   def clip_adam(self, param, grad, m, v, n, hyper, info, slot, norm_slot):
     check(self.lib.v4l_clip_adam(self.h, self.ctx.stream(), ptr(param), ptr(grad), ptr(m), ptr(v), n,

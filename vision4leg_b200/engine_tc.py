@@ -137,6 +137,7 @@ class _PlanTC:
     self.layout = layout
     self.W = TcWeights(ops, layout, with_dgrad=with_backward)
     self._ws = {}
+    self.world = 1                    # data-parallel world size (loss scale, see _begin_backward)
     self._rr, self._forked = 0, set()
     self.k_base = [k for k in layout if k.startswith("encoder.base.seq_fcs.") and k.endswith("weight")]
     self.k_head = sorted((k for k in layout if k.startswith(head_prefix) and k.endswith("weight")),
@@ -261,16 +262,27 @@ class _PlanTC:
       self.W.fwd[pre + "0.weight"].dev_table, gflat, x_idx=self._idx, x_estride=2, subs=subs, out_scale=inv,
       dbias=self._view(gflat, pre + "0.bias"), defer=True))
 
-  def _begin_backward(self, d_out, B):
-    """fp32 d_out [B, out_dim] -> loss-scaled fp16 [B,16].  Static loss scale: d_out ~ 1/B, so
-    scale ~ 4B keeps fp16 gradients O(1e2); every fp32 result (dW, db, dgamma, dbeta) is multiplied
-    by 1/scale where it is produced."""
-    scale = float(min(4096, max(64, 1 << int(np.floor(np.log2(4 * B))))))
+  def loss_scale(self, B):
+    """Static loss scale of the fp16 backward: d_out ~ 1/B_global, so scale ~ 4 B_global keeps fp16
+    gradients O(1e2); every fp32 result (dW, db, dgamma, dbeta) is multiplied by 1/scale where it is
+    produced.  Data parallel: d_out carries 1 / (B * world), so the scale follows the GLOBAL minibatch."""
     if LOSS_SCALE_OVERRIDE:
-      scale = float(LOSS_SCALE_OVERRIDE)
+      return float(LOSS_SCALE_OVERRIDE)
+    scale = float(min(32768, max(64, 1 << int(np.floor(np.log2(4 * B * self.world))))))
+    return min(scale, 4096.0) if self.world == 1 else scale
+
+  def grad_in(self, B):
+    """fp16 [B,16] buffer the backward starts from; the loss kernels write it directly
+    (scale_f16 = loss_scale(B)), see backward(..., d_out=None)"""
+    return self.buf("dout16", (B, 16))
+
+  def _begin_backward(self, d_out, B):
+    """fp32 d_out [B, out_dim] -> loss-scaled fp16 [B,16] (d_out None: grad_in(B) was already written)"""
+    scale = self.loss_scale(B)
     self._inv_scale = 1.0 / scale
-    g16 = self.buf("dout16", (B, 16))
-    self.ops.gather_rows_f16(d_out, True, None, g16, B, self.out_dim, self.out_dim, 16, scale=scale)
+    g16 = self.grad_in(B)
+    if d_out is not None:
+      self.ops.gather_rows_f16(d_out, True, None, g16, B, self.out_dim, self.out_dim, 16, scale=scale)
     return g16
 
 
@@ -384,9 +396,10 @@ class LocoPlanTC(_PlanTC):
         gflat, out_scale=inv, dbias=self._view(gflat, p + norm + ".bias"), defer=True))
     return g["dx"]
 
-  def backward(self, gflat, d_out):
-    """d_out fp32 [B,out_dim]; writes every weight/bias/LayerNorm gradient (fp32) into gflat at
-    the layout offsets."""
+  def backward(self, gflat, d_out, flush=True):
+    """d_out fp32 [B,out_dim] (None: the loss kernel already wrote grad_in(B)); writes every
+    weight/bias/LayerNorm gradient (fp32) into gflat at the layout offsets.  flush=False leaves the
+    split-K partials pending for the fused optimiser tail (v4l_opt_tail)."""
     ops, T, d, B, flat = self.ops, self.T, self.d, self._B, self._flat
     R = B * T
     A = self.out_dim
@@ -451,7 +464,8 @@ class LocoPlanTC(_PlanTC):
                 RM(16, 16 * 64, 64, 0), mask=a3, a_strides=strides, a_off=d)
     self._trunk_bwd(gflat, da3, B, "encoder.depth_visual_base.layers.")
     self._join_all()
-    ops.tc_wgrad_flush()
+    if flush:
+      ops.tc_wgrad_flush()
 
 
 class NaturePlanTC(_PlanTC):
@@ -480,7 +494,7 @@ class NaturePlanTC(_PlanTC):
     self._lin_fwd(flat, self.k_head[2], h2, B, 256, out, out_map or RM.dense(self.out_dim), False, c_f32=True)
     return out
 
-  def backward(self, gflat, d_out):
+  def backward(self, gflat, d_out, flush=True):
     ops, B, ws = self.ops, self._B, self._ws
     W = self.vd + self.sd
     g16 = self._begin_backward(d_out, B)
@@ -498,7 +512,8 @@ class NaturePlanTC(_PlanTC):
     self._lin_bwd(gflat, self.k_proj, a3, 1024, dcat, self.vd, B, da3, RM.dense(1024), mask=a3, dy_pitch=W, dy_off=0)
     self._trunk_bwd(gflat, da3, B, "encoder.visual_base.layers.")
     self._join_all()
-    ops.tc_wgrad_flush()
+    if flush:
+      ops.tc_wgrad_flush()
 
 
 PLANS = {"loco": LocoPlanTC, "nature": NaturePlanTC}
