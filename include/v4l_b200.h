@@ -304,22 +304,36 @@ typedef struct {
 } v4l_tc_wgrad_args;
 int v4l_tc_wgrad(v4l_ctx* ctx, void* stream, const v4l_tc_wgrad_args* args);
 int v4l_tc_wgrad_flush(v4l_ctx* ctx, void* stream);
+/* Weight + bias gradient of the first NatureCNN convolution (Conv2d(4,32,8,stride 4), reference
+ * torchrl/networks/base.py:317-318) on the space-to-depth layouts: x_s2d f16 [n_img,16,16,64] (v4l_ingest_img),
+ * dy_cells f16 [B,8,8,128] (gradient of conv1's output stored as 2x2 cells, channel = (py*2+px)*32 + n).
+ * One CTA per image range; each pixel window and each dY cell is loaded once (csrc/tc_wgrad_s2d.cu).
+ * index / dw / dbias / out_scale / defer / accumulate as v4l_tc_wgrad (packed K = (dy*2+dx)*64 + c).   */
+int v4l_tc_wgrad_conv1(v4l_ctx* ctx, void* stream, const void* x_s2d, int64_t n_img, const int32_t* x_idx,
+                       const void* dy_cells, int B, const int32_t* index, float* dw, float* dbias,
+                       float out_scale, int defer, int accumulate);
 
 /* ---- fused optimiser tail of one network pass (tensor-core tier; csrc/step_ops.cu):
- * phase 1  split-K reduction of all deferred weight-gradient partials into the fp32 gradient bucket;
+ * phase 1  split-K reduction of all deferred weight-gradient partials into the fp32 gradient bucket
+ *          (accumulating the squared norm of what it writes);
  * phase 2  clip_grad_norm_(max_norm) + Adam over the flat bucket (same arithmetic as v4l_clip_adam,
- *          reference ppo.py:71-75,116-120; a2c.py:30-40), pre-clip norm into info[norm_slot];
- * phase 4  fp16 re-pack (v4l_pack_f16 semantics) of the weights the NEXT forward reads from the
- *          updated bucket, Adam step counter + optional minibatch slot advance.
- * `phases` is a bit mask; consecutive phases are separated by a device-wide barrier inside ONE
- * kernel (grid = one CTA per SM).  Data-parallel runs launch phase 1, all-reduce the bucket, then
- * launch phases 2|4.                                                                              */
+ *          reference ppo.py:71-75,116-120; a2c.py:30-40), pre-clip norm into info[norm_slot]; every
+ *          updated parameter i is also written, rounded to f16, at scatter[i] = (a, b, c, d): positions
+ *          a, b of packed_self and c, d of packed_other (-1 = none) — the tap-major operand copies
+ *          (v4l_pack_f16 layouts) of this network and, for shared-encoder weights, of the other one;
+ *          finally the Adam step counter and the optional minibatch slot advance.
+ * `phases` is a bit mask; 1|2 runs in ONE kernel (grid = one CTA per SM) with a device-wide barrier
+ * between the norm and the step.  Data-parallel runs launch phase 1, all-reduce the bucket, then
+ * launch phase 2 (which then reads the norm from the bucket).  extra_lo/extra_n: the range of the
+ * bucket that is NOT written by a reduction job (logstd) and must be added to the norm in 1|2.      */
 typedef struct {
   int32_t phases;
   float* param; float* grad; float* m; float* v; int64_t n;
   float* hyper;                 /* as v4l_clip_adam */
   float* info; const int32_t* slot; int32_t norm_slot;
-  const float* pack_src; const int32_t* pack_table; void* packed; int64_t n_pack;   /* or NULL */
+  int64_t extra_lo, extra_n;
+  const int32_t* scatter;       /* int32 [n][4] or NULL */
+  void* packed_self; void* packed_other;
   int32_t* slot_advance;        /* optional: incremented by 1 at the very end */
 } v4l_opt_tail_args;
 int v4l_opt_tail(v4l_ctx* ctx, void* stream, const v4l_opt_tail_args* args);

@@ -18,7 +18,9 @@ identical rollout tensors for the reduced-precision tier.  Three levels:
      sign-like (|dw| = lr whatever |g|), so a gradient component within the noise of 0 moves its weight by
      2 lr the other way.  This is a property of 16-bit STORAGE, not of these kernels:
      tools/probe_storage_rounding.py reproduces it on the CPU with the oracle's own fp32 arithmetic and
-     straight-through fp16 rounding of the stored tensors (bf16 storage drifts ~8x further).  Asserted here:
+     straight-through fp16 rounding of the stored tensors and drifts by the same amounts (policy_loss 10 %,
+     ratio extremes 9-10 %, grad_norm/pf 9 %, held-out means 5 % after 16 steps; profiles/r2_storage_drift.txt).
+     Asserted here:
      GAE at 1e-2, every statistic within FREE_RTOL of the fp32 trajectory, held-out outputs within
      FREE_RTOL_OUT (measured numbers are printed and kept in profiles/).
 
@@ -65,12 +67,13 @@ def _atol(k, ref, rtol):
   return 1e-4
 
 
-def info_errors(infos, refs, rtol=RTOL):
+def info_errors(infos, refs, rtol=RTOL, rtol_grad_norm=None):
   """[(minibatch, key, got, want, err / allowed)] with allowed = rtol*|want| + atol(key)"""
   rows = []
   for i, (a, b) in enumerate(zip(infos, refs)):
     for k in g.INFO_KEYS:
-      rows.append((i, k, float(a[k]), float(b[k]), abs(a[k] - b[k]) / (rtol * abs(b[k]) + _atol(k, b, rtol))))
+      rt = rtol_grad_norm if (rtol_grad_norm and k.startswith("grad_norm/")) else rtol
+      rows.append((i, k, float(a[k]), float(b[k]), abs(a[k] - b[k]) / (rt * abs(b[k]) + _atol(k, b, rt))))
   return rows
 
 
@@ -201,7 +204,11 @@ def test_tc_tier_epoch_teacher_forced(family):
   extra = dict(gae)
   _sync_from_oracle(agent, orc)
   extra.update(_heldout(agent, orc, S))
-  rows = info_errors(infos, refs)
+  # grad_norm/*: 3e-2.  The surrogate's gradient is discontinuous in the ratio (a sample whose ratio is within
+  # the 3e-3 forward error of 1 +- clip switches between "contributes" and "clipped"), so along the trajectory,
+  # where ~1 % of the 1024 samples sit that close to the boundary, the logged gradient NORM moves by ~1 %;
+  # on the first minibatch (ratio ~ 1, nothing near the boundary) it is within 1e-3 (step test above).
+  rows = info_errors(infos, refs, rtol_grad_norm=3e-2)
   _report("forced_" + family, rows, extra, RTOL)
   assert extra["gae/advs"] < RTOL and extra["gae/returns"] < RTOL
   bad = [(i, k, a, b, round(e, 2)) for i, k, a, b, e in rows if not e <= 1.0]

@@ -8,7 +8,7 @@ PPOOracle.update_per_epoch with that forward and comparing with the plain fp32 o
 16-bit STORAGE alone does to the trajectory (ReLU gates that flip for pre-activations within the rounding
 error of 0, amplified by Adam's sign-like first steps) from anything specific to the CUDA kernels.
 
-  python tools/probe_storage_rounding.py [f16|bf16] [B] [minibatches] [opt_epochs]
+  python tools/probe_storage_rounding.py [f16|bf16|eps1e-6] [B] [minibatches] [opt_epochs]
 """
 import math
 import os
@@ -23,10 +23,13 @@ from oracle import ppo_oracle as po, synth   # noqa: E402
 from tests import _golden as g   # noqa: E402
 
 MODE = sys.argv[1] if len(sys.argv) > 1 else "f16"
-DT = {"f16": torch.float16, "bf16": torch.bfloat16}[MODE]
+DT = {"f16": torch.float16, "bf16": torch.bfloat16}.get(MODE)
+EPS = float(MODE[3:]) if MODE.startswith("eps") else 0.0     # "eps1e-6": relative noise of that size instead
 
 
 def q(x):
+  if DT is None:      # fp32-rounding-sized perturbation (what a different summation order does)
+    return x + (x * EPS * torch.randn_like(x)).detach()
   return x + (x.to(DT).float() - x).detach()
 
 

@@ -44,7 +44,7 @@ def main():
   ks = sorted(((e.time_range.start, e.time_range.end, e.name, getattr(e, "device_resource_id", getattr(e, "stream", -1)))
                for e in evs if "memcpy" not in e.name.lower() and "memset" not in e.name.lower()), key=lambda x: x[0])
   print("kernels recorded:", len(ks))
-  starts = [i for i, k in enumerate(ks) if "slot_advance" in k[2]]
+  starts = [i for i, k in enumerate(ks) if "mb_begin" in k[2] or "slot_advance" in k[2]]
   if len(starts) < 4:
     print("could not find minibatch boundaries", len(starts)); return
   a, b = starts[3], starts[4]

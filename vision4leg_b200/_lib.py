@@ -79,8 +79,8 @@ class TcWgradArgs(C.Structure):
 class OptTailArgs(C.Structure):
   _fields_ = [("phases", C.c_int32), ("param", C.c_void_p), ("grad", C.c_void_p), ("m", C.c_void_p),
               ("v", C.c_void_p), ("n", C.c_int64), ("hyper", C.c_void_p), ("info", C.c_void_p),
-              ("slot", C.c_void_p), ("norm_slot", C.c_int32), ("pack_src", C.c_void_p),
-              ("pack_table", C.c_void_p), ("packed", C.c_void_p), ("n_pack", C.c_int64),
+              ("slot", C.c_void_p), ("norm_slot", C.c_int32), ("extra_lo", C.c_int64), ("extra_n", C.c_int64),
+              ("scatter", C.c_void_p), ("packed_self", C.c_void_p), ("packed_other", C.c_void_p),
               ("slot_advance", C.c_void_p)]
 
 
@@ -147,6 +147,7 @@ SIGNATURES = {
   "v4l_tc_gemm": [_vp, _vp, C.POINTER(TcGemmArgs)],
   "v4l_tc_wgrad": [_vp, _vp, C.POINTER(TcWgradArgs)],
   "v4l_tc_wgrad_flush": [_vp, _vp],
+  "v4l_tc_wgrad_conv1": [_vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _f, _i, _i],
   "v4l_opt_tail": [_vp, _vp, C.POINTER(OptTailArgs)],
   "v4l_opt_tail_error": [_vp],
   "v4l_mb_begin": [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i],

@@ -104,6 +104,7 @@ class PPOUpdateEngine:
       self.plan_t = Plan(self.ops, self.S, self.A, self.pf_layout, nh, with_backward=False)
       self.plan_t.pack(self.t_flat)
       self.plan_pf.world = self.plan_vf.world = self.world
+      self._build_scatter()
     else:
       self.plan_pf = engine.make_plan(self.family, self.ops, self.S, self.A, **kw)
       self.plan_vf = engine.make_plan(self.family, self.ops, self.S, 1, **kw)
@@ -159,6 +160,31 @@ class PPOUpdateEngine:
         self.P_t[n] = view
     self.t_logstd = dict(t_named)["logstd"].data
     self._param_ptrs = [(p, p.data_ptr()) for _, p in pf_named + vf_named + t_named]
+
+  def _build_scatter(self):
+    """For every element of an optimiser bucket: where its fp16 copies live in the packed operand buffers
+    (TcWeights: tap-major forward + data-gradient orientation) of its own network and — shared-encoder
+    weights — of the other one.  The optimiser tail writes them in the Adam pass (v4l_opt_tail)."""
+    def positions(W, lo_src, lo_dst, n_dst):
+      tab = W.table.cpu().numpy().astype(np.int64)
+      pos = np.nonzero(tab >= 0)[0]
+      dst = tab[pos] + lo_src - lo_dst              # index in the destination bucket
+      ok = (dst >= 0) & (dst < n_dst)
+      pos, dst = pos[ok], dst[ok]
+      out = -np.ones((n_dst, 2), np.int64)
+      order = np.argsort(dst, kind="stable")
+      pos, dst = pos[order], dst[order]
+      first = np.r_[True, dst[1:] != dst[:-1]]
+      rank = np.arange(len(dst)) - np.maximum.accumulate(np.where(first, np.arange(len(dst)), 0))
+      assert rank.max(initial=0) <= 1, "a parameter appears in more than two packed positions"
+      out[dst, rank] = pos
+      return out
+    self.scatter = {}
+    for name, (lo, n, W_self, lo_other, W_other) in {
+        "vf": (self.vf_range[0], self.n_vf, self.plan_vf.W, self.pf_range[0], self.plan_pf.W),
+        "pf": (self.pf_range[0], self.n_pf, self.plan_pf.W, self.vf_range[0], self.plan_vf.W)}.items():
+      t = np.concatenate([positions(W_self, lo, lo, n), positions(W_other, lo_other, lo, n)], axis=1)
+      self.scatter[name] = torch.tensor(t.astype(np.int32), device=self.device).contiguous()
 
   def check_views(self):
     for p, ptr in self._param_ptrs:
@@ -450,8 +476,7 @@ class PPOUpdateEngine:
                 self.clipped_value_loss, self.clip_para, self._info, self._slot,
                 d_f16=pvf.grad_in(B), scale_f16=pvf.loss_scale(B))
     pvf.backward(self.g_vf, None, flush=False)
-    self._tail(self.vf_flat, self.g_vf, self.m_vf, self.v_vf, self.n_vf, self.hyper_vf, INFO_GRAD_NORM_VF,
-               self.pf_flat, ppf.W, None)
+    self._tail("vf", None)
     # ---- actor
     ppf.forward(self.pf_flat, imgs, idx, st, B, b["mean"])
     if with_target:
@@ -461,20 +486,27 @@ class PPOUpdateEngine:
                 self.entropy_coeff, self._info, self._slot, target_indexed=True,
                 d_f16=ppf.grad_in(B), scale_f16=ppf.loss_scale(B))
     ppf.backward(self.g_pf, None, flush=False)
-    self._tail(self.pf_flat, self.g_pf, self.m_pf, self.v_pf, self.n_pf, self.hyper_pf, INFO_GRAD_NORM_PF,
-               self.vf_flat, pvf.W, self._slot)
+    self._tail("pf", self._slot)
 
-  def _tail(self, flat, g, m, v, n, hyper, norm_slot, pack_src, W, slot_advance):
-    """reduce -> (all-reduce) -> clip + Adam -> re-pack `W` from `pack_src` -> counters"""
+  def _tail(self, which, slot_advance):
+    """reduce -> (all-reduce) -> clip + Adam (+ fp16 operand copies of both networks) -> counters"""
+    if which == "vf":
+      flat, g, m, v, n, hyper, norm_slot = self.vf_flat, self.g_vf, self.m_vf, self.v_vf, self.n_vf, self.hyper_vf, INFO_GRAD_NORM_VF
+      W_self, W_other, extra = self.plan_vf.W, self.plan_pf.W, (0, 0)
+    else:
+      flat, g, m, v, n, hyper, norm_slot = self.pf_flat, self.g_pf, self.m_pf, self.v_pf, self.n_pf, self.hyper_pf, INFO_GRAD_NORM_PF
+      W_self, W_other = self.plan_pf.W, self.plan_vf.W
+      off = self.pf_layout["logstd"][0]
+      extra = (off, self.A)
     kw = dict(param=flat, grad=g, m=m, v=v, n=n, hyper=hyper, info=self._info, slot=self._slot,
-              norm_slot=norm_slot, pack_src=pack_src, pack_table=W.table, packed=W.packed, n_pack=W.size,
-              slot_advance=slot_advance)
+              norm_slot=norm_slot, extra=extra, scatter=self.scatter[which], packed_self=W_self.packed,
+              packed_other=W_other.packed, slot_advance=slot_advance)
     if self.world > 1:
       self.ops.opt_tail(1)
       self._allreduce(g)
-      self.ops.opt_tail(6, **kw)
+      self.ops.opt_tail(2, **kw)
     else:
-      self.ops.opt_tail(7, **kw)
+      self.ops.opt_tail(3, **kw)
 
   def _allreduce(self, t):
     import torch.distributed as dist
@@ -512,7 +544,10 @@ class PPOUpdateEngine:
       self._graphs.clear()
     B = rows * E
     if self.precision == "f16":
-      self.plan_vf.pack(self.vf_flat)       # later re-packs ride on the optimiser tails (_minibatch_tc)
+      # parameters may have been changed from outside (load_state_dict) since the last epoch: re-pack both
+      # operand copies once; inside the epoch the optimiser tails keep them current (_minibatch_tc)
+      self.plan_vf.pack(self.vf_flat)
+      self.plan_pf.pack(self.pf_flat)
     if tail == 0 and len(perms) > 0:
       # uniform minibatches: flat_idx is [n_mb, B] and the device slot counter indexes it
       if getattr(self, "_flat_idx_static", None) is None or self._flat_idx_static.numel() != flat.size:

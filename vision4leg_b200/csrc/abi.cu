@@ -53,6 +53,7 @@ extern "C" int v4l_ctx_create(v4l_ctx** out, int device, size_t scratch_bytes) {
   c->defer_elems = total_elems - c->scratch_elems;
   c->defer_cursor = 0;
   c->n_jobs = 0;
+  c->early_flush = 0;
   cudaError_t e = cudaMalloc(&c->scratch, scratch_bytes);
   if (e != cudaSuccess) {
     v4l_set_error("v4l_ctx_create: cudaMalloc(%zu) -> %s", scratch_bytes, cudaGetErrorString(e));

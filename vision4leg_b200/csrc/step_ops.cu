@@ -6,9 +6,10 @@
 // by the LENGTH of that chain, so the small HBM/latency-bound links are merged:
 //
 //   v4l_mb_begin   row-index selection + advantage statistics + proprio rows -> fp16 (was 3 launches)
-//   v4l_opt_tail   split-K reduction of the weight-gradient partials -> squared norm -> global-norm
-//                  clip + Adam -> fp16 re-pack of the weights the NEXT forward reads -> slot advance
-//                  (was 5-6 launches); phases are separated by a device-wide barrier.
+//   v4l_opt_tail   split-K reduction of the weight-gradient partials (+ squared norm of what it writes) ->
+//                  device-wide barrier -> global-norm clip + Adam, each updated weight written straight
+//                  into the fp16 operand copies the NEXT forward passes read -> step / slot counters
+//                  (was 5-6 launches).
 //
 // The device-wide barrier needs all CTAs of the grid co-resident: the grid is one CTA per SM, the
 // kernel uses no dynamic shared memory and <= 64 registers, so a CTA always finds a slot as soon as
@@ -70,14 +71,24 @@ mb_begin_kernel(const int32_t* __restrict__ flat_idx, const int32_t* __restrict_
     s += a; s2 += (double)a * a;
     mx = fmaxf(mx, a); mn = fminf(mn, a);
   }
-  // (2) proprio rows -> fp16, zero padded to Sp columns (the first Linear's K is a multiple of 64)
+  // (2) proprio rows -> fp16, zero padded to Sp columns (the first Linear's K is a multiple of 64): one unit =
+  //     8 columns of one row -> one index load, 8 independent loads, one 16-byte store
   if (st16) {
-    const long long total = (long long)n * Sp;
-    for (long long e = gtid; e < total; e += gsz) {
-      const int r = (int)(e / Sp), c = (int)(e - (long long)r * Sp);
-      float v = 0.f;
-      if (c < S) v = state[(long long)flat_idx[base + r] * S + c];
-      st16[e] = __float2half(v);
+    const int cpr = Sp >> 3;                       // 8-column chunks per row (Sp is a multiple of 64)
+    const long long units = (long long)n * cpr;
+    for (long long u = gtid; u < units; u += gsz) {
+      const int r = (int)(u / cpr), c0 = (int)(u - (long long)r * cpr) << 3;
+      const float* src = state + (long long)flat_idx[base + r] * S + c0;
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = (c0 + j < S) ? src[j] : 0.f;
+      uint4 w;
+      __half2 h;
+      h = __floats2half2_rn(f[0], f[1]); w.x = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2half2_rn(f[2], f[3]); w.y = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2half2_rn(f[4], f[5]); w.z = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2half2_rn(f[6], f[7]); w.w = *reinterpret_cast<uint32_t*>(&h);
+      *reinterpret_cast<uint4*>(st16 + (long long)r * Sp + c0) = w;
     }
   }
   // (3) advantage statistics {sum, sumsq, n, max, min}: per-CTA partials, summed in CTA order by the
@@ -110,18 +121,20 @@ mb_begin_kernel(const int32_t* __restrict__ flat_idx, const int32_t* __restrict_
 // =================================================================================================
 // fused optimiser tail
 // =================================================================================================
-constexpr int TAIL_THREADS = 512;
+constexpr int TAIL_THREADS = 1024;
 
 struct TailParams {
   v4l_reduce_job jobs[V4L_MAX_JOBS];
-  int job_first[V4L_MAX_JOBS + 1];   // prefix sums of lane-items (outputs x lanes) per job
+  int job_first[V4L_MAX_JOBS + 1];   // prefix sums of lane-items (outputs x lanes, padded to whole warps) per job
   int job_lanes_log2[V4L_MAX_JOBS];  // log2 of the lanes that share one output's split sum
   int n_jobs;
-  int phases;                        // bit 0: reduce, bit 1: norm + clip + Adam, bit 2: re-pack + finish
+  int phases;                        // bit 0: reduce, bit 1: norm + clip + Adam (+ fp16 operand copies)
   float* p; float* g; float* m; float* v; long long n;
   float* hyper;                      // {lr, b1, b2, eps, max_norm, step, ...}
   float* info; const int32_t* slot; int norm_slot;
-  const float* pack_src; const int32_t* pack_table; __half* packed; long long n_pack;
+  long long extra_lo, extra_n;       // gradient range NOT produced by a reduction job (logstd), for the norm
+  const int4* scatter;               // [n] packed fp16 positions of parameter i: (self a, self b, other a, other b), -1 = none
+  __half* packed_self; __half* packed_other;
   int32_t* slot_advance;             // optional: minibatch slot counter to increment at the very end
   double* part;                      // [gridDim.x] squared-norm partials
   unsigned int* bar;                 // [2] barrier arrival counter, exit counter
@@ -146,15 +159,17 @@ __device__ __forceinline__ void grid_barrier(const TailParams& P, unsigned int& 
   __syncthreads();
 }
 
-// dw[index[n*Kp + kp]] = scale * sum_split partial[split][kp / 128][n][kp % 128]  (+ bias rows), one
-// output per group of 2^lanes_log2 lanes: each lane sums a strided subset of the splits, then a fixed
-// shuffle tree combines them.  partial is kp-fastest, so reads AND (for Linear layers) writes coalesce.
-__device__ __forceinline__ void reduce_phase(const TailParams& P) {
+// dw[index[n*Kp + kp]] = scale * sum_split partial[split][kp / 128][n][kp % 128]  (+ bias rows).  Work unit =
+// 4 consecutive kp of one n (a float4 of the kp-fastest partial layout; Kp is a multiple of 64) shared by a
+// group of 2^lanes_log2 lanes: each lane sums a strided subset of the splits (<= 4 independent 16-byte loads in
+// flight), then a fixed shuffle tree combines the lanes.  A bias output is a unit with one live component.
+// Returns this thread's sum of squares of the gradient values it wrote (for the global norm).
+__device__ __forceinline__ double reduce_phase(const TailParams& P) {
   const int total = P.job_first[P.n_jobs];
-  const int lane = threadIdx.x & 31;
+  double sq = 0.0;
   for (int base = blockIdx.x * TAIL_THREADS; base < total; base += gridDim.x * TAIL_THREADS) {
     const int item = base + threadIdx.x;
-    // the job of this item (items of one warp may straddle two jobs: lanes are masked, not the warp)
+    // a job's items are padded to whole warps, so all lanes of a warp work on the same job (same L)
     int j = 0;
     bool live = item < total;
     if (live) {
@@ -166,40 +181,64 @@ __device__ __forceinline__ void reduce_phase(const TailParams& P) {
     const int ll = P.job_lanes_log2[j];
     const int L = 1 << ll;
     const int rel = live ? item - P.job_first[j] : 0;
-    const int o = rel >> ll, l = rel & (L - 1);
-    const long long n_w = (long long)J.N_valid * J.Kp;
-    live = live && o < n_w + (J.has_bias ? J.N_valid : 0);      // a job's items are padded to whole warps
+    const int u = rel >> ll, l = rel & (L - 1);
+    const int units_w = (J.N_valid * J.Kp) >> 2;
+    live = live && u < units_w + (J.has_bias ? J.N_valid : 0);
     const long long split_stride = (long long)(J.kin_tiles + J.has_bias) * 128 * J.Nmma;
-    const float* src;
-    long long dst = -1;
+    const float* src = J.partial;
+    int4 dst = make_int4(-1, -1, -1, -1);
     float* out = J.dw;
-    if (o < n_w) {
-      const int n = o / J.Kp, kp = o - n * J.Kp;
-      src = J.partial + ((long long)(kp >> 7) * J.Nmma + n) * 128 + (kp & 127);
-      dst = J.index ? (long long)J.index[o] : (long long)o;
-    } else {                                    // bias gradient: K slice `kin_tiles`, lane 0
-      const int n = (int)(o - n_w);
-      src = J.partial + ((long long)J.kin_tiles * J.Nmma + n) * 128;
-      dst = n; out = J.dbias;
-    }
-    float s = 0.f;
+    const bool is_w = u < units_w;
     if (live) {
-      int z = l;
-      for (; z + 3 * L < J.splits; z += 4 * L) {
-        const float a0 = src[(long long)z * split_stride], a1 = src[(long long)(z + L) * split_stride];
-        const float a2 = src[(long long)(z + 2 * L) * split_stride], a3 = src[(long long)(z + 3 * L) * split_stride];
-        s += a0; s += a1; s += a2; s += a3;
+      if (is_w) {
+        const int o = u << 2;
+        const int n = o / J.Kp, kp = o - n * J.Kp;
+        src = J.partial + ((long long)(kp >> 7) * J.Nmma + n) * 128 + (kp & 127);
+        dst = J.index ? __ldg(reinterpret_cast<const int4*>(J.index + o)) : make_int4(o, o + 1, o + 2, o + 3);
+      } else {                                  // bias gradient: K slice `kin_tiles`, lane 0 of the row
+        const int n = u - units_w;
+        src = J.partial + ((long long)J.kin_tiles * J.Nmma + n) * 128;
+        dst.x = n; out = J.dbias;
       }
-      for (; z < J.splits; z += L) s += src[(long long)z * split_stride];
     }
-    // combine the L lanes of an output (L <= 32 divides the warp; same tree for every output)
-    for (int off = 1; off < L; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if (live && l == 0 && dst >= 0) {
-      const float r = s * J.scale;
-      out[dst] = J.accumulate ? out[dst] + r : r;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (dst.x >= 0 || dst.y >= 0 || dst.z >= 0 || dst.w >= 0) {
+      // (padding of the packed layouts — all four index < 0 — is skipped unread)
+      for (int z0 = l; z0 < J.splits; z0 += 4 * L) {
+        float4 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int z = z0 + q * L;
+          v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (z < J.splits) {
+            const float* a = src + (long long)z * split_stride;
+            if (is_w) v[q] = __ldcg(reinterpret_cast<const float4*>(a));
+            else v[q].x = __ldcg(a);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
+      }
+    }
+    // combine the L lanes of a unit (L <= 32 divides the warp; same tree for every output)
+    for (int off = 1; off < L; off <<= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+    }
+    if (l == 0 && live) {
+      const float r4[4] = {acc.x, acc.y, acc.z, acc.w};
+      const int d4[4] = {dst.x, dst.y, dst.z, dst.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (d4[q] < 0) continue;
+        float r = r4[q] * J.scale;
+        if (J.accumulate) r += out[d4[q]];
+        out[d4[q]] = r;
+        sq += (double)r * r;
+      }
     }
   }
-  (void)lane;
+  return sq;
 }
 
 __global__ void __launch_bounds__(TAIL_THREADS, 1) opt_tail_kernel(const __grid_constant__ TailParams P) {
@@ -210,14 +249,19 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) opt_tail_kernel(const __grid_
   const long long gtid = blockIdx.x * (long long)TAIL_THREADS + threadIdx.x;
   const long long gsz = (long long)gridDim.x * TAIL_THREADS;
 
-  if (P.phases & 1) reduce_phase(P);
+  double sq = 0.0;
+  if (P.phases & 1) sq = reduce_phase(P);
   if (P.phases & 2) {
-    if (P.phases & 1) grid_barrier(P, generation);
-    // ---- squared norm of the whole gradient bucket (clip_grad_norm_, reference ppo.py:73-74,118-119)
-    double s = 0.0;
-    for (long long i = gtid; i < P.n; i += gsz) { const double x = __ldcg(P.g + i); s += x * x; }
-    s = block_reduce_t(s, AddD(), 0.0, shd);
-    if (threadIdx.x == 0) P.part[blockIdx.x] = s;
+    // ---- squared norm of the whole gradient bucket (clip_grad_norm_, reference ppo.py:73-74,118-119):
+    //      after a fused reduction every element was just written by a job of this launch (accumulated
+    //      above), except the `extra` range (logstd, written by the loss kernel); otherwise read the bucket
+    if (P.phases & 1) {
+      for (long long i = gtid; i < P.extra_n; i += gsz) { const double x = __ldcg(P.g + P.extra_lo + i); sq += x * x; }
+    } else {
+      for (long long i = gtid; i < P.n; i += gsz) { const double x = __ldcg(P.g + i); sq += x * x; }
+    }
+    sq = block_reduce_t(sq, AddD(), 0.0, shd);
+    if (threadIdx.x == 0) P.part[blockIdx.x] = sq;
     grid_barrier(P, generation);
     // ---- every CTA derives the same clip factor from the partials, summed in the same order
     if (threadIdx.x < 32) {
@@ -260,37 +304,51 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) opt_tail_kernel(const __grid_
         }
         reinterpret_cast<float4*>(P.m)[i] = m4; reinterpret_cast<float4*>(P.v)[i] = v4;
         reinterpret_cast<float4*>(P.p)[i] = p4;
+        if (P.scatter) {
+          // fp16 operand copies of the weights (tap-major forward + data-gradient orientations) the next
+          // forward passes read: this network's own and, for shared-encoder weights, the other network's
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int4 pos = __ldg(P.scatter + 4 * i + q);
+            const __half h = __float2half(gp[q]);
+            if (pos.x >= 0) P.packed_self[pos.x] = h;
+            if (pos.y >= 0) P.packed_self[pos.y] = h;
+            if (pos.z >= 0) P.packed_other[pos.z] = h;
+            if (pos.w >= 0) P.packed_other[pos.w] = h;
+          }
+        }
       }
       for (long long i = (n4 << 2) + gtid; i < P.n; i += gsz) {
         const float gi = __ldcg(P.g + i) * coef;
         const float mi = b1 * P.m[i] + (1.f - b1) * gi;
         const float vi = b2 * P.v[i] + (1.f - b2) * gi * gi;
         P.m[i] = mi; P.v[i] = vi;
-        P.p[i] -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+        const float pn = P.p[i] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+        P.p[i] = pn;
+        if (P.scatter) {
+          const int4 pos = __ldg(P.scatter + i);
+          const __half h = __float2half(pn);
+          if (pos.x >= 0) P.packed_self[pos.x] = h;
+          if (pos.y >= 0) P.packed_self[pos.y] = h;
+          if (pos.z >= 0) P.packed_other[pos.z] = h;
+          if (pos.w >= 0) P.packed_other[pos.w] = h;
+        }
       }
     }
   }
-  if (P.phases & 4) {
-    if (P.phases & 3) grid_barrier(P, generation);
-    // ---- the step counter moves only after every CTA has used it (barrier above)
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      if ((P.phases & 2) && s_coef >= 0.f) P.hyper[5] += 1.f;
-      if (P.slot_advance) *P.slot_advance += 1;
-    }
-    // ---- fp16 re-pack (tap-major, forward + data-gradient orientations) of the weights the next
-    //      forward pass reads; the bucket was just updated by all CTAs
-    if (P.packed)
-      for (long long i = gtid; i < P.n_pack; i += gsz) {
-        const int sidx = P.pack_table[i];
-        P.packed[i] = __float2half(sidx >= 0 ? __ldcg(P.pack_src + sidx) : 0.f);
-      }
-  }
-  // ---- re-arm the barrier words for the next launch
-  if (generation > 0) {
+  // ---- the CTA that finishes last re-arms the barrier words and moves the counters (every CTA has read
+  //      the Adam step count by then)
+  if (P.phases & 2) {
     __syncthreads();
     if (threadIdx.x == 0) {
+      __threadfence();
       const unsigned int t = atomicAdd(P.bar + 1, 1u);
-      if (t == gridDim.x - 1) { P.bar[0] = 0u; P.bar[1] = 0u; __threadfence(); }
+      if (t == gridDim.x - 1) {
+        P.bar[0] = 0u; P.bar[1] = 0u;
+        if (s_coef >= 0.f) P.hyper[5] += 1.f;
+        if (P.slot_advance) *P.slot_advance += 1;
+        __threadfence();
+      }
     }
   }
 }
@@ -302,8 +360,9 @@ extern "C" int v4l_mb_begin(v4l_ctx* ctx, void* stream, const int32_t* flat_idx,
                             int S, void* state_f16, int Sp) {
   V4L_REQUIRE(ctx && flat_idx && slot && cur_idx && adv && stats && n > 0, "v4l_mb_begin: bad argument");
   V4L_REQUIRE(!state_f16 || (S >= 0 && Sp >= S && (S == 0 || state)), "v4l_mb_begin: bad proprio arguments");
+  V4L_REQUIRE(!state_f16 || Sp % 8 == 0, "v4l_mb_begin: Sp must be a multiple of 8");
   const long long work = max((long long)n, state_f16 ? (long long)n * Sp / 8 : 0LL);
-  const int ctas = max(1, min(ctx->sm_count, v4l_cdiv(work, MB_THREADS)));
+  const int ctas = max(1, min(2 * ctx->sm_count, v4l_cdiv(work, MB_THREADS)));
   double* part = reinterpret_cast<double*>(ctx->scratch);
   V4L_LAUNCH(mb_begin_kernel, ctas, MB_THREADS, 0, (cudaStream_t)stream, flat_idx, slot, cur_idx, n, adv, stats, part,
              ctx->counters + 2, state, S, reinterpret_cast<__half*>(state_f16), Sp);
@@ -311,23 +370,36 @@ extern "C" int v4l_mb_begin(v4l_ctx* ctx, void* stream, const int32_t* flat_idx,
   return 0;
 }
 
-// lanes sharing one output's split sum: ~<= 8 splits per lane
+// lanes sharing one unit's split sum: <= 4 splits per lane (one round of independent loads)
 static int lanes_log2_for(int splits) {
   int ll = 0;
-  while ((1 << ll) < 32 && (splits >> ll) > 8) ++ll;
+  while ((1 << ll) < 32 && ((splits + (1 << ll) - 1) >> ll) > 4) ++ll;
   return ll;
 }
 
 extern "C" int v4l_opt_tail(v4l_ctx* ctx, void* stream, const v4l_opt_tail_args* a) {
   V4L_REQUIRE(ctx && a, "v4l_opt_tail: NULL argument");
   const int phases = a->phases;
-  V4L_REQUIRE(phases > 0 && phases < 8, "v4l_opt_tail: bad phases %d", phases);
+  V4L_REQUIRE(phases > 0 && phases < 4, "v4l_opt_tail: bad phases %d", phases);
   V4L_REQUIRE(!(phases & 2) || (a->param && a->grad && a->m && a->v && a->hyper && a->n > 0),
               "v4l_opt_tail: the optimiser phase needs param/grad/m/v/hyper");
   V4L_REQUIRE(!(phases & 2) || ((((uintptr_t)a->param | (uintptr_t)a->grad | (uintptr_t)a->m | (uintptr_t)a->v) & 15) == 0),
               "v4l_opt_tail: buckets must be 16-byte aligned");
   V4L_REQUIRE(a->norm_slot < V4L_INFO_STRIDE, "v4l_opt_tail: bad norm_slot");
-  V4L_REQUIRE(!a->packed || (a->pack_src && a->pack_table && a->n_pack > 0), "v4l_opt_tail: bad pack arguments");
+  V4L_REQUIRE(!a->scatter || (a->packed_self && a->packed_other && (((uintptr_t)a->scatter) & 15) == 0),
+              "v4l_opt_tail: bad scatter arguments");
+  V4L_REQUIRE(a->extra_n >= 0 && a->extra_lo >= 0 && a->extra_lo + a->extra_n <= (a->n > 0 ? a->n : 0) + 0,
+              "v4l_opt_tail: bad extra range");
+  if (phases == 3 && ctx->early_flush) {
+    // some gradients were already written by an earlier flush: reduce first, then take the norm from the bucket
+    ctx->early_flush = 0;
+    v4l_opt_tail_args t = *a;
+    t.phases = 1;
+    if (int r = v4l_opt_tail(ctx, stream, &t)) return r;
+    t.phases = 2;
+    return v4l_opt_tail(ctx, stream, &t);
+  }
+  if (phases & 2) ctx->early_flush = 0;
   static TailParams P;               // large: keep it off the stack (single host thread per context)
   memset(&P, 0, sizeof(P));
   int total = 0;
@@ -338,7 +410,8 @@ extern "C" int v4l_opt_tail(v4l_ctx* ctx, void* stream, const v4l_opt_tail_args*
       P.job_first[i] = total;
       const int ll = lanes_log2_for(J.splits);
       P.job_lanes_log2[i] = ll;
-      const long long outs = (long long)J.N_valid * J.Kp + (J.has_bias ? J.N_valid : 0);
+      V4L_REQUIRE(J.Kp % 4 == 0, "v4l_opt_tail: packed K (%d) must be a multiple of 4", J.Kp);
+      const long long outs = (((long long)J.N_valid * J.Kp) >> 2) + (J.has_bias ? J.N_valid : 0);    // units
       V4L_REQUIRE(((outs << ll) + total + 32) < (1LL << 31), "v4l_opt_tail: too many reduction items");
       total += (int)((((outs << ll) + 31) >> 5) << 5);     // whole warps per job: a warp never straddles two jobs
     }
@@ -350,16 +423,17 @@ extern "C" int v4l_opt_tail(v4l_ctx* ctx, void* stream, const v4l_opt_tail_args*
   P.phases = phases;
   P.p = a->param; P.g = a->grad; P.m = a->m; P.v = a->v; P.n = a->n;
   P.hyper = a->hyper; P.info = a->info; P.slot = a->slot; P.norm_slot = a->norm_slot;
-  P.pack_src = a->pack_src; P.pack_table = a->pack_table; P.packed = reinterpret_cast<__half*>(a->packed);
-  P.n_pack = a->n_pack;
+  P.extra_lo = a->extra_lo; P.extra_n = a->extra_n;
+  P.scatter = reinterpret_cast<const int4*>(a->scatter);
+  P.packed_self = reinterpret_cast<__half*>(a->packed_self);
+  P.packed_other = reinterpret_cast<__half*>(a->packed_other);
   P.slot_advance = a->slot_advance;
   P.part = reinterpret_cast<double*>(ctx->scratch);
   P.bar = ctx->counters + 4;
   P.err = ctx->counters + 6;
-  // one CTA per SM when a barrier is needed (co-residency); a pure reduction may use more
-  const bool needs_barrier = (phases & (phases - 1)) != 0;
+  // one CTA per SM when the barrier is needed (co-residency); a pure reduction may use more
   int grid = ctx->sm_count;
-  if (!needs_barrier && phases == 1) grid = max(1, min(4 * ctx->sm_count, v4l_cdiv(total, TAIL_THREADS)));
+  if (phases == 1) grid = max(1, min(2 * ctx->sm_count, v4l_cdiv(total, TAIL_THREADS)));
   V4L_LAUNCH(opt_tail_kernel, grid, TAIL_THREADS, 0, (cudaStream_t)stream, P);
   V4L_CHECK_LAUNCH();
   return 0;

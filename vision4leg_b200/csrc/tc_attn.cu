@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) tc_attn_fwd_kernel(const __grid
   __shared__ uint32_t tmem_slot;
 
   v4l_pdl_trigger();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const int row0 = blockIdx.x * p.rows_per_tile;
   {  // zero all tiles: rows beyond the TMA box (tile padding) must contribute exact zeros
     uint4* z = reinterpret_cast<uint4*>(smem);
@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) tc_attn_fwd_kernel(const __grid
   const uint32_t tmem = tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // converged warp, one elected lane issues: operands of UTCHMMA / UTMALDG stay in uniform registers
+    if (tc::elect_one()) {
       tc::mbar_expect_tx(&bar_load, 3u * p.rows_per_tile * 128u);
       tc::tma_load_2d(sQ, &p.tmap_qkv, &bar_load, 0, row0);
       tc::tma_load_2d(sK, &p.tmap_qkv, &bar_load, 64, row0);
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) tc_attn_bwd_kernel(const __grid
   __shared__ uint32_t tmem_slot;
 
   v4l_pdl_trigger();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const int row0 = blockIdx.x * p.rows_per_tile;
   {
     uint4* z = reinterpret_cast<uint4*>(smem);
@@ -230,7 +231,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) tc_attn_bwd_kernel(const __grid
   // TMEM columns: dP [0,128)  dQ [128,192)  dK [192,256)  dV [256,320)
 
   if (warp == 0) {
-    if (lane == 0) {
+    // converged warp, one elected lane issues: operands of UTCHMMA / UTMALDG stay in uniform registers
+    if (tc::elect_one()) {
       tc::mbar_expect_tx(&bar_load, 4u * p.rows_per_tile * 128u);
       tc::tma_load_2d(sQ, &p.tmap_qkv, &bar_load, 0, row0);
       tc::tma_load_2d(sK, &p.tmap_qkv, &bar_load, 64, row0);

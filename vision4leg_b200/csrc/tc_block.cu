@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
   v4l_pdl_trigger();
   const bool tl = blockIdx.x == 0 && threadIdx.x == 32;
   stamp(0, 0, tl);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const int row0 = blockIdx.x * p.rows_per_tile;
   {  // zero the activation tiles (padding rows of a tile must be exact zeros / finite)
     uint4* z = reinterpret_cast<uint4*>(sm + OFF_X);
@@ -182,7 +182,8 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_fwd_kernel(const __gri
   constexpr uint32_t C_QKV = 0, C_S = 192, C_O = 320, C_PROJ = 384, C_F1 = 0, C_F2 = 448;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // converged warp, one elected lane issues: operands of UTCHMMA / UTMALDG stay in uniform registers
+    if (tc::elect_one()) {
       const uint32_t base = tc::smem_u32(sm);
       tc::mbar_expect_tx(&bar_in, static_cast<uint32_t>(p.rows_per_tile) * 128u + 192u * 128u);
       tc::tma_load_2d(sm + OFF_X, &p.tm_x, &bar_in, 0, row0);
@@ -607,7 +608,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
   v4l_pdl_trigger();
   const bool tl = blockIdx.x == 0 && threadIdx.x == 32;
   stamp(1, 0, tl);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const int row0 = blockIdx.x * p.rows_per_tile;
   {
     uint4* z = reinterpret_cast<uint4*>(sm + BO_R1);
@@ -635,7 +636,8 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tc_block_bwd_kernel(const __gri
   constexpr uint32_t C_DF1 = 0, C_DH = 256, C_DO = 320, C_DX = 384, C_DP = 0, C_DQKV = 128;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // converged warp, one elected lane issues: operands of UTCHMMA / UTMALDG stay in uniform registers
+    if (tc::elect_one()) {
       const uint32_t base = tc::smem_u32(sm);
       tc::mbar_expect_tx(&bar_wa, 64u * 1024u);
       tc::tma_load_2d(sm + BO_W, &p.tm_w2d, &bar_wa, 0, 0);

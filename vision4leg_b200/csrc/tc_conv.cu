@@ -50,25 +50,41 @@ struct ConvFlatParams {
   int group;                   // tiles whose MMAs are issued interleaved (independent accumulators)
 };
 
-// Consecutive tcgen05.mma into the SAME accumulator form a dependent chain (~85 ns each whatever N
-// is: measured), so narrow layers are bound by that latency, not by the MMA's width.  The MMAs of G
-// tiles (independent accumulators, G <= accumulator stages) are therefore issued interleaved; everything
-// is kept in registers (static indices) because this single thread's instruction stream is the next limit.
+// MMA issue loop, executed by the WHOLE issuer warp (converged; the warp index is made provably uniform
+// with a shuffle) with one elected lane issuing: every descriptor is then computed in uniform registers and
+// a tcgen05.mma costs its hardware floor (~48 cycles for N <= 64; tools/ubench/mma_rate.cu).  Round 1 ran
+// this loop under `if (lane == 0)` — tabulated descriptors included — where the compiler must move each
+// operand of each UTCHMMA into uniform registers through an elect + broadcast loop: ~150 cycles per MMA
+// whatever N is, which had been misread as a property of the tensor pipe.  The MMAs of G tiles
+// (independent accumulators) are still issued interleaved.
 struct IssueCtx {
   uint64_t *full_bar, *empty_bar, *tmem_full, *tmem_empty;
-  const uint32_t* aoff;
-  const uint64_t* bdesc;
-  uint32_t ring_addr, stage_bytes, tmem_base;
-  int acc_cols, n_acc, n_mma;
+  uint32_t ring_addr, stage_bytes, tmem_base, w_addr, copy_bytes;
+  int acc_cols, n_acc;
   uint32_t idesc;
   int stages, num_tiles;
 };
 
+// byte offset of tap t's A start inside a stage (mode 0: pre-shifted copy whose residue matches)
+__device__ __forceinline__ uint32_t tap_offset(const struct ConvFlatParams& p, int t, uint32_t copy_bytes);
+
 template <int G>
-__device__ __forceinline__ void issue_mmas(const IssueCtx& c) {
+__device__ __forceinline__ void issue_mmas(const struct ConvFlatParams& p, const IssueCtx& c);
+
+__device__ __forceinline__ uint32_t tap_offset(const ConvFlatParams& p, int t, uint32_t copy_bytes) {
+  const int sh = p.shift[t];
+  if (p.mode != 0) return static_cast<uint32_t>(sh) * 128u;
+  int cpy = 0;
+  for (int q = 0; q < p.n_copies; ++q) if (p.copy_res[q] == (sh & 7)) cpy = q;
+  return cpy * copy_bytes + static_cast<uint32_t>(sh & ~7) * 128u;
+}
+
+template <int G>
+__device__ __forceinline__ void issue_mmas(const ConvFlatParams& p, const IssueCtx& c) {
   int stage = 0; uint32_t phase = 0;
   int acc = 0; uint32_t acc_phase = 0;
   const int step = static_cast<int>(gridDim.x);
+  const uint64_t bdesc0 = tc::umma_smem_desc(c.w_addr, 0, 1024);
   for (int tile = blockIdx.x; tile < c.num_tiles; tile += G * step) {
     bool v[G];
     uint32_t d[G];
@@ -89,24 +105,25 @@ __device__ __forceinline__ void issue_mmas(const IssueCtx& c) {
       }
     }
     tc::tc_fence_after();
-    {
-      const uint32_t ao = c.aoff[0];
-      const uint64_t bd = c.bdesc[0];
+    if (tc::elect_one()) {
+      for (int t = 0; t < p.n_taps; ++t) {
+        const uint32_t toff = tap_offset(p, t, c.copy_bytes);
+        for (int j = 0; j < p.kc; ++j) {
+          const uint32_t ao = (toff + j * p.load_rows * 128) >> 4;
+          const uint64_t bd = bdesc0 + (((t * p.kc + j) * p.N * 128) >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+              if (v[g]) tc::umma_f16(d[g], ab[g] + ao + 2 * k, bd + 2 * k, c.idesc, (t | j | k) ? 1u : 0u);
+          }
+        }
+      }
 #pragma unroll
       for (int g = 0; g < G; ++g)
-        if (v[g]) tc::umma_f16(d[g], ab[g] + ao, bd, c.idesc, 0u);
+        if (v[g]) { tc::umma_commit(eb[g]); tc::umma_commit(tf[g]); }
     }
-#pragma unroll 2
-    for (int i = 1; i < c.n_mma; ++i) {
-      const uint32_t ao = c.aoff[i];
-      const uint64_t bd = c.bdesc[i];
-#pragma unroll
-      for (int g = 0; g < G; ++g)
-        if (v[g]) tc::umma_f16(d[g], ab[g] + ao, bd, c.idesc, 1u);
-    }
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-      if (v[g]) { tc::umma_commit(eb[g]); tc::umma_commit(tf[g]); }
+    __syncwarp();
   }
 }
 
@@ -116,14 +133,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) tc_conv_flat_kernel(const __gri
   __shared__ uint64_t full_bar[CV_MAX_STAGES], empty_bar[CV_MAX_STAGES], tmem_full[CV_MAX_ACC], tmem_empty[CV_MAX_ACC], w_bar;
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_bias[256];
-  // the MMA issuer is ONE thread: with narrow N each tcgen05.mma is only ~16-32 tensor-core cycles,
-  // so descriptor arithmetic in the issue loop would bound the kernel.  All per-(tap, chunk, k)
-  // descriptor parts are tabulated once; the loop is load, add, issue.
-  __shared__ uint64_t s_bdesc[CV_MAX_MMA];
-  __shared__ uint32_t s_aoff[CV_MAX_MMA];      // (byte offset of the A start inside a stage) >> 4
 
   v4l_pdl_trigger();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const int N = p.N;
   // accumulator stages in TMEM = epilogue warpgroups: a tile's MMAs are short next to the
   // MMA -> epilogue -> MMA hand-over, so narrow layers need several tiles in flight
@@ -147,23 +159,6 @@ __global__ void __launch_bounds__(CV_THREADS, 1) tc_conv_flat_kernel(const __gri
   if (warp == 1) tc::tmem_alloc(&tmem_base_slot, 512);
   v4l_pdl_wait();
   for (int i = threadIdx.x; i < 256; i += CV_THREADS) s_bias[i] = (p.bias && i < p.N_valid) ? p.bias[i] : 0.f;
-  const int n_mma = p.n_taps * p.kc * 4;
-  for (int i = threadIdx.x; i < n_mma; i += CV_THREADS) {
-    const int k = i & 3, tj = i >> 2;            // tj = t * kc + j
-    const int t = tj / p.kc, j = tj - t * p.kc;
-    const int sh = p.shift[t];
-    uint32_t off;
-    if (p.mode == 0) {
-      int c = 0;
-      for (int q = 0; q < p.n_copies; ++q) if (p.copy_res[q] == (sh & 7)) c = q;
-      off = c * copy_bytes + static_cast<uint32_t>(sh & ~7) * 128u;
-    } else {
-      off = static_cast<uint32_t>(sh) * 128u;
-    }
-    off += j * p.load_rows * 128 + k * 32;
-    s_aoff[i] = off >> 4;
-    s_bdesc[i] = tc::umma_smem_desc(tc::smem_u32(w_smem) + tj * N * 128 + k * 32, 0, 1024);
-  }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -171,40 +166,40 @@ __global__ void __launch_bounds__(CV_THREADS, 1) tc_conv_flat_kernel(const __gri
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
-    if (lane == 0) {
+    // whole warp converged, one elected lane issues
+    if (tc::elect_one()) {
       tc::mbar_expect_tx(&w_bar, w_bytes);
       for (int q = 0; q < n_chunks; ++q) tc::tma_load_2d(w_smem + q * N * 128, &p.tm_w, &w_bar, q * 64, 0);
-      int stage = 0; uint32_t phase = 0;
-      auto src_row = [&](int tile) -> long long {      // first tensor row of the tile
-        if (!p.a_idx) return (long long)tile * 128;
+    }
+    __syncwarp();
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int row0 = tile * 128;                          // first tensor row of the tile
+      if (p.a_idx) {
         const int img = tile / p.tiles_per_img;
-        return (long long)p.a_idx[img] * p.P + (long long)(tile - img * p.tiles_per_img) * 128;
-      };
-      long long row_next = blockIdx.x < p.num_tiles ? src_row(blockIdx.x) : 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const long long row0 = row_next;
-        if (tile + gridDim.x < p.num_tiles) row_next = src_row(tile + gridDim.x);
-        tc::mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* s = ring + stage * stage_bytes;
+        row0 = __shfl_sync(0xffffffffu, p.a_idx[img], 0) * p.P + (tile - img * p.tiles_per_img) * 128;
+      }
+      tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* s = ring + stage * stage_bytes;
+      if (tc::elect_one()) {
         tc::mbar_expect_tx(&full_bar[stage], stage_bytes);
         for (int c = 0; c < p.n_copies; ++c)
           for (int j = 0; j < p.kc; ++j)
             tc::tma_load_2d(s + c * copy_bytes + j * p.load_rows * 128, &p.tm_a, &full_bar[stage], j * 64,
-                            static_cast<int>(row0) + p.copy_res[c]);
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                            row0 + p.copy_res[c]);
       }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ================================
-    if (lane == 0) {
-      const uint32_t idesc = tc::umma_idesc_f16(128, N, 0, 0);
-      tc::mbar_wait(&w_bar, 0);
-      IssueCtx c{full_bar, empty_bar, tmem_full, tmem_empty, s_aoff, s_bdesc, tc::smem_u32(ring), stage_bytes, tmem_base,
-                 acc_cols, n_acc, n_mma, idesc, p.stages, p.num_tiles};
-      if (p.group >= 4) issue_mmas<4>(c);
-      else if (p.group == 2) issue_mmas<2>(c);
-      else issue_mmas<1>(c);
-    }
+    const uint32_t idesc = tc::umma_idesc_f16(128, N, 0, 0);
+    tc::mbar_wait(&w_bar, 0);
+    IssueCtx c{full_bar, empty_bar, tmem_full, tmem_empty, tc::smem_u32(ring), stage_bytes, tmem_base,
+               tc::smem_u32(w_smem), copy_bytes, acc_cols, n_acc, idesc, p.stages, p.num_tiles};
+    if (p.group >= 4) issue_mmas<4>(p, c);
+    else if (p.group == 2) issue_mmas<2>(p, c);
+    else issue_mmas<1>(p, c);
   } else if (((warp - 2) >> 2) < n_acc) {
     // ============================== epilogue ==================================
     const int wg = (warp - 2) >> 2;

@@ -64,7 +64,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   __shared__ float s_bias[256];
 
   v4l_pdl_trigger();               // the next kernel may start its prologue now
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, so the producer / issuer loops below run converged
+  // and their descriptors and coordinates stay in uniform registers (see tc_wgrad_s2d.cu)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int n_chunk = blockIdx.y;
   const int n0 = n_chunk * p.N;
   const int N = min(p.N, p.N_total - n0);                 // UMMA N of this chunk (multiple of 16)
@@ -99,32 +101,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
-    if (lane == 0) {
+    // whole warp converged, one elected lane issues
+    {
       int stage = 0; uint32_t phase = 0;
-      // minibatch row gather (bb == 1 only): the index of the NEXT tile's image is fetched while this
-      // tile's loads are issued, so the dependent global load never stalls the single producer thread
-      int idx_next = (p.a_idx && blockIdx.x < p.num_tiles) ? p.a_idx[blockIdx.x / p.h_tiles] : 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int b0, h0;
         if (p.bb == 1) { b0 = tile / p.h_tiles; h0 = (tile - b0 * p.h_tiles) * p.bh; }
         else           { b0 = tile * p.bb; h0 = 0; }
-        const int ab0 = p.a_idx ? idx_next : b0;
-        if (p.a_idx && tile + gridDim.x < p.num_tiles) idx_next = p.a_idx[(tile + gridDim.x) / p.h_tiles];
+        // minibatch row gather (bb == 1 only)
+        int ab0 = b0;
+        if (p.a_idx) ab0 = __shfl_sync(0xffffffffu, p.a_idx[b0], 0);
         for (int it = 0; it < k_iters; ++it) {
           const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + A_TILE_BYTES;
-          tc::mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
-          tc::tma_load_4d(sa, &p.tmap_a, &full_bar[stage], kc * 64, p.tap_dw[tap], h0 + p.tap_dh[tap], ab0);
-          tc::tma_load_2d(sb, &p.tmap_b, &full_bar[stage], it * 64, n0);
+          if (tc::elect_one()) {
+            tc::mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+            tc::tma_load_4d(sa, &p.tmap_a, &full_bar[stage], kc * 64, p.tap_dw[tap], h0 + p.tap_dh[tap], ab0);
+            tc::tma_load_2d(sb, &p.tmap_b, &full_bar[stage], it * 64, n0);
+          }
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ================================
-    if (lane == 0) {
+    {
       const uint32_t idesc = tc::umma_idesc_f16(128, N, 0, 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -136,17 +140,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
           tc::mbar_wait(&full_bar[stage], phase);
           tc::tc_fence_after();
           const uint32_t sa = tc::smem_u32(smem + stage * stage_bytes);
-          const uint32_t sb = sa + A_TILE_BYTES;
+          const uint64_t adesc0 = tc::umma_smem_desc(sa, 0, 1024);
+          const uint64_t bdesc0 = tc::umma_smem_desc(sa + A_TILE_BYTES, 0, 1024);
+          if (tc::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {                      // 4 x UMMA_K(16) = 64
-            const uint64_t adesc = tc::umma_smem_desc(sa + k * 32, 0, 1024);
-            const uint64_t bdesc = tc::umma_smem_desc(sb + k * 32, 0, 1024);
-            tc::umma_f16(d_tmem, adesc, bdesc, idesc, (it | k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)                        // 4 x UMMA_K(16) = 64; +32 B = +2 in the address field
+              tc::umma_f16(d_tmem, adesc0 + 2 * k, bdesc0 + 2 * k, idesc, (it | k) ? 1u : 0u);
+            tc::umma_commit(&empty_bar[stage]);                // frees the smem stage when MMAs retire
           }
-          tc::umma_commit(&empty_bar[stage]);                // frees the smem stage when MMAs retire
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        tc::umma_commit(&tmem_full[acc]);                    // accumulator ready for the epilogue
+        if (tc::elect_one()) tc::umma_commit(&tmem_full[acc]); // accumulator ready for the epilogue
+        __syncwarp();
         if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -448,7 +454,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
   __shared__ uint32_t tmem_base_slot;
 
   v4l_pdl_trigger();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const int split = blockIdx.x, kt = blockIdx.y;
   const int Nmma = 64 * p.n_atoms;
   const int box_rows = p.bw * p.bh * p.bb;
@@ -489,7 +495,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer: whole warp converged, one elected lane issues
+    {
       // the two 64-channel atoms of this CTA's K slice: packed index kp = tap * x_C + c
       int a_tap[2], a_c0[2];
       for (int j = 0; j < 2; ++j) {
@@ -499,31 +506,32 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
         a_tap[j] = tap; a_c0[j] = c0;
       }
       int stage = 0; uint32_t phase = 0;
-      // gather index of the next tile's image fetched one tile ahead (see tc_gemm_kernel)
-      int idx_next = (p.x_idx && tile_lo < tile_hi) ? p.x_idx[p.bb == 1 ? tile_lo / p.h_tiles : tile_lo * p.bb] : 0;
       for (int tile = tile_lo; tile < tile_hi; ++tile) {
         int b0, h0;
         if (p.bb == 1) { b0 = tile / p.h_tiles; h0 = (tile - b0 * p.h_tiles) * p.bh; }
         else           { b0 = tile * p.bb; h0 = 0; }
-        const int xb0 = p.x_idx ? idx_next : b0;
-        if (p.x_idx && tile + 1 < tile_hi) idx_next = p.x_idx[p.bb == 1 ? (tile + 1) / p.h_tiles : (tile + 1) * p.bb];
+        int xb0 = b0;
+        if (p.x_idx) xb0 = __shfl_sync(0xffffffffu, p.x_idx[b0], 0);
         for (int sub = 0; sub < p.n_sub; ++sub) {
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* s = smem + stage * stage_bytes;
-          tc::mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>((bias_cta ? 0 : 2) + p.n_atoms) * box_rows * 128u);
-          for (int j = 0; j < 2 && !bias_cta; ++j)
-            tc::tma_load_4d(s + j * ATOM_BYTES, &p.tmap_x, &full_bar[stage], a_c0[j],
-                            p.sub_dw[sub] + p.tap_dw[a_tap[j]],
-                            h0 * p.x_estride + p.sub_dh[sub] + p.tap_dh[a_tap[j]], xb0);
-          for (int j = 0; j < p.n_atoms; ++j)
-            tc::tma_load_4d(s + (2 + j) * ATOM_BYTES, &p.tmap_dy, &full_bar[stage], p.sub_dyc[sub] + j * 64, 0,
-                            h0, b0);
+          if (tc::elect_one()) {
+            tc::mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>((bias_cta ? 0 : 2) + p.n_atoms) * box_rows * 128u);
+            for (int j = 0; j < 2 && !bias_cta; ++j)
+              tc::tma_load_4d(s + j * ATOM_BYTES, &p.tmap_x, &full_bar[stage], a_c0[j],
+                              p.sub_dw[sub] + p.tap_dw[a_tap[j]],
+                              h0 * p.x_estride + p.sub_dh[sub] + p.tap_dh[a_tap[j]], xb0);
+            for (int j = 0; j < p.n_atoms; ++j)
+              tc::tma_load_4d(s + (2 + j) * ATOM_BYTES, &p.tmap_dy, &full_bar[stage], p.sub_dyc[sub] + j * 64, 0,
+                              h0, b0);
+          }
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = tc::umma_idesc_f16(128, Nmma, 1, 1);     // both operands MN-major
       int stage = 0; uint32_t phase = 0;
       uint32_t first = 1;
@@ -531,19 +539,22 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
         tc::mbar_wait(&full_bar[stage], phase);
         tc::tc_fence_after();
         const uint32_t sa = tc::smem_u32(smem + stage * stage_bytes);
-        const uint32_t sb = sa + 2 * ATOM_BYTES;
-        for (int k = 0; k < ksteps; ++k) {
-          // MN-major SW128: 16 reduction rows per MMA = 2 groups of 8 rows (SBO = 1024 B);
-          // consecutive 64-channel atoms are ATOM_BYTES apart (LBO)
-          const uint64_t adesc = tc::umma_smem_desc(sa + k * 2048, ATOM_BYTES, 1024);
-          const uint64_t bdesc = tc::umma_smem_desc(sb + k * 2048, ATOM_BYTES, 1024);
-          tc::umma_f16(tmem_base, adesc, bdesc, idesc, first ? 0u : 1u);
-          first = 0;
+        // MN-major SW128: 16 reduction rows per MMA = 2 groups of 8 rows (SBO = 1024 B);
+        // consecutive 64-channel atoms are ATOM_BYTES apart (LBO); a K step is +2048 B = +128 in the address field
+        const uint64_t adesc0 = tc::umma_smem_desc(sa, ATOM_BYTES, 1024);
+        const uint64_t bdesc0 = tc::umma_smem_desc(sa + 2 * ATOM_BYTES, ATOM_BYTES, 1024);
+        const uint32_t accum0 = first ? 0u : 1u;           // uniform: only the very first MMA overwrites
+        if (tc::elect_one()) {
+          for (int k = 0; k < ksteps; ++k)
+            tc::umma_f16(tmem_base, adesc0 + 128 * k, bdesc0 + 128 * k, idesc, k ? 1u : accum0);
+          tc::umma_commit(&empty_bar[stage]);
         }
-        tc::umma_commit(&empty_bar[stage]);
+        __syncwarp();
+        first = 0;
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      tc::umma_commit(&tmem_full);
+      if (tc::elect_one()) tc::umma_commit(&tmem_full);
+      __syncwarp();
     }
   } else {
     const int quad = warp & 3;
@@ -690,6 +701,7 @@ extern "C" int v4l_tc_wgrad(v4l_ctx* ctx, void* stream, const v4l_tc_wgrad_args*
   if (a->defer && (ctx->n_jobs == V4L_MAX_JOBS ||
                    ctx->defer_elems - ctx->defer_cursor < (size_t)ytiles * 128 * Nmma)) {
     if (int r = v4l_tc_wgrad_flush(ctx, stream)) return r;
+    ctx->early_flush = 1;
   }
   float* region = a->defer ? ctx->defer_base + ctx->defer_cursor : ctx->scratch;
   const size_t avail = a->defer ? ctx->defer_elems - ctx->defer_cursor : ctx->scratch_elems;

@@ -199,6 +199,13 @@ class Ops:
     check(self.lib.v4l_tc_wgrad(self.h, self.ctx.stream(), C.byref(g)))
     self.launches += 1 if defer else 2
 
+  def tc_wgrad_conv1(self, x_s2d, x_idx, dy_cells, B, index, dw, dbias, out_scale=1.0, defer=True, accumulate=False):
+    """conv1 weight + bias gradient on the space-to-depth image / cell layouts (v4l_tc_wgrad_conv1)"""
+    check(self.lib.v4l_tc_wgrad_conv1(self.h, self.ctx.stream(), ptr(x_s2d), x_s2d.shape[0], ptr(x_idx), ptr(dy_cells),
+                                      B, ptr(index), ptr(dw), ptr(dbias), out_scale, 1 if defer else 0,
+                                      1 if accumulate else 0))
+    self.launches += 1 if defer else 2
+
   def tc_wgrad_flush(self):
     check(self.lib.v4l_tc_wgrad_flush(self.h, self.ctx.stream()))
     self.launches += 1
@@ -375,14 +382,15 @@ class Ops:
     self.launches += 1
 
   def opt_tail(self, phases, param=None, grad=None, m=None, v=None, n=0, hyper=None, info=None, slot=None,
-               norm_slot=-1, pack_src=None, pack_table=None, packed=None, n_pack=0, slot_advance=None):
+               norm_slot=-1, extra=(0, 0), scatter=None, packed_self=None, packed_other=None, slot_advance=None):
     """fused optimiser tail (v4l_opt_tail): phases bit 0 = split-K reduction of the deferred weight-
-    gradient partials, bit 1 = clip + Adam, bit 2 = fp16 re-pack + step / slot counters"""
+    gradient partials, bit 1 = clip + Adam + fp16 operand copies + step / slot counters"""
     a = _lib.OptTailArgs()
     a.phases = phases
     a.param, a.grad, a.m, a.v, a.n = ptr(param), ptr(grad), ptr(m), ptr(v), n
     a.hyper, a.info, a.slot, a.norm_slot = ptr(hyper), ptr(info), ptr(slot), norm_slot
-    a.pack_src, a.pack_table, a.packed, a.n_pack = ptr(pack_src), ptr(pack_table), ptr(packed), n_pack
+    a.extra_lo, a.extra_n = extra
+    a.scatter, a.packed_self, a.packed_other = ptr(scatter), ptr(packed_self), ptr(packed_other)
     a.slot_advance = ptr(slot_advance)
     check(self.lib.v4l_opt_tail(self.h, self.ctx.stream(), C.byref(a)))
     self.launches += 1

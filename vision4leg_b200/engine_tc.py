@@ -80,6 +80,7 @@ def _conv_tables(off, N, C, KH, KW, s):
 FUSED_LAYER = True
 N_WGRAD_STREAMS = 4
 FLAT_CONV1 = True
+CONV1_WGRAD_S2D = True            # conv1 weight gradient by the single-load kernel (False: generic v4l_tc_wgrad)
 
 
 class TcWeights:
@@ -255,6 +256,12 @@ class _PlanTC:
     pd = self.W.dgr[pre + "2.weight"]
     ops.tc_gemm(da2, (B, 6, 6, 64), (B, 8, 8), (8, 8, 2), [(-dx_, -dy_) for dx_, dy_ in self.taps2], 1, pd.w, pd.rows, 128,
                 None, da1c, RM(64, 64 * 128, 128, 0), mask=a1c)
+    if CONV1_WGRAD_S2D:
+      # dedicated kernel: each pixel window and each dY cell loaded once per image (csrc/tc_wgrad_s2d.cu);
+      # it is the LAST link of the backward chain, so it runs on the main stream with the whole machine
+      ops.tc_wgrad_conv1(self._imgs, self._idx, da1c, B, self.W.fwd[pre + "0.weight"].dev_table, gflat,
+                         self._view(gflat, pre + "0.bias"), out_scale=inv, defer=True)
+      return
     # conv1: per sub-position (py,px) of a cell, X is the stride-2 sub-grid of the s2d image
     subs = [(px, py, (py * 2 + px) * 32) for py in range(2) for px in range(2)]
     self._side(lambda: ops.tc_wgrad(
