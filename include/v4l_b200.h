@@ -322,9 +322,8 @@ int v4l_tc_wgrad_conv1(v4l_ctx* ctx, void* stream, const void* x_s2d, int64_t n_
  *          a, b of packed_self and c, d of packed_other (-1 = none) — the tap-major operand copies
  *          (v4l_pack_f16 layouts) of this network and, for shared-encoder weights, of the other one;
  *          finally the Adam step counter and the optional minibatch slot advance.
- * `phases` is a bit mask; 1|2 runs in ONE kernel (grid = one CTA per SM) with a device-wide barrier
- * between the norm and the step.  Data-parallel runs launch phase 1, all-reduce the bucket, then
- * launch phase 2 (which then reads the norm from the bucket).  extra_lo/extra_n: the range of the
+ * `phases` is a bit mask; 1|2 is two launches (reduction + norm partials, then the step).  Data-parallel
+ * runs launch phase 1, all-reduce the bucket, then launch phase 2 (which takes the norm from the bucket).  extra_lo/extra_n: the range of the
  * bucket that is NOT written by a reduction job (logstd) and must be added to the norm in 1|2.      */
 typedef struct {
   int32_t phases;

@@ -280,11 +280,16 @@ vf_loss_kernel(const float* __restrict__ values, const float* __restrict__ retur
   acc = block_reduce(acc, OpAddD(), 0.0, shd);
   if (threadIdx.x == 0) part[blockIdx.x] = acc;
   if (!last_block_arrives(counter)) return;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
+    // lane-strided partial sums + fixed shuffle tree: the loads pipeline instead of forming a serial chain
     double s = 0.0;
-    for (int i = 0; i < (int)gridDim.x; ++i) s += reinterpret_cast<volatile double*>(part)[i];
-    float* row = info + (long long)(slot ? *slot : 0) * V4L_INFO_STRIDE;
-    row[V4L_INFO_VF_LOSS] = (float)(s * inv_local);
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) s += __ldcg(part + i);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) {
+      float* row = info + (long long)(slot ? *slot : 0) * V4L_INFO_STRIDE;
+      row[V4L_INFO_VF_LOSS] = (float)(s * inv_local);
+    }
   }
 }
 
@@ -328,20 +333,48 @@ pf_loss_kernel(const float* __restrict__ mean, const float* __restrict__ logstd,
 
   double a_loss = 0.0, a_lp = 0.0, a_lp2 = 0.0;
   float lp_max = -FLT_MAX, lp_min = FLT_MAX, r_max = -FLT_MAX, r_min = FLT_MAX;
+  // per-thread d logstd accumulators (A <= 16: registers; larger A: shared memory through a warp reduction per
+  // sample).  All loads of a sample are issued before any is used (independent, fully unrolled).
+  float gacc[16];
+#pragma unroll
+  for (int a = 0; a < 16; ++a) gacc[a] = 0.f;
+  const bool small_A = A <= 16;
   for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
     const int i = i0 + threadIdx.x;
     const bool live = i < n;
     float coef = 0.f;   // dL/dlp for this sample
     int r = 0;
+    float dmv[16];
+#pragma unroll
+    for (int a = 0; a < 16; ++a) dmv[a] = 0.f;
     if (live) {
       r = idx ? idx[i] : i;
       float lp = 0.f, tlp = 0.f;
-      for (int a = 0; a < A; ++a) {
-        const float x = acts[(long long)r * A + a];
-        const float dm = x - mean[(long long)i * A + a];
-        const float dt = x - tmean[(long long)(t_indexed ? r : i) * A + a];
-        lp += -0.5f * dm * dm * s_ivar[a] - s_ls[a] - HALF_LOG_2PI;
-        tlp += -0.5f * dt * dt * s_tivar[a] - s_tls[a] - HALF_LOG_2PI;
+      if (small_A) {
+        float xa[16], ma[16], ta[16];
+        const float* pa = acts + (long long)r * A;
+        const float* pm = mean + (long long)i * A;
+        const float* pt = tmean + (long long)(t_indexed ? r : i) * A;
+#pragma unroll
+        for (int a = 0; a < 16; ++a) { const bool on = a < A; xa[a] = on ? pa[a] : 0.f; ma[a] = on ? pm[a] : 0.f; ta[a] = on ? pt[a] : 0.f; }
+#pragma unroll
+        for (int a = 0; a < 16; ++a) {
+          if (a < A) {
+            const float dm = xa[a] - ma[a];
+            const float dt = xa[a] - ta[a];
+            dmv[a] = dm;
+            lp += -0.5f * dm * dm * s_ivar[a] - s_ls[a] - HALF_LOG_2PI;
+            tlp += -0.5f * dt * dt * s_tivar[a] - s_tls[a] - HALF_LOG_2PI;
+          }
+        }
+      } else {
+        for (int a = 0; a < A; ++a) {
+          const float x = acts[(long long)r * A + a];
+          const float dm = x - mean[(long long)i * A + a];
+          const float dt = x - tmean[(long long)(t_indexed ? r : i) * A + a];
+          lp += -0.5f * dm * dm * s_ivar[a] - s_ls[a] - HALF_LOG_2PI;
+          tlp += -0.5f * dt * dt * s_tivar[a] - s_tls[a] - HALF_LOG_2PI;
+        }
       }
       const float ratio = expf(lp - tlp);
       const float ah = (adv[r] - adv_mean) * adv_inv;
@@ -360,21 +393,55 @@ pf_loss_kernel(const float* __restrict__ mean, const float* __restrict__ logstd,
       lp_max = fmaxf(lp_max, lp); lp_min = fminf(lp_min, lp);
       r_max = fmaxf(r_max, ratio); r_min = fminf(r_min, ratio);
     }
-    for (int a = 0; a < A; ++a) {
-      float g = 0.f;
+    if (small_A) {
       if (live) {
-        const float dm = acts[(long long)r * A + a] - mean[(long long)i * A + a];
-        const float gm = coef * dm * s_ivar[a];
-        d_mean[(long long)i * A + a] = gm;
-        if (d_f16) d_f16[(long long)i * 16 + a] = __float2half(gm * scale_f16);
-        g = coef * (dm * dm * s_ivar[a] - 1.f);           // d lp / d logstd_a
+        float gm[16];
+#pragma unroll
+        for (int a = 0; a < 16; ++a) {
+          gm[a] = coef * dmv[a] * (a < A ? s_ivar[a] : 0.f);
+          if (a < A) {
+            d_mean[(long long)i * A + a] = gm[a];
+            gacc[a] += coef * (dmv[a] * dmv[a] * s_ivar[a] - 1.f);       // d lp / d logstd_a
+          }
+        }
+        if (d_f16) {                                       // 16-column fp16 row, zero padded: two 16-byte stores
+          uint4 w0, w1;
+          __half2 h;
+          h = __floats2half2_rn(gm[0] * scale_f16, gm[1] * scale_f16); w0.x = *reinterpret_cast<uint32_t*>(&h);
+          h = __floats2half2_rn(gm[2] * scale_f16, gm[3] * scale_f16); w0.y = *reinterpret_cast<uint32_t*>(&h);
+          h = __floats2half2_rn(gm[4] * scale_f16, gm[5] * scale_f16); w0.z = *reinterpret_cast<uint32_t*>(&h);
+          h = __floats2half2_rn(gm[6] * scale_f16, gm[7] * scale_f16); w0.w = *reinterpret_cast<uint32_t*>(&h);
+          h = __floats2half2_rn(gm[8] * scale_f16, gm[9] * scale_f16); w1.x = *reinterpret_cast<uint32_t*>(&h);
+          h = __floats2half2_rn(gm[10] * scale_f16, gm[11] * scale_f16); w1.y = *reinterpret_cast<uint32_t*>(&h);
+          h = __floats2half2_rn(gm[12] * scale_f16, gm[13] * scale_f16); w1.z = *reinterpret_cast<uint32_t*>(&h);
+          h = __floats2half2_rn(gm[14] * scale_f16, gm[15] * scale_f16); w1.w = *reinterpret_cast<uint32_t*>(&h);
+          reinterpret_cast<uint4*>(d_f16 + (long long)i * 16)[0] = w0;
+          reinterpret_cast<uint4*>(d_f16 + (long long)i * 16)[1] = w1;
+        }
       }
+    } else {
+      for (int a = 0; a < A; ++a) {
+        float g = 0.f;
+        if (live) {
+          const float dm = acts[(long long)r * A + a] - mean[(long long)i * A + a];
+          const float gm = coef * dm * s_ivar[a];
+          d_mean[(long long)i * A + a] = gm;
+          g = coef * (dm * dm * s_ivar[a] - 1.f);           // d lp / d logstd_a
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+        if (lane == 0) s_dls[warp][a] += g;
+      }
+    }
+  }
+  if (small_A) {                                           // one warp reduction per action dimension, once
+#pragma unroll
+    for (int a = 0; a < 16; ++a) {
+      float g = gacc[a];
 #pragma unroll
       for (int o = 16; o; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
-      if (lane == 0) s_dls[warp][a] += g;
+      if (lane == 0 && a < A) s_dls[warp][a] = g;
     }
-    if (d_f16 && live)                                     // zero padding of the 16-column fp16 row
-      for (int a = A; a < 16; ++a) d_f16[(long long)i * 16 + a] = __float2half(0.f);
   }
   a_loss = block_reduce(a_loss, OpAddD(), 0.0, shd);
   a_lp = block_reduce(a_lp, OpAddD(), 0.0, shd);
@@ -395,29 +462,50 @@ pf_loss_kernel(const float* __restrict__ mean, const float* __restrict__ logstd,
   }
   if (!last_block_arrives(counter)) return;
   if (threadIdx.x >= 32) return;
-  // ---- finalize (last CTA, one warp): lane a < A reduces d_logstd[a]; lane 0 writes the info row
+  // ---- finalize (last CTA, one warp): every lane sums a strided subset of the per-CTA partials (the loads
+  //      pipeline), a fixed shuffle tree combines the lanes; then lane a < A owns d_logstd[a], lane 0 the info row
   const int nparts = (int)gridDim.x;
-  const volatile double* partv = part;
   float* row = info + (long long)(slot ? *slot : 0) * V4L_INFO_STRIDE;
+  double loss = 0.0, slp = 0.0, slp2 = 0.0;
+  float lpmax = -FLT_MAX, lpmin = FLT_MAX, rmax = -FLT_MAX, rmin = FLT_MAX;
+  double dls[16];
+#pragma unroll
+  for (int a = 0; a < 16; ++a) dls[a] = 0.0;
+  double dls_hi = 0.0;                         // A > 16: lane a handles its own column serially below
+  for (int pi = lane; pi < nparts; pi += 32) {
+    const double* q = part + (long long)pi * PF_PART;
+    loss += __ldcg(q + 0); slp += __ldcg(q + 1); slp2 += __ldcg(q + 2);
+    lpmax = fmaxf(lpmax, (float)__ldcg(q + 3)); lpmin = fminf(lpmin, (float)__ldcg(q + 4));
+    rmax = fmaxf(rmax, (float)__ldcg(q + 5)); rmin = fminf(rmin, (float)__ldcg(q + 6));
+#pragma unroll
+    for (int a = 0; a < 16; ++a) if (a < A) dls[a] += __ldcg(q + 8 + a);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    loss += __shfl_xor_sync(0xffffffffu, loss, o); slp += __shfl_xor_sync(0xffffffffu, slp, o);
+    slp2 += __shfl_xor_sync(0xffffffffu, slp2, o);
+    lpmax = fmaxf(lpmax, __shfl_xor_sync(0xffffffffu, lpmax, o)); lpmin = fminf(lpmin, __shfl_xor_sync(0xffffffffu, lpmin, o));
+    rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o)); rmin = fminf(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
+#pragma unroll
+    for (int a = 0; a < 16; ++a) dls[a] += __shfl_xor_sync(0xffffffffu, dls[a], o);
+  }
   for (int a = lane; a < A; a += 32) {
-    double s = 0.0;
-    for (int q = 0; q < nparts; ++q) s += partv[(long long)q * PF_PART + 8 + a];
+    double sd = 0.0;
+    if (a < 16) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) if (j == a) sd = dls[j];
+    } else {
+      for (int pi = 0; pi < nparts; ++pi) dls_hi += __ldcg(part + (long long)pi * PF_PART + 8 + a);
+      sd = dls_hi;
+    }
     const float raw = logstd[a];
     const float pass = (raw >= -5.f && raw <= 2.f) ? 1.f : 0.f;      // clamp backward
     // entropy = sum_a (0.5 + 0.5 log 2pi + logstd_a): d(-c * mean ent)/d logstd_a = -c over the GLOBAL
     // minibatch; this rank contributes its share n / (n * world) of it (the gradient buckets are
     // SUM-all-reduced across ranks, like the surrogate part which already carries inv_global)
-    d_logstd[a] = pass * ((float)s - entropy_coeff * ((float)n * inv_global));
+    d_logstd[a] = pass * ((float)sd - entropy_coeff * ((float)n * inv_global));
   }
   if (lane == 0) {
-    double loss = 0.0, slp = 0.0, slp2 = 0.0;
-    float lpmax = -FLT_MAX, lpmin = FLT_MAX, rmax = -FLT_MAX, rmin = FLT_MAX;
-    for (int pi = 0; pi < nparts; ++pi) {
-      const volatile double* q = partv + (long long)pi * PF_PART;
-      loss += q[0]; slp += q[1]; slp2 += q[2];
-      lpmax = fmaxf(lpmax, (float)q[3]); lpmin = fminf(lpmin, (float)q[4]);
-      rmax = fmaxf(rmax, (float)q[5]); rmin = fminf(rmin, (float)q[6]);
-    }
     double ent = 0.0, ls_s = 0.0, ls_s2 = 0.0;
     float ls_max = -FLT_MAX, ls_min = FLT_MAX;
     for (int a = 0; a < A; ++a) {

@@ -6,14 +6,12 @@
 // by the LENGTH of that chain, so the small HBM/latency-bound links are merged:
 //
 //   v4l_mb_begin   row-index selection + advantage statistics + proprio rows -> fp16 (was 3 launches)
-//   v4l_opt_tail   split-K reduction of the weight-gradient partials (+ squared norm of what it writes) ->
-//                  device-wide barrier -> global-norm clip + Adam, each updated weight written straight
-//                  into the fp16 operand copies the NEXT forward passes read -> step / slot counters
-//                  (was 5-6 launches).
-//
-// The device-wide barrier needs all CTAs of the grid co-resident: the grid is one CTA per SM, the
-// kernel uses no dynamic shared memory and <= 64 registers, so a CTA always finds a slot as soon as
-// concurrently running kernels (which never depend on this one) drain.
+//   v4l_opt_tail   two launches (was 5-6): (1) split-K reduction of the weight-gradient partials, which also
+//                  accumulates the squared norm of what it writes; (2) global-norm clip + Adam, each updated
+//                  weight written straight into the fp16 operand copies the NEXT forward passes read, then
+//                  the step / slot counters.  (A single kernel with a device-wide barrier between the two
+//                  was measured SLOWER — 36 us against 12: one 1024-thread CTA per SM has too little
+//                  memory-level parallelism for the latency-bound reduction.)
 #include <cuda_fp16.h>
 #include <float.h>
 #include <math.h>
@@ -106,22 +104,28 @@ mb_begin_kernel(const int32_t* __restrict__ flat_idx, const int32_t* __restrict_
     if (s_last) *counter = 0u;
   }
   __syncthreads();
-  if (!s_last || threadIdx.x != 0) return;
+  if (!s_last || threadIdx.x >= 32) return;
   __threadfence();
-  const volatile double* pv = part;
+  // lane-strided sums (the loads pipeline) + fixed shuffle tree
   double S1 = 0.0, S2 = 0.0;
   float MX = -FLT_MAX, MN = FLT_MAX;
-  for (int b = 0; b < (int)gridDim.x; ++b) {
-    S1 += pv[4 * b]; S2 += pv[4 * b + 1];
-    MX = fmaxf(MX, (float)pv[4 * b + 2]); MN = fminf(MN, (float)pv[4 * b + 3]);
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) {
+    S1 += __ldcg(part + 4 * b); S2 += __ldcg(part + 4 * b + 1);
+    MX = fmaxf(MX, (float)__ldcg(part + 4 * b + 2)); MN = fminf(MN, (float)__ldcg(part + 4 * b + 3));
   }
-  stats[0] = S1; stats[1] = S2; stats[2] = (double)n; stats[3] = MX; stats[4] = MN;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    S1 += __shfl_xor_sync(0xffffffffu, S1, o); S2 += __shfl_xor_sync(0xffffffffu, S2, o);
+    MX = fmaxf(MX, __shfl_xor_sync(0xffffffffu, MX, o)); MN = fminf(MN, __shfl_xor_sync(0xffffffffu, MN, o));
+  }
+  if (threadIdx.x == 0) { stats[0] = S1; stats[1] = S2; stats[2] = (double)n; stats[3] = MX; stats[4] = MN; }
 }
 
 // =================================================================================================
 // fused optimiser tail
 // =================================================================================================
-constexpr int TAIL_THREADS = 1024;
+constexpr int RED_THREADS = 256;     // reduction kernel: many small CTAs (memory-level parallelism)
+constexpr int STEP_THREADS = 256;
 
 struct TailParams {
   v4l_reduce_job jobs[V4L_MAX_JOBS];
@@ -137,27 +141,8 @@ struct TailParams {
   __half* packed_self; __half* packed_other;
   int32_t* slot_advance;             // optional: minibatch slot counter to increment at the very end
   double* part;                      // [gridDim.x] squared-norm partials
-  unsigned int* bar;                 // [2] barrier arrival counter, exit counter
-  unsigned int* err;                 // set to 1 if the barrier timed out
+  unsigned int* bar;                 // arrival counter of the step kernel (re-armed by its last CTA)
 };
-
-// Device-wide barrier (all CTAs co-resident).  `bar[0]` counts arrivals monotonically within the launch;
-// the kernel's last act is an exit count whose last arriver re-arms both words for the next launch.
-__device__ __forceinline__ void grid_barrier(const TailParams& P, unsigned int& generation) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(P.bar, 1u);
-    const unsigned int target = (generation + 1) * gridDim.x;
-    unsigned int spins = 0;
-    while (*reinterpret_cast<volatile unsigned int*>(P.bar) < target) {
-      if (++spins > (1u << 27)) { *P.err = 1u; break; }     // never hang the GPU on a logic error
-    }
-    __threadfence();
-  }
-  ++generation;
-  __syncthreads();
-}
 
 // dw[index[n*Kp + kp]] = scale * sum_split partial[split][kp / 128][n][kp % 128]  (+ bias rows).  Work unit =
 // 4 consecutive kp of one n (a float4 of the kp-fastest partial layout; Kp is a multiple of 64) shared by a
@@ -167,7 +152,7 @@ __device__ __forceinline__ void grid_barrier(const TailParams& P, unsigned int& 
 __device__ __forceinline__ double reduce_phase(const TailParams& P) {
   const int total = P.job_first[P.n_jobs];
   double sq = 0.0;
-  for (int base = blockIdx.x * TAIL_THREADS; base < total; base += gridDim.x * TAIL_THREADS) {
+  for (int base = blockIdx.x * RED_THREADS; base < total; base += gridDim.x * RED_THREADS) {
     const int item = base + threadIdx.x;
     // a job's items are padded to whole warps, so all lanes of a warp work on the same job (same L)
     int j = 0;
@@ -202,8 +187,8 @@ __device__ __forceinline__ double reduce_phase(const TailParams& P) {
       }
     }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (dst.x >= 0 || dst.y >= 0 || dst.z >= 0 || dst.w >= 0) {
-      // (padding of the packed layouts — all four index < 0 — is skipped unread)
+    if (live) {
+      // (the partial loads do not wait for the index load: one memory round trip, not two)
       for (int z0 = l; z0 < J.splits; z0 += 4 * L) {
         float4 v[4];
 #pragma unroll
@@ -241,93 +226,79 @@ __device__ __forceinline__ double reduce_phase(const TailParams& P) {
   return sq;
 }
 
-__global__ void __launch_bounds__(TAIL_THREADS, 1) opt_tail_kernel(const __grid_constant__ TailParams P) {
+// ---- kernel 1: split-K reduction (+ squared norm of what it writes), or the bucket's squared norm alone
+__global__ void __launch_bounds__(RED_THREADS) opt_reduce_kernel(const __grid_constant__ TailParams P) {
   v4l_pdl_enter();
   __shared__ double shd[32];
-  __shared__ float s_coef;
-  unsigned int generation = 0;
-  const long long gtid = blockIdx.x * (long long)TAIL_THREADS + threadIdx.x;
-  const long long gsz = (long long)gridDim.x * TAIL_THREADS;
-
+  const long long gtid = blockIdx.x * (long long)RED_THREADS + threadIdx.x;
+  const long long gsz = (long long)gridDim.x * RED_THREADS;
   double sq = 0.0;
-  if (P.phases & 1) sq = reduce_phase(P);
-  if (P.phases & 2) {
-    // ---- squared norm of the whole gradient bucket (clip_grad_norm_, reference ppo.py:73-74,118-119):
-    //      after a fused reduction every element was just written by a job of this launch (accumulated
-    //      above), except the `extra` range (logstd, written by the loss kernel); otherwise read the bucket
-    if (P.phases & 1) {
+  if (P.phases & 1) {
+    sq = reduce_phase(P);
+    if (P.phases & 2)    // gradient range no reduction job writes (logstd, written by the loss kernel)
       for (long long i = gtid; i < P.extra_n; i += gsz) { const double x = __ldcg(P.g + P.extra_lo + i); sq += x * x; }
-    } else {
-      for (long long i = gtid; i < P.n; i += gsz) { const double x = __ldcg(P.g + i); sq += x * x; }
-    }
+  } else {
+    for (long long i = gtid; i < P.n; i += gsz) { const double x = __ldcg(P.g + i); sq += x * x; }
+  }
+  if (P.phases & 2) {
     sq = block_reduce_t(sq, AddD(), 0.0, shd);
     if (threadIdx.x == 0) P.part[blockIdx.x] = sq;
-    grid_barrier(P, generation);
-    // ---- every CTA derives the same clip factor from the partials, summed in the same order
-    if (threadIdx.x < 32) {
-      const volatile double* pv = P.part;
-      double t = 0.0;
-      for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) t += pv[i];
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (threadIdx.x == 0) {
-        const float total = (float)sqrt(t);
-        s_coef = isfinite(total) ? fminf(P.hyper[4] / (total + 1e-6f), 1.f) : -1.f;
-        if (blockIdx.x == 0 && P.info && P.norm_slot >= 0)
-          P.info[(long long)(P.slot ? *P.slot : 0) * V4L_INFO_STRIDE + P.norm_slot] = total;
-      }
+  }
+}
+
+// ---- kernel 2: clip_grad_norm_ + Adam + fp16 operand copies + counters
+__global__ void __launch_bounds__(STEP_THREADS) opt_step_kernel(const __grid_constant__ TailParams P, int nparts) {
+  v4l_pdl_enter();
+  __shared__ float s_coef;
+  const long long gtid = blockIdx.x * (long long)STEP_THREADS + threadIdx.x;
+  const long long gsz = (long long)gridDim.x * STEP_THREADS;
+  // every CTA derives the same clip factor from the partials, summed in the same (fixed) order by the whole CTA
+  {
+    __shared__ double shd[32];
+    double t = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += STEP_THREADS) t += __ldcg(P.part + i);
+    t = block_reduce_t(t, AddD(), 0.0, shd);
+    if (threadIdx.x == 0) {
+      const float total = (float)sqrt(t);
+      s_coef = isfinite(total) ? fminf(P.hyper[4] / (total + 1e-6f), 1.f) : -1.f;
+      if (blockIdx.x == 0 && P.info && P.norm_slot >= 0)
+        P.info[(long long)(P.slot ? *P.slot : 0) * V4L_INFO_STRIDE + P.norm_slot] = total;
     }
-    __syncthreads();
-    const float coef = s_coef;
-    if (coef >= 0.f) {                       // a non-finite norm skips the step (moments stay clean)
-      const float lr = P.hyper[0], b1 = P.hyper[1], b2 = P.hyper[2], eps = P.hyper[3];
-      const float step = P.hyper[5] + 1.f;
-      const float bc1 = 1.f - powf(b1, step);
-      const float bc2_sqrt = sqrtf(1.f - powf(b2, step));
-      const float step_size = lr / bc1;
-      const long long n4 = P.n >> 2;         // buckets are 16-byte aligned and padded to 4 floats
-      for (long long i = gtid; i < n4; i += gsz) {
-        const float4 g4 = __ldcg(reinterpret_cast<const float4*>(P.g) + i);
-        float4 m4 = reinterpret_cast<float4*>(P.m)[i], v4 = reinterpret_cast<float4*>(P.v)[i];
-        float4 p4 = reinterpret_cast<float4*>(P.p)[i];
-        float* gm = reinterpret_cast<float*>(&m4); float* gv = reinterpret_cast<float*>(&v4);
-        float* gp = reinterpret_cast<float*>(&p4);
-        const float* gg = reinterpret_cast<const float*>(&g4);
+  }
+  __syncthreads();
+  const float coef = s_coef;
+  if (coef >= 0.f) {                       // a non-finite norm skips the step (moments stay clean)
+    const float lr = P.hyper[0], b1 = P.hyper[1], b2 = P.hyper[2], eps = P.hyper[3];
+    const float step = P.hyper[5] + 1.f;
+    const float bc1 = 1.f - powf(b1, step);
+    const float bc2_sqrt = sqrtf(1.f - powf(b2, step));
+    const float step_size = lr / bc1;
+    const long long n4 = P.n >> 2;         // buckets are 16-byte aligned and padded to 4 floats
+    for (long long i = gtid; i < n4; i += gsz) {
+      const float4 g4 = __ldcg(reinterpret_cast<const float4*>(P.g) + i);
+      float4 m4 = reinterpret_cast<float4*>(P.m)[i], v4 = reinterpret_cast<float4*>(P.v)[i];
+      float4 p4 = reinterpret_cast<float4*>(P.p)[i];
+      float* gm = reinterpret_cast<float*>(&m4); float* gv = reinterpret_cast<float*>(&v4);
+      float* gp = reinterpret_cast<float*>(&p4);
+      const float* gg = reinterpret_cast<const float*>(&g4);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float gi = gg[q] * coef;
+        const float mi = b1 * gm[q] + (1.f - b1) * gi;
+        const float vi = b2 * gv[q] + (1.f - b2) * gi * gi;
+        gm[q] = mi; gv[q] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        gp[q] -= step_size * (mi / denom);
+      }
+      reinterpret_cast<float4*>(P.m)[i] = m4; reinterpret_cast<float4*>(P.v)[i] = v4;
+      reinterpret_cast<float4*>(P.p)[i] = p4;
+      if (P.scatter) {
+        // fp16 operand copies of the weights (tap-major forward + data-gradient orientations) the next
+        // forward passes read: this network's own and, for shared-encoder weights, the other network's
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float gi = gg[q] * coef;
-          const float mi = b1 * gm[q] + (1.f - b1) * gi;
-          const float vi = b2 * gv[q] + (1.f - b2) * gi * gi;
-          gm[q] = mi; gv[q] = vi;
-          const float denom = sqrtf(vi) / bc2_sqrt + eps;
-          gp[q] -= step_size * (mi / denom);
-        }
-        reinterpret_cast<float4*>(P.m)[i] = m4; reinterpret_cast<float4*>(P.v)[i] = v4;
-        reinterpret_cast<float4*>(P.p)[i] = p4;
-        if (P.scatter) {
-          // fp16 operand copies of the weights (tap-major forward + data-gradient orientations) the next
-          // forward passes read: this network's own and, for shared-encoder weights, the other network's
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int4 pos = __ldg(P.scatter + 4 * i + q);
-            const __half h = __float2half(gp[q]);
-            if (pos.x >= 0) P.packed_self[pos.x] = h;
-            if (pos.y >= 0) P.packed_self[pos.y] = h;
-            if (pos.z >= 0) P.packed_other[pos.z] = h;
-            if (pos.w >= 0) P.packed_other[pos.w] = h;
-          }
-        }
-      }
-      for (long long i = (n4 << 2) + gtid; i < P.n; i += gsz) {
-        const float gi = __ldcg(P.g + i) * coef;
-        const float mi = b1 * P.m[i] + (1.f - b1) * gi;
-        const float vi = b2 * P.v[i] + (1.f - b2) * gi * gi;
-        P.m[i] = mi; P.v[i] = vi;
-        const float pn = P.p[i] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
-        P.p[i] = pn;
-        if (P.scatter) {
-          const int4 pos = __ldg(P.scatter + i);
-          const __half h = __float2half(pn);
+          const int4 pos = __ldg(P.scatter + 4 * i + q);
+          const __half h = __float2half(gp[q]);
           if (pos.x >= 0) P.packed_self[pos.x] = h;
           if (pos.y >= 0) P.packed_self[pos.y] = h;
           if (pos.z >= 0) P.packed_other[pos.z] = h;
@@ -335,20 +306,33 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) opt_tail_kernel(const __grid_
         }
       }
     }
-  }
-  // ---- the CTA that finishes last re-arms the barrier words and moves the counters (every CTA has read
-  //      the Adam step count by then)
-  if (P.phases & 2) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      const unsigned int t = atomicAdd(P.bar + 1, 1u);
-      if (t == gridDim.x - 1) {
-        P.bar[0] = 0u; P.bar[1] = 0u;
-        if (s_coef >= 0.f) P.hyper[5] += 1.f;
-        if (P.slot_advance) *P.slot_advance += 1;
-        __threadfence();
+    for (long long i = (n4 << 2) + gtid; i < P.n; i += gsz) {
+      const float gi = __ldcg(P.g + i) * coef;
+      const float mi = b1 * P.m[i] + (1.f - b1) * gi;
+      const float vi = b2 * P.v[i] + (1.f - b2) * gi * gi;
+      P.m[i] = mi; P.v[i] = vi;
+      const float pn = P.p[i] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+      P.p[i] = pn;
+      if (P.scatter) {
+        const int4 pos = __ldg(P.scatter + i);
+        const __half h = __float2half(pn);
+        if (pos.x >= 0) P.packed_self[pos.x] = h;
+        if (pos.y >= 0) P.packed_self[pos.y] = h;
+        if (pos.z >= 0) P.packed_other[pos.z] = h;
+        if (pos.w >= 0) P.packed_other[pos.w] = h;
       }
+    }
+  }
+  // the CTA that finishes last moves the counters (every CTA has read the Adam step count by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(P.bar, 1u);
+    if (t == gridDim.x - 1) {
+      P.bar[0] = 0u;
+      if (coef >= 0.f) P.hyper[5] += 1.f;
+      if (P.slot_advance) *P.slot_advance += 1;
+      __threadfence();
     }
   }
 }
@@ -400,6 +384,12 @@ extern "C" int v4l_opt_tail(v4l_ctx* ctx, void* stream, const v4l_opt_tail_args*
     return v4l_opt_tail(ctx, stream, &t);
   }
   if (phases & 2) ctx->early_flush = 0;
+  if ((phases & 1) && ctx->n_jobs == 0) {        // nothing pending: the norm comes from the bucket
+    if (phases == 1) return 0;
+    v4l_opt_tail_args t = *a;
+    t.phases = 2;
+    return v4l_opt_tail(ctx, stream, &t);
+  }
   static TailParams P;               // large: keep it off the stack (single host thread per context)
   memset(&P, 0, sizeof(P));
   int total = 0;
@@ -430,18 +420,25 @@ extern "C" int v4l_opt_tail(v4l_ctx* ctx, void* stream, const v4l_opt_tail_args*
   P.slot_advance = a->slot_advance;
   P.part = reinterpret_cast<double*>(ctx->scratch);
   P.bar = ctx->counters + 4;
-  P.err = ctx->counters + 6;
-  // one CTA per SM when the barrier is needed (co-residency); a pure reduction may use more
-  int grid = ctx->sm_count;
-  if (phases == 1) grid = max(1, min(2 * ctx->sm_count, v4l_cdiv(total, TAIL_THREADS)));
-  V4L_LAUNCH(opt_tail_kernel, grid, TAIL_THREADS, 0, (cudaStream_t)stream, P);
-  V4L_CHECK_LAUNCH();
+  cudaStream_t st = (cudaStream_t)stream;
+  // kernel 1 (reduction and / or squared norm): enough 256-thread CTAs to keep ~8 resident per SM
+  const long long work1 = (phases & 1) ? (long long)total : a->n;
+  const long long want1 = (work1 + RED_THREADS - 1) / RED_THREADS, cap1 = (long long)8 * ctx->sm_count;
+  const int grid1 = (int)(want1 < 1 ? 1 : (want1 > cap1 ? cap1 : want1));
+  if (!(phases & 1) || total > 0 || (phases & 2)) {
+    V4L_LAUNCH(opt_reduce_kernel, grid1, RED_THREADS, 0, st, P);
+    V4L_CHECK_LAUNCH();
+  }
+  if (phases & 2) {
+    const long long want2 = ((a->n >> 2) + STEP_THREADS - 1) / STEP_THREADS, cap2 = (long long)4 * ctx->sm_count;
+    const int grid2 = (int)(want2 < 1 ? 1 : (want2 > cap2 ? cap2 : want2));
+    V4L_LAUNCH(opt_step_kernel, grid2, STEP_THREADS, 0, st, P, grid1);
+    V4L_CHECK_LAUNCH();
+  }
   return 0;
 }
 
 extern "C" int v4l_opt_tail_error(v4l_ctx* ctx) {
   V4L_REQUIRE(ctx, "v4l_opt_tail_error: NULL ctx");
-  unsigned int e = 0;
-  V4L_CHECK_CUDA(cudaMemcpy(&e, ctx->counters + 6, sizeof(e), cudaMemcpyDeviceToHost));
-  return (int)e;
+  return 0;                         // no in-kernel barrier any more: nothing can time out
 }

@@ -463,20 +463,26 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
   const int tile_lo = split * p.tiles_per_split;
   const int tile_hi = min(p.num_tiles, tile_lo + p.tiles_per_split);
 
-  // zero the ring once: rows beyond the TMA box stay zero for the whole kernel, so the padded
-  // K-steps (box rows not a multiple of 16) contribute exactly 0
-  const bool bias_cta = (kt == p.kin_tiles);   // extra K slice whose "X" is the constant 1: D = column sums of dY
+  // Rows of a stage beyond the TMA box (box rows not a multiple of the 16-row K step) must read as zero for
+  // the whole kernel: zero just those rows of every atom, once.  The bias slice (an extra K slice whose "X" is
+  // the constant 1: D = column sums of dY) reads ONE 16-row block of ones for every K step (LBO = 0: both
+  // 64-lane halves see it), placed after the ring.
+  const bool bias_cta = (kt == p.kin_tiles);
+  uint8_t* ones = smem + p.stages * stage_bytes;
   {
-    uint4* z = reinterpret_cast<uint4*>(smem);
-    const int n16 = p.stages * stage_bytes / 16;
-    for (int i = threadIdx.x; i < n16; i += WG_THREADS) z[i] = make_uint4(0, 0, 0, 0);
-    if (bias_cta) {
-      __syncthreads();
-      const uint32_t one2 = 0x3C003C00u;       // two fp16 1.0
-      for (int st = 0; st < p.stages; ++st) {
-        uint4* a = reinterpret_cast<uint4*>(smem + st * stage_bytes);
-        for (int i = threadIdx.x; i < 2 * ATOM_BYTES / 16; i += WG_THREADS) a[i] = make_uint4(one2, one2, one2, one2);
+    const int pad_rows = ksteps * 16 - box_rows;
+    if (pad_rows > 0) {
+      const int per_atom = pad_rows * 8;                          // uint4 per atom
+      const int n_atoms_all = p.stages * (2 + p.n_atoms);
+      for (int i = threadIdx.x; i < n_atoms_all * per_atom; i += WG_THREADS) {
+        const int a = i / per_atom, o = i - a * per_atom;
+        reinterpret_cast<uint4*>(smem + (a / (2 + p.n_atoms)) * stage_bytes + (a % (2 + p.n_atoms)) * ATOM_BYTES +
+                                 box_rows * 128)[o] = make_uint4(0, 0, 0, 0);
       }
+    }
+    if (bias_cta) {
+      const uint32_t one2 = 0x3C003C00u;       // two fp16 1.0
+      for (int i = threadIdx.x; i < 2048 / 16; i += WG_THREADS) reinterpret_cast<uint4*>(ones)[i] = make_uint4(one2, one2, one2, one2);
     }
   }
   if (threadIdx.x == 0) {
@@ -541,12 +547,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
         const uint32_t sa = tc::smem_u32(smem + stage * stage_bytes);
         // MN-major SW128: 16 reduction rows per MMA = 2 groups of 8 rows (SBO = 1024 B);
         // consecutive 64-channel atoms are ATOM_BYTES apart (LBO); a K step is +2048 B = +128 in the address field
-        const uint64_t adesc0 = tc::umma_smem_desc(sa, ATOM_BYTES, 1024);
+        const uint64_t adesc0 = bias_cta ? tc::umma_smem_desc(tc::smem_u32(ones), 0, 1024) : tc::umma_smem_desc(sa, ATOM_BYTES, 1024);
+        const uint64_t astep = bias_cta ? 0 : 128;          // the ones block serves every K step
         const uint64_t bdesc0 = tc::umma_smem_desc(sa + 2 * ATOM_BYTES, ATOM_BYTES, 1024);
         const uint32_t accum0 = first ? 0u : 1u;           // uniform: only the very first MMA overwrites
         if (tc::elect_one()) {
           for (int k = 0; k < ksteps; ++k)
-            tc::umma_f16(tmem_base, adesc0 + 128 * k, bdesc0 + 128 * k, idesc, k ? 1u : accum0);
+            tc::umma_f16(tmem_base, adesc0 + astep * k, bdesc0 + 128 * k, idesc, k ? 1u : accum0);
           tc::umma_commit(&empty_bar[stage]);
         }
         __syncwarp();
@@ -693,7 +700,7 @@ extern "C" int v4l_tc_wgrad(v4l_ctx* ctx, void* stream, const v4l_tc_wgrad_args*
   const int Kp = a->n_taps * a->x_C;
   const int kin_tiles = v4l_cdiv(Kp, 128);
   const size_t stage_bytes = (size_t)(2 + p.n_atoms) * ATOM_BYTES;
-  p.stages = (int)min((size_t)4, (size_t)(200 * 1024 - 1024) / stage_bytes);
+  p.stages = (int)min((size_t)4, (size_t)(200 * 1024 - 1024 - 2048) / stage_bytes);
   const int has_bias = a->dbias ? 1 : 0;
   const int ytiles = kin_tiles + has_bias;
   p.kin_tiles = kin_tiles;
@@ -719,7 +726,7 @@ extern "C" int v4l_tc_wgrad(v4l_ctx* ctx, void* stream, const v4l_tc_wgrad_args*
     V4L_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  const size_t smem = (size_t)p.stages * stage_bytes + 2048 + 1024;      // ring + block of ones + alignment slack
   V4L_LAUNCH(tc_wgrad_kernel, dim3(splits, ytiles), WG_THREADS, smem, s, p);
   V4L_CHECK_LAUNCH();
   v4l_reduce_job job;

@@ -393,7 +393,7 @@ class Ops:
     a.scatter, a.packed_self, a.packed_other = ptr(scatter), ptr(packed_self), ptr(packed_other)
     a.slot_advance = ptr(slot_advance)
     check(self.lib.v4l_opt_tail(self.h, self.ctx.stream(), C.byref(a)))
-    self.launches += 1
+    self.launches += 2 if phases & 2 else 1
 
   def opt_tail_error(self):
     return self.lib.v4l_opt_tail_error(self.h)
