@@ -21,8 +21,8 @@ def main():
   ap.add_argument("--A", type=int, default=12)
   ap.add_argument("--precision", default="f16")
   args = ap.parse_args()
-  from oracle import synth
-  from tests._harness import build_nets, load_np_sd, make_ppo
+  from benchutil import synth
+  from benchutil.harness import build_nets, load_np_sd, make_ppo
   E = 8
   T = args.batch // E * args.minibatches
   pf, vf = build_nets(args.model, args.S, args.A)

@@ -17,8 +17,8 @@ def main():
   ap.add_argument("--batch", type=int, default=1024)
   ap.add_argument("--minibatches", type=int, default=8)
   args = ap.parse_args()
-  from oracle import synth
-  from tests._harness import build_nets, load_np_sd, make_ppo
+  from benchutil import synth
+  from benchutil.harness import build_nets, load_np_sd, make_ppo
   E, S, A = 8, 93, 12
   T = args.batch // E * args.minibatches
   pf, vf = build_nets(args.model, S, A)

@@ -201,9 +201,12 @@ class PPOUpdateEngine:
     r = dict(T=T, E=E, N=N, state=f(N, self.S), acts=f(N, self.A), values=f(N), rewards=f(N),
              terminals=f(N), advs=f(N), rets=f(N), last_value=f(E))
     if self.has_img:
-      r["img"] = f(N, engine.IMG_ELEMS)
       if self.precision == "f16":
+        # the tensor-core tier keeps only the fp16 space-to-depth image (32 KB / transition: a 2^20-transition
+        # sweep is 34 GB); fp32 rows pass through a bounded staging chunk on the way in (_copy_obs_rows)
         r["imgs"] = torch.empty((N, 16, 16, 64), device=dev, dtype=torch.float16)
+      else:
+        r["img"] = f(N, engine.IMG_ELEMS)
     if self.precision == "f16":
       r["tmean_all"] = f(N, self.A)        # target-policy action means, filled during the first opt-epoch
     self._roll = r
@@ -235,8 +238,6 @@ class PPOUpdateEngine:
         self._pending_half = (host["obs_img16"], host["obs_state"])
     else:
       self._copy_obs_rows(obs, D, 0, T * E)
-      if self.precision == "f16" and self.has_img:
-        self.ops.ingest_img(r["img"], r["imgs"], T * E)     # fp32 CHW -> fp16 space-to-depth NHWC
     self.h2d_bytes = T * E * D * 4
     if self._pending_half is not None:
       self.h2d_bytes = T * E * (engine.IMG_ELEMS * 2 + self.S * 4)
@@ -258,7 +259,17 @@ class PPOUpdateEngine:
     base = obs.data_ptr() + n0 * D * 4
     if self.S:
       self.ops.h2d_2d(r["state"][n0:], self.S * 4, base, D * 4, self.S * 4, n)
-    if self.has_img:
+    if self.has_img and self.precision == "f16":
+      # fp32 CHW rows -> bounded staging chunk -> fp16 space-to-depth NHWC (v4l_ingest_img)
+      chunk = min(n, 4096)
+      stage = r.get("img_stage")
+      if stage is None or stage.shape[0] < chunk:
+        stage = r["img_stage"] = torch.empty((chunk, engine.IMG_ELEMS), device=self.device, dtype=torch.float32)
+      for c0 in range(0, n, chunk):
+        m = min(chunk, n - c0)
+        self.ops.h2d_2d(stage, engine.IMG_ELEMS * 4, base + (c0 * D + self.S) * 4, D * 4, engine.IMG_ELEMS * 4, m)
+        self.ops.ingest_img(stage, r["imgs"][n0 + c0:], m)
+    elif self.has_img:
       self.ops.h2d_2d(r["img"][n0:], engine.IMG_ELEMS * 4, base + self.S * 4, D * 4, engine.IMG_ELEMS * 4, n)
 
   def _stream_chunk(self, obs, D, trows, E, k, rows):
@@ -576,8 +587,6 @@ class PPOUpdateEngine:
           self.h2d_bytes += T * E * D * 4 - T * E * (engine.IMG_ELEMS * 2 + self.S * 4)
           self._pending_half = None
         self._copy_obs_rows(obs, D, 0, T * E)
-        if self.precision == "f16" and self.has_img:
-          self.ops.ingest_img(r["img"], r["imgs"], T * E)
       self._run_ragged(flat, T, E, rows)
     info = self._info[:n_mb, :len(INFO_KEYS)].cpu().numpy()
     self.d2h_bytes = info.nbytes

@@ -77,6 +77,28 @@ class Ops:
     self.h = self.ctx.handle
     self.device = self.ctx.device
     self.launches = 0     # kernel launches issued through this object (bench `gpu_launches`)
+    self._rec = None      # when a list: (entry point, argument struct copy, FLOPs) of the tensor-core launches,
+                          # so that a profiler / bench.py can replay a kernel family on its own (record())
+
+  def record(self, on=True):
+    """start (returns nothing) / stop (returns the list) recording tensor-core launches for replay()"""
+    if on:
+      self._rec = []
+      return None
+    rec, self._rec = self._rec, None
+    return rec
+
+  def _note(self, fn, g, flops, keep=()):
+    if self._rec is not None:
+      self._rec.append((fn, type(g).from_buffer_copy(g), float(flops), keep))
+
+  def replay(self, rec):
+    """re-issue recorded launches on the current stream (same arguments, same buffers)"""
+    for fn, g, _, _ in rec:
+      if isinstance(g, tuple):
+        check(getattr(self.lib, fn)(self.h, self.ctx.stream(), *g))
+      else:
+        check(getattr(self.lib, fn)(self.h, self.ctx.stream(), C.byref(g)))
 
   # ---- side stream: independent work (weight gradients, frozen-target forward) leaves the
   #      critical path; under CUDA-graph capture this becomes a parallel branch of the graph
@@ -156,6 +178,8 @@ class Ops:
     g.mask, g.flags, g.res = ptr(mask), flags, ptr(res)
     check(self.lib.v4l_tc_gemm(self.h, self.ctx.stream(), C.byref(g)))
     self.launches += 1
+    self._note("v4l_tc_gemm", g, 2.0 * out_grid[0] * out_grid[1] * out_grid[2] * N_valid * len(taps) *
+               min(a_shape[3], kchunks * 64))
 
   def tc_conv_flat(self, x, C_, P, Wg, Hout, Wout, taps, w, N_pad, N_valid, bias, c, c_map, n_img, x_idx=None,
                    flags=0, mode=0):
@@ -170,10 +194,11 @@ class Ops:
     g.c, g.c_map, g.n_img, g.x_idx, g.flags, g.mode = ptr(c), c_map.c(), n_img, ptr(x_idx), flags, mode
     check(self.lib.v4l_tc_conv_flat(self.h, self.ctx.stream(), C.byref(g)))
     self.launches += 1
+    self._note("v4l_tc_conv_flat", g, 2.0 * n_img * Hout * Wout * N_valid * len(taps) * C_)
 
   def tc_wgrad(self, x, x_shape, dy, dy_C, out_grid, box, taps, N_valid, index, dw, x_idx=None,
                x_estride=1, subs=None, dy_strides=None, dy_off=0, x_strides=None, out_scale=1.0,
-               dbias=None, defer=False):
+               dbias=None, defer=False, algo_flops=None):
     """subs: [(sub_dw, sub_dh, dy_channel_offset)] sub-iterations per tile (space-to-depth cells)"""
     g = TcWgradArgs()
     g.x = ptr(x)
@@ -198,6 +223,9 @@ class Ops:
     g.dbias, g.defer = ptr(dbias), 1 if defer else 0
     check(self.lib.v4l_tc_wgrad(self.h, self.ctx.stream(), C.byref(g)))
     self.launches += 1 if defer else 2
+    if algo_flops is None:       # dW: 2 x rows x K x N (+ db); algo_flops overrides it (LayerNorm affine: diagonal only)
+      algo_flops = 2.0 * out_grid[0] * out_grid[1] * out_grid[2] * N_valid * (len(taps) * x_shape[3] + 1)
+    self._note("v4l_tc_wgrad", g, algo_flops)
 
   def tc_wgrad_conv1(self, x_s2d, x_idx, dy_cells, B, index, dw, dbias, out_scale=1.0, defer=True, accumulate=False):
     """conv1 weight + bias gradient on the space-to-depth image / cell layouts (v4l_tc_wgrad_conv1)"""
@@ -205,6 +233,10 @@ class Ops:
                                       B, ptr(index), ptr(dw), ptr(dbias), out_scale, 1 if defer else 0,
                                       1 if accumulate else 0))
     self.launches += 1 if defer else 2
+    if self._rec is not None:          # replayed through a closure (plain-argument entry point)
+      args = (ptr(x_s2d), x_s2d.shape[0], ptr(x_idx), ptr(dy_cells), B, ptr(index), ptr(dw), ptr(dbias), out_scale,
+              1 if defer else 0, 1 if accumulate else 0)
+      self._rec.append(("v4l_tc_wgrad_conv1", args, 2.0 * B * 225 * 32 * 257, ()))
 
   def tc_wgrad_flush(self):
     check(self.lib.v4l_tc_wgrad_flush(self.h, self.ctx.stream()))
@@ -262,6 +294,7 @@ class Ops:
       setattr(a, k, ptr(out.get(k)))
     check(self.lib.v4l_tc_block_fwd(self.h, self.ctx.stream(), C.byref(a)))
     self.launches += 1
+    self._note("v4l_tc_block_fwd", a, B * (2.0 * T * 64 * (192 + 64 + 256 + 256) + 4.0 * T * T * 64))
 
   def tc_block_bwd(self, dy, B, T, saved, w, g1, g2, out):
     """Fused data-gradient pass of one encoder layer (v4l_tc_block_bwd). saved: qkv, xh1, xh2, f1, p,
@@ -278,6 +311,8 @@ class Ops:
       setattr(a, k, ptr(out[k]))
     check(self.lib.v4l_tc_block_bwd(self.h, self.ctx.stream(), C.byref(a)))
     self.launches += 1
+    # data gradients only: the four projections + dP, dQ, dK, dV (the weight gradients are separate launches)
+    self._note("v4l_tc_block_bwd", a, B * (2.0 * T * 64 * (192 + 64 + 256 + 256) + 8.0 * T * T * 64))
 
   def attn_bwd_f16(self, qkv, p, d_o, d_qkv, B, T, d, nh):
     if nh == 1 and d == 64:

@@ -400,7 +400,8 @@ class LocoPlanTC(_PlanTC):
     for norm, xh, dyn in (("norm2", Ly["xh2"], dy), ("norm1", Ly["xh1"], g["dh"])):
       self._side(lambda: ops.tc_wgrad(
         xh, (R, 1, 1, d), dyn, d, (R, 1, 1), (1, 1, 128), [(0, 0)], d, self._diag_table(p + norm + ".weight"),
-        gflat, out_scale=inv, dbias=self._view(gflat, p + norm + ".bias"), defer=True))
+        gflat, out_scale=inv, dbias=self._view(gflat, p + norm + ".bias"), defer=True,
+        algo_flops=4.0 * R * d))        # dgamma = diag(xhat^T dy), dbeta = colsum(dy): 2 x 2 x R x d useful FLOPs
     return g["dx"]
 
   def backward(self, gflat, d_out, flush=True):
