@@ -107,3 +107,14 @@ def test_data_parallel_host_logic_world2():
     p.join(timeout=60)
   for rank, msg in results:
     assert msg == "ok", "rank %d: %s" % (rank, msg)
+
+
+def test_entropy_bonus_share_formula():
+  """The actor-loss kernel writes d_logstd = s_local - c * n_local * inv_global on every rank (csrc/ppo_ops.cu,
+  pf_loss finalize) and the buckets are SUM-all-reduced: the entropy bonus' gradient must come out as -c once,
+  not once per rank (round-1 advisor finding: it was -c * world)."""
+  c, world, n_local = 0.005, 8, 128
+  inv_global = 1.0 / (n_local * world)
+  s_local = np.random.default_rng(0).standard_normal(world)
+  summed = sum(s - c * n_local * inv_global for s in s_local)
+  assert abs(summed - (s_local.sum() - c)) < 1e-12
