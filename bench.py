@@ -69,6 +69,7 @@ def parse():
   ap.add_argument("--sweep-transitions", type=int, default=1 << 20)
   ap.add_argument("--sweep-batch", type=int, default=65536, help="GLOBAL minibatch of the strong-scaling sweep")
   ap.add_argument("--sweep-steps", type=int, default=1)
+  ap.add_argument("--sweep-timeout", type=int, default=300)
   ap.add_argument("--no-roofline", action="store_true")
   return ap.parse_args()
 
@@ -407,22 +408,6 @@ def main():
       roof_inputs = kernel_rooflines(args, eng, peaks())          # needs the engine's plans and rollout
     except Exception as ex:
       roof_inputs = {"roofline": {"error": repr(ex)[:300]}, "gae": None}
-  sweep = None
-  if not args.no_sweep and args.precision == "f16":
-    try:
-      sweep = strong_sweep(args, dev, pg, world, rank, pf_np, vf_np, barrier, max_over_ranks)
-    except Exception as ex:             # never let the auxiliary sweep take the headline line down
-      sweep = {"error": repr(ex)[:300]}
-
-  if world > 1:
-    # no collective is issued past this point; ranks leave without tearing NCCL down (destroying a
-    # communicator that captured CUDA graphs still reference can block) — hard exit after flushing
-    import torch.distributed as dist
-    dist.barrier()
-    torch.cuda.synchronize(dev)
-    if rank != 0:
-      sys.stdout.flush()
-      os._exit(0)
   pk = peaks()
   line = {
     "metric": "ppo_update_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
@@ -442,6 +427,40 @@ def main():
   if roof_inputs:
     line["roofline"] = roof_inputs["roofline"]
     line["gae"] = roof_inputs["gae"]
+  sweep = None
+  if not args.no_sweep and args.precision == "f16":
+    # The sweep is auxiliary: the headline line above is complete.  A watchdog prints it (rank 0) and ends the
+    # process if the sweep has not come back in time (e.g. a rank lost to an allocation failure would leave its
+    # peers inside a collective), so the one-line contract holds whatever happens in here.
+    def _bail():
+      if rank == 0:
+        line.setdefault("strong_sweep", {"error": "watchdog: the sweep did not finish within %d s" % args.sweep_timeout})
+        print(json.dumps(line))
+        sys.stdout.flush()
+      os._exit(0)
+    dog = threading.Timer(args.sweep_timeout, _bail)
+    dog.daemon = True
+    dog.start()
+    try:
+      sweep = strong_sweep(args, dev, pg, world, rank, pf_np, vf_np, barrier, max_over_ranks)
+    except Exception as ex:             # a failure on EVERY rank (bad arguments): report it
+      sweep = {"error": repr(ex)[:300]}
+    if rank == 0 and sweep is not None:
+      line["strong_sweep"] = sweep     # (the watchdog keeps running until the barrier below has been passed)
+  else:
+    dog = None
+
+  if world > 1:
+    # no collective is issued past this point; ranks leave without tearing NCCL down (destroying a
+    # communicator that captured CUDA graphs still reference can block) — hard exit after flushing
+    import torch.distributed as dist
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    if rank != 0:
+      sys.stdout.flush()
+      os._exit(0)
+  if dog is not None:
+    dog.cancel()
   if sweep is not None:
     line["strong_sweep"] = sweep
   if world == 1 and not args.no_fp32_tier and args.precision == "f16":
@@ -634,6 +653,11 @@ def strong_sweep(args, dev, pg, world, rank, pf_np, vf_np, barrier, max_over_ran
   Bl = args.sweep_batch // world
   N = T * El
   free, _ = torch.cuda.mem_get_info(dev)
+  if world > 1:                       # the same decision on every rank (the least free memory decides)
+    import torch.distributed as dist
+    t = torch.tensor([float(free)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    free = float(t)
   need = N * (32768 + S * 4 + A * 8 + 64) + (12 << 30) * min(1.0, Bl / 65536.0) * 3
   if need > free * 0.92:
     return {"skipped": "needs %.0f GB of HBM, %.0f GB free" % (need / 2**30, free / 2**30)}

@@ -239,7 +239,12 @@ int v4l_pf_loss(v4l_ctx* ctx, void* stream, const float* mean, const float* logs
                 float* d_mean, float* d_logstd, int n, int A, float inv_global, float inv_local,
                 float clip_para, float entropy_coeff, float* info, const int32_t* slot,
                 int target_indexed /* 0: target_mean is [n,A] (row i); 1: a per-rollout table read at row idx[i] */,
-                void* d_mean_f16 /* optional f16 [n,16] = scale_f16 * d_mean, zero padded (A <= 16) */, float scale_f16);
+                void* d_mean_f16 /* optional f16 [n,16] = scale_f16 * d_mean, zero padded (A <= 16) */, float scale_f16,
+                int stats_per_slot /* 1: adv_stats is a [minibatches, 8] table (v4l_adv_stats_epoch) read at row *slot */);
+/* stats[mb] (double[8]) = { sum, sumsq, n, max, min } of adv[flat_idx[mb*n + i]], i < n, for every minibatch of an
+ * epoch in one launch (the row lists and the advantages are fixed once GAE has run)              */
+int v4l_adv_stats_epoch(v4l_ctx* ctx, void* stream, const int32_t* flat_idx, int n_minibatches, int n,
+                        const float* adv, double* stats);
 
 /* ---- clip_grad_norm_(0.5) + Adam(eps=1e-5) over a flat bucket
  *      (reference ppo.py:71-75,116-120; a2c.py:30-40).

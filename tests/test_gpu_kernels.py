@@ -320,3 +320,101 @@ def test_select_rows_and_slot():
     ops.slot_advance(slot, 0)
   ops.slot_advance(slot, 6)
   assert int(slot) == 0
+
+
+# =================================================================================================
+# round-2 entry points: minibatch prologue, epoch advantage statistics, fused optimiser tail
+# =================================================================================================
+def test_mb_begin_and_epoch_stats():
+  engine, ops = _ops()
+  torch.manual_seed(3)
+  N, n, n_mb, S, Sp = 4096, 1000, 4, 93, 128
+  rng = np.random.default_rng(3)
+  flat = torch.tensor(rng.integers(0, N, size=n_mb * n).astype(np.int32), device=DEV)
+  adv = torch.randn(N, device=DEV) * 3
+  state = torch.randn(N, S, device=DEV)
+  slot = torch.zeros(1, device=DEV, dtype=torch.int32)
+  cur = torch.zeros(n, device=DEV, dtype=torch.int32)
+  stats = torch.zeros(8, device=DEV, dtype=torch.float64)
+  st16 = torch.full((n, Sp), float("nan"), device=DEV, dtype=torch.float16)
+  table = torch.zeros((n_mb, 8), device=DEV, dtype=torch.float64)
+  ops.adv_stats_epoch(flat, n_mb, n, adv, table)
+  for s in range(n_mb):
+    slot.fill_(s)
+    ops.mb_begin(flat, slot, cur, n, adv, stats, state, S, st16, Sp)
+    rows = flat[s * n:(s + 1) * n].long()
+    assert torch.equal(cur.long(), rows)
+    a = adv[rows].double()
+    ref = [float(a.sum()), float((a * a).sum()), float(n), float(a.max()), float(a.min())]
+    for got in (stats, table[s]):
+      np.testing.assert_allclose(got[:5].cpu().numpy(), ref, rtol=1e-12)
+    assert torch.equal(st16[:, :S], state[rows].half()) and float(st16[:, S:].abs().max()) == 0.0
+  # the same launch without statistics / without proprio rows
+  ops.mb_begin(flat, slot, cur, n, adv, None)
+  assert torch.equal(cur.long(), flat[(n_mb - 1) * n:].long())
+
+
+def test_opt_tail_matches_clip_adam_and_pack():
+  """v4l_opt_tail phase 2 (norm from the bucket) == v4l_clip_adam, and the fp16 operand copies it writes ==
+  v4l_pack_f16 of the updated bucket through the same table."""
+  engine, ops = _ops()
+  torch.manual_seed(9)
+  n = 50000                                   # multiple of 4 (buckets are padded to 16 bytes)
+  p0 = torch.randn(n, device=DEV)
+  rng = np.random.default_rng(9)
+  # packing table: every parameter appears at two positions of a padded fp16 buffer, some entries are padding
+  n_pack = 2 * n + 1000
+  perm = rng.permutation(n_pack)
+  table = -np.ones(n_pack, np.int32)
+  table[perm[:n]] = np.arange(n); table[perm[n:2 * n]] = np.arange(n)
+  scatter = -np.ones((n, 4), np.int32)
+  scatter[:, 0] = perm[:n]; scatter[:, 1] = perm[n:2 * n]
+  scatter[::7, 2] = perm[:n][::7]             # some parameters also live in the "other" network's buffer
+  table_t, scatter_t = torch.tensor(table, device=DEV), torch.tensor(scatter, device=DEV)
+  for step in range(3):
+    gr = torch.randn(n, device=DEV) * (10.0 if step == 0 else 1e-4)
+    if step == 0:
+      pa, pb = p0.clone(), p0.clone()
+      ma, va, mb_, vb = (torch.zeros(n, device=DEV) for _ in range(4))
+      ha = torch.tensor([3e-4, 0.9, 0.999, 1e-5, 0.5, 0, 0, 0], device=DEV); hb = ha.clone()
+      ia, ib = torch.zeros(1, 32, device=DEV), torch.zeros(1, 32, device=DEV)
+      slot = torch.zeros(1, device=DEV, dtype=torch.int32)
+      adv_slot = torch.zeros(1, device=DEV, dtype=torch.int32)
+      packed_self = torch.zeros(n_pack, device=DEV, dtype=torch.float16)
+      packed_other = torch.zeros(n_pack, device=DEV, dtype=torch.float16)
+    ops.clip_adam(pa, gr, ma, va, n, ha, ia, slot, 5)
+    ops.opt_tail(2, param=pb, grad=gr, m=mb_, v=vb, n=n, hyper=hb, info=ib, slot=slot, norm_slot=5,
+                 scatter=scatter_t, packed_self=packed_self, packed_other=packed_other, slot_advance=adv_slot)
+    torch.cuda.synchronize()
+    assert abs(float(ia[0, 5]) - float(ib[0, 5])) <= 1e-6 * float(ia[0, 5])
+    assert rel(pb, pa) < 1e-6 and rel(mb_, ma) < 1e-6 and rel(vb, va) < 1e-6
+    ref = torch.zeros(n_pack, device=DEV, dtype=torch.float16)
+    ops.pack_f16(pb, table_t, ref, n_pack)
+    assert torch.equal(packed_self, ref)
+    assert torch.equal(packed_other[perm[:n][::7]], pb[::7].half())
+  assert float(hb[5]) == 3.0 and int(adv_slot) == 3
+
+
+def test_pf_loss_stats_table_and_f16_gradient():
+  """the per-minibatch statistics table (stats_per_slot) and the loss-scaled fp16 gradient row"""
+  engine, ops = _ops()
+  torch.manual_seed(4)
+  n, A = 700, 12
+  mean, tmean, acts = torch.randn(n, A, device=DEV) * 0.1, torch.randn(n, A, device=DEV) * 0.1, torch.randn(n, A, device=DEV) * 0.2
+  logstd = torch.full((A,), math.log(0.125), device=DEV); adv = torch.randn(n, device=DEV)
+  st = torch.zeros((3, 8), device=DEV, dtype=torch.float64)
+  a = adv.double()
+  st[2, 0], st[2, 1], st[2, 2], st[2, 3], st[2, 4] = a.sum(), (a * a).sum(), n, a.max(), a.min()
+  slot = torch.full((1,), 2, device=DEV, dtype=torch.int32)
+  info = torch.zeros(3, 32, device=DEV)
+  outs = []
+  for per_slot in (False, True):
+    d_mean = torch.zeros(n, A, device=DEV); d_ls = torch.zeros(A, device=DEV)
+    d16 = torch.full((n, 16), float("nan"), device=DEV, dtype=torch.float16)
+    ops.pf_loss(mean, logstd, tmean, logstd, acts, adv, None, st if per_slot else st[2], d_mean, d_ls, n, A, 1.0 / n, 1.0 / n,
+                0.2, 0.005, info, slot, d_f16=d16, scale_f16=256.0, stats_per_slot=per_slot)
+    torch.cuda.synchronize()
+    outs.append((d_mean.clone(), d_ls.clone(), info[2].clone()))
+    assert torch.equal(d16[:, :A], (d_mean * 256.0).half()) and float(d16[:, A:].abs().max()) == 0.0
+  for x, y in zip(outs[0], outs[1]):
+    assert torch.equal(x, y)

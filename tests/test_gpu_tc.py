@@ -544,3 +544,34 @@ def test_tc_conv_flat_swapped_roles_conv1():
   ops.tc_conv_flat(x, 64, 256, 16, 15, 15, taps2, w, 32, 32, bias, out, cm(), B, x_idx=idx, flags=RELU, mode=0x101)
   torch.cuda.synchronize()
   assert rel(out.float(), ref.float()) < 1e-3
+
+
+def test_tc_wgrad_conv1_single_load_matches_generic_and_torch():
+  """v4l_tc_wgrad_conv1 (each pixel window / dY cell loaded once, sub-positions summed from TMEM) against the
+  generic tap-box weight gradient on the same cell-layout gradient and against torch's conv2d backward."""
+  engine, ops = _ops()
+  torch.manual_seed(17)
+  for B, gather in ((5, False), (300, True)):
+    Nimg = B + 3
+    img = bf(torch.randn(Nimg, 4, 64, 64, device=DEV))
+    s2d = img.reshape(Nimg, 4, 16, 4, 16, 4).permute(0, 2, 4, 3, 5, 1).reshape(Nimg, 16, 16, 64).contiguous()
+    idx = torch.tensor(np.random.default_rng(B).permutation(Nimg)[:B].astype(np.int32), device=DEV) if gather else None
+    dy = bf(torch.randn(B, 15, 15, 32, device=DEV))
+    cells = torch.zeros(B, 16, 16, 32, device=DEV, dtype=torch.float16)
+    cells[:, :15, :15] = dy
+    cells = cells.reshape(B, 8, 2, 8, 2, 32).permute(0, 1, 3, 2, 4, 5).reshape(B, 8, 8, 128).contiguous()
+    n_, dy_, dx_, py_, px_, c_ = np.meshgrid(np.arange(32), np.arange(2), np.arange(2), np.arange(4), np.arange(4),
+                                             np.arange(4), indexing="ij")
+    index = torch.tensor((n_ * 256 + c_ * 64 + (4 * dy_ + py_) * 8 + (4 * dx_ + px_)).reshape(32, 256).astype(np.int32),
+                         device=DEV)
+    dw = torch.full((32, 4, 8, 8), float("nan"), device=DEV); db = torch.full((32,), float("nan"), device=DEV)
+    ops.tc_wgrad_conv1(s2d, idx, cells, B, index, dw, db, out_scale=0.5, defer=False)
+    x = img if idx is None else img[idx.long()]
+    w = torch.zeros(32, 4, 8, 8, device=DEV, requires_grad=True)
+    b = torch.zeros(32, device=DEV, requires_grad=True)
+    F.conv2d(x.float(), w, b, stride=4).backward(dy.float().permute(0, 3, 1, 2))
+    assert rel(dw, 0.5 * w.grad) < 1e-4, (B, rel(dw, 0.5 * w.grad))
+    assert rel(db, 0.5 * b.grad) < 1e-4
+    # accumulate: a second pass adds onto the first
+    ops.tc_wgrad_conv1(s2d, idx, cells, B, index, dw, db, out_scale=0.5, defer=False, accumulate=True)
+    assert rel(dw, w.grad) < 1e-4 and rel(db, b.grad) < 1e-4

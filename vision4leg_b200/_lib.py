@@ -142,7 +142,8 @@ SIGNATURES = {
   "v4l_adv_stats": [_vp, _vp, _vp, _vp, _i, _vp],
   "v4l_vf_loss": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _i, _f, _vp, _vp, _vp, _f],
   "v4l_pf_loss": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _f,
-                  _f, _vp, _vp, _i, _vp, _f],
+                  _f, _vp, _vp, _i, _vp, _f, _i],
+  "v4l_adv_stats_epoch": [_vp, _vp, _vp, _i, _i, _vp, _vp],
   "v4l_clip_adam": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i],
   "v4l_tc_gemm": [_vp, _vp, C.POINTER(TcGemmArgs)],
   "v4l_tc_wgrad": [_vp, _vp, C.POINTER(TcWgradArgs)],

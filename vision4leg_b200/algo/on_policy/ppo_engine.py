@@ -112,6 +112,7 @@ class PPOUpdateEngine:
     self._graphs = {}
     self._roll = None
     self._mb_bufs = {}
+    self._epoch_stats = None          # [minibatches, 8] doubles while an epoch of uniform minibatches runs
 
   # ---------------------------------------------------------------------------------------------
   def _build_buckets(self):
@@ -433,9 +434,11 @@ class PPOUpdateEngine:
     if self.precision == "f16":
       return self._minibatch_tc(B, b, idx, inv_local, inv_global, with_target)
     ops.select_rows(self._flat_idx, self._slot, idx, B)
-    ops.adv_stats(r["advs"], idx, B, b["stats"])
-    if self.world > 1:
-      self._allreduce_stats(b)
+    es = self._epoch_stats
+    if es is None:
+      ops.adv_stats(r["advs"], idx, B, b["stats"])
+      if self.world > 1:
+        self._allreduce_stats(b)
     inp = self._input(B, idx)
     # ---- critic
     self.plan_vf.forward(self.P_vf, inp, b["values"])
@@ -449,9 +452,9 @@ class PPOUpdateEngine:
     # ---- actor
     self.plan_pf.forward(self.P_pf, inp, b["mean"])
     self.plan_t.forward(self.P_t, inp, b["tmean"])
-    ops.pf_loss(b["mean"], self.logstd, b["tmean"], self.t_logstd, r["acts"], r["advs"], idx, b["stats"],
-                b["d_mean"], self.G_pf["logstd"], B, self.A, inv_global, inv_local, self.clip_para,
-                self.entropy_coeff, self._info, self._slot)
+    ops.pf_loss(b["mean"], self.logstd, b["tmean"], self.t_logstd, r["acts"], r["advs"], idx,
+                b["stats"] if es is None else es, b["d_mean"], self.G_pf["logstd"], B, self.A, inv_global, inv_local,
+                self.clip_para, self.entropy_coeff, self._info, self._slot, stats_per_slot=es is not None)
     self.plan_pf.backward(self.P_pf, self.G_pf, b["d_mean"])
     if self.world > 1:
       self._allreduce(self.g_pf)
@@ -468,9 +471,10 @@ class PPOUpdateEngine:
     ops, r = self.ops, self._roll
     imgs, st = r["imgs"], b["st"]
     ppf, pvf = self.plan_pf, self.plan_vf
-    ops.mb_begin(self._flat_idx, self._slot, idx, B, r["advs"], b["stats"], r["state"] if self.S else None,
-                 self.S, st, ppf.Sp)
-    if self.world > 1:
+    es = self._epoch_stats            # advantage statistics of every minibatch, computed once per epoch (run_epoch)
+    ops.mb_begin(self._flat_idx, self._slot, idx, B, r["advs"], b["stats"] if es is None else None,
+                 r["state"] if self.S else None, self.S, st, ppf.Sp)
+    if es is None and self.world > 1:
       self._allreduce_stats(b)
     # The frozen target policy (copied once per update_per_epoch, ppo.py:34) only depends on the rollout
     # row: its action mean is computed when a row is first visited (first opt-epoch), as a parallel
@@ -492,10 +496,10 @@ class PPOUpdateEngine:
     ppf.forward(self.pf_flat, imgs, idx, st, B, b["mean"])
     if with_target:
       ops.join(1)
-    ops.pf_loss(b["mean"], self.logstd, r["tmean_all"], self.t_logstd, r["acts"], r["advs"], idx, b["stats"],
-                b["d_mean"], self.G_pf["logstd"], B, self.A, inv_global, inv_local, self.clip_para,
-                self.entropy_coeff, self._info, self._slot, target_indexed=True,
-                d_f16=ppf.grad_in(B), scale_f16=ppf.loss_scale(B))
+    ops.pf_loss(b["mean"], self.logstd, r["tmean_all"], self.t_logstd, r["acts"], r["advs"], idx,
+                b["stats"] if es is None else es, b["d_mean"], self.G_pf["logstd"], B, self.A, inv_global, inv_local,
+                self.clip_para, self.entropy_coeff, self._info, self._slot, target_indexed=True,
+                d_f16=ppf.grad_in(B), scale_f16=ppf.loss_scale(B), stats_per_slot=es is not None)
     ppf.backward(self.g_pf, None, flush=False)
     self._tail("pf", self._slot)
 
@@ -567,6 +571,21 @@ class PPOUpdateEngine:
       self._flat_idx_static.copy_(self._flat_idx.view(-1))
       self._flat_idx = self._flat_idx_static
       self._slot.zero_()
+      # advantage statistics of all minibatches in ONE launch (and, data parallel, ONE exchange per epoch instead
+      # of one per minibatch on the critical path): rows and advantages are fixed from here on
+      st_all = getattr(self, "_stats_table", None)
+      if st_all is None or st_all.shape[0] != n_mb:
+        st_all = self._stats_table = torch.zeros((n_mb, 8), device=dev, dtype=torch.float64)
+        self._graphs.clear()
+      self.ops.adv_stats_epoch(self._flat_idx, n_mb, B, r["advs"], st_all)
+      if self.world > 1:
+        import torch.distributed as dist
+        allst = torch.empty((self.world, n_mb, 8), device=dev, dtype=torch.float64)
+        dist.all_gather_into_tensor(allst.view(-1), st_all.view(-1), group=self.pg)
+        st_all[:, 0:3] = allst[:, :, 0:3].sum(0)
+        st_all[:, 3] = allst[:, :, 3].max(0).values
+        st_all[:, 4] = allst[:, :, 4].min(0).values
+      self._epoch_stats = st_all
       pending, self._pending_obs = getattr(self, "_pending_obs", None), None
       self._pending_half_cur, self._pending_half = getattr(self, "_pending_half", None), None
       cur = torch.cuda.current_stream(dev)
@@ -588,6 +607,7 @@ class PPOUpdateEngine:
           self._pending_half = None
         self._copy_obs_rows(obs, D, 0, T * E)
       self._run_ragged(flat, T, E, rows)
+    self._epoch_stats = None
     info = self._info[:n_mb, :len(INFO_KEYS)].cpu().numpy()
     self.d2h_bytes = info.nbytes
     return [dict(zip(INFO_KEYS, (float(x) for x in row))) for row in info]

@@ -309,8 +309,9 @@ pf_loss_kernel(const float* __restrict__ mean, const float* __restrict__ logstd,
                float* __restrict__ d_mean, __half* __restrict__ d_f16, float scale_f16, int n, int A,
                float inv_global, float inv_local, float clip, float entropy_coeff, double* part, int t_indexed,
                float* __restrict__ d_logstd, unsigned int* counter, float* __restrict__ info,
-               const int32_t* __restrict__ slot) {
+               const int32_t* __restrict__ slot, int stats_per_slot) {
   v4l_pdl_enter();
+  if (stats_per_slot && slot) adv_stats += (long long)(*slot) * 8;      // per-minibatch table (v4l_adv_stats_epoch)
   __shared__ float s_ls[MAX_A], s_tls[MAX_A], s_ivar[MAX_A], s_tivar[MAX_A];
   __shared__ float s_dls[LOSS_THREADS / 32][MAX_A];
   __shared__ double shd[32];
@@ -721,7 +722,8 @@ extern "C" int v4l_pf_loss(v4l_ctx* ctx, void* stream, const float* mean, const 
                            const float* adv, const int32_t* idx, const double* adv_stats,
                            float* d_mean, float* d_logstd, int n, int A, float inv_global,
                            float inv_local, float clip_para, float entropy_coeff, float* info,
-                           const int32_t* slot, int target_indexed, void* d_mean_f16, float scale_f16) {
+                           const int32_t* slot, int target_indexed, void* d_mean_f16, float scale_f16,
+                           int stats_per_slot) {
   V4L_REQUIRE(ctx && mean && logstd && target_mean && target_logstd && acts && adv && adv_stats &&
               d_mean && d_logstd && info, "v4l_pf_loss: NULL argument");
   V4L_REQUIRE(n > 0 && A > 0 && A <= MAX_A, "v4l_pf_loss: bad shape n=%d A=%d (A <= %d)", n, A, MAX_A);
@@ -731,7 +733,8 @@ extern "C" int v4l_pf_loss(v4l_ctx* ctx, void* stream, const float* mean, const 
   V4L_REQUIRE(!d_mean_f16 || A <= 16, "v4l_pf_loss: the fp16 gradient row holds 16 columns (A = %d)", A);
   V4L_LAUNCH(pf_loss_kernel, ctas, LOSS_THREADS, 0, s, mean, logstd, target_mean, target_logstd, acts, adv, idx,
              adv_stats, d_mean, reinterpret_cast<__half*>(d_mean_f16), scale_f16, n, A, inv_global, inv_local,
-             clip_para, entropy_coeff, part, (target_indexed && idx) ? 1 : 0, d_logstd, ctx->counters + 1, info, slot);
+             clip_para, entropy_coeff, part, (target_indexed && idx) ? 1 : 0, d_logstd, ctx->counters + 1, info, slot,
+             stats_per_slot);
   V4L_CHECK_LAUNCH();
   return 0;
 }

@@ -90,7 +90,9 @@ mb_begin_kernel(const int32_t* __restrict__ flat_idx, const int32_t* __restrict_
     }
   }
   // (3) advantage statistics {sum, sumsq, n, max, min}: per-CTA partials, summed in CTA order by the
-  //     last CTA to arrive (deterministic)
+  //     last CTA to arrive (deterministic).  stats == NULL: they were computed for the whole epoch up front
+  //     (v4l_adv_stats_epoch) and nothing is left to do here.
+  if (!stats) return;
   s = block_reduce_t(s, AddD(), 0.0, shd);
   s2 = block_reduce_t(s2, AddD(), 0.0, shd);
   mx = block_reduce_t(mx, MaxF(), -FLT_MAX, shf);
@@ -119,6 +121,32 @@ mb_begin_kernel(const int32_t* __restrict__ flat_idx, const int32_t* __restrict_
     MX = fmaxf(MX, __shfl_xor_sync(0xffffffffu, MX, o)); MN = fminf(MN, __shfl_xor_sync(0xffffffffu, MN, o));
   }
   if (threadIdx.x == 0) { stats[0] = S1; stats[1] = S2; stats[2] = (double)n; stats[3] = MX; stats[4] = MN; }
+}
+
+// Advantage statistics of EVERY minibatch of an epoch in one launch: the advantages and the row lists are fixed
+// once GAE has run and the permutations are drawn, so the per-minibatch statistics (and, data parallel, their
+// exchange across ranks) leave the per-minibatch chain.  stats[mb] = {sum, sumsq, n, max, min, -, -, -}.
+__global__ void __launch_bounds__(256) adv_stats_epoch_kernel(const int32_t* __restrict__ flat_idx, int n,
+                                                              const float* __restrict__ adv, double* __restrict__ stats) {
+  v4l_pdl_enter();
+  __shared__ double shd[32];
+  __shared__ float shf[32];
+  const int32_t* idx = flat_idx + (long long)blockIdx.x * n;
+  double s = 0.0, s2 = 0.0;
+  float mx = -FLT_MAX, mn = FLT_MAX;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float a = adv[idx[i]];
+    s += a; s2 += (double)a * a;
+    mx = fmaxf(mx, a); mn = fminf(mn, a);
+  }
+  s = block_reduce_t(s, AddD(), 0.0, shd);
+  s2 = block_reduce_t(s2, AddD(), 0.0, shd);
+  mx = block_reduce_t(mx, MaxF(), -FLT_MAX, shf);
+  mn = block_reduce_t(mn, MinF(), FLT_MAX, shf);
+  if (threadIdx.x == 0) {
+    double* o = stats + (long long)blockIdx.x * 8;
+    o[0] = s; o[1] = s2; o[2] = (double)n; o[3] = mx; o[4] = mn; o[5] = 0.0; o[6] = 0.0; o[7] = 0.0;
+  }
 }
 
 // =================================================================================================
@@ -342,7 +370,7 @@ __global__ void __launch_bounds__(STEP_THREADS) opt_step_kernel(const __grid_con
 extern "C" int v4l_mb_begin(v4l_ctx* ctx, void* stream, const int32_t* flat_idx, const int32_t* slot,
                             int32_t* cur_idx, int n, const float* adv, double* stats, const float* state,
                             int S, void* state_f16, int Sp) {
-  V4L_REQUIRE(ctx && flat_idx && slot && cur_idx && adv && stats && n > 0, "v4l_mb_begin: bad argument");
+  V4L_REQUIRE(ctx && flat_idx && slot && cur_idx && adv && n > 0, "v4l_mb_begin: bad argument");
   V4L_REQUIRE(!state_f16 || (S >= 0 && Sp >= S && (S == 0 || state)), "v4l_mb_begin: bad proprio arguments");
   V4L_REQUIRE(!state_f16 || Sp % 8 == 0, "v4l_mb_begin: Sp must be a multiple of 8");
   const long long work = max((long long)n, state_f16 ? (long long)n * Sp / 8 : 0LL);
@@ -435,6 +463,14 @@ extern "C" int v4l_opt_tail(v4l_ctx* ctx, void* stream, const v4l_opt_tail_args*
     V4L_LAUNCH(opt_step_kernel, grid2, STEP_THREADS, 0, st, P, grid1);
     V4L_CHECK_LAUNCH();
   }
+  return 0;
+}
+
+extern "C" int v4l_adv_stats_epoch(v4l_ctx* ctx, void* stream, const int32_t* flat_idx, int n_minibatches, int n,
+                                   const float* adv, double* stats) {
+  V4L_REQUIRE(ctx && flat_idx && adv && stats && n > 0 && n_minibatches > 0, "v4l_adv_stats_epoch: bad argument");
+  V4L_LAUNCH(adv_stats_epoch_kernel, n_minibatches, 256, 0, (cudaStream_t)stream, flat_idx, n, adv, stats);
+  V4L_CHECK_LAUNCH();
   return 0;
 }
 

@@ -403,11 +403,16 @@ class Ops:
 
   def pf_loss(self, mean, logstd, tmean, tlogstd, acts, adv, idx, stats, d_mean, d_logstd, n, A,
               inv_global, inv_local, clip_para, entropy_coeff, info, slot, target_indexed=False,
-              d_f16=None, scale_f16=1.0):
+              d_f16=None, scale_f16=1.0, stats_per_slot=False):
     check(self.lib.v4l_pf_loss(self.h, self.ctx.stream(), ptr(mean), ptr(logstd), ptr(tmean),
                                ptr(tlogstd), ptr(acts), ptr(adv), ptr(idx), ptr(stats), ptr(d_mean),
                                ptr(d_logstd), n, A, inv_global, inv_local, clip_para, entropy_coeff,
-                               ptr(info), ptr(slot), 1 if target_indexed else 0, ptr(d_f16), scale_f16))
+                               ptr(info), ptr(slot), 1 if target_indexed else 0, ptr(d_f16), scale_f16,
+                               1 if stats_per_slot else 0))
+    self.launches += 1
+
+  def adv_stats_epoch(self, flat_idx, n_mb, n, adv, stats):
+    check(self.lib.v4l_adv_stats_epoch(self.h, self.ctx.stream(), ptr(flat_idx), n_mb, n, ptr(adv), ptr(stats)))
     self.launches += 1
 
   def mb_begin(self, flat_idx, slot, cur_idx, n, adv, stats, state=None, S=0, state_f16=None, Sp=0):
