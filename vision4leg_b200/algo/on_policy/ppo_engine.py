@@ -95,8 +95,8 @@ class PPOUpdateEngine:
     self.precision = precision
     if precision == "f16":
       if self.family not in engine_tc.PLANS:
-        raise NotImplementedError("the tensor-core tier covers the LocoTransformer and NatureCNN "
-                                  "families; use precision='fp32' for %s" % self.family)
+        raise NotImplementedError("the tensor-core tier covers the image families (LocoTransformer, NatureCNN and "
+                                  "their vision-only variants); use precision='fp32' for %s" % self.family)
       nh = kw.get("n_heads", (1, 1))
       Plan = engine_tc.PLANS[self.family]
       self.plan_pf = Plan(self.ops, self.S, self.A, self.pf_layout, nh)

@@ -86,8 +86,9 @@ CONV1_WGRAD_S2D = True            # conv1 weight gradient by the single-load ker
 class TcWeights:
   """Packed fp16 copies (forward and data-gradient orientations) of one network's GEMM weights."""
 
-  def __init__(self, ops, layout, with_dgrad=True):
-    """layout: {param name: (flat offset, shape)} relative to the flat fp32 bucket handed to pack()"""
+  def __init__(self, ops, layout, with_dgrad=True, flatten_names=("encoder.visual_projector.projection.0.weight",)):
+    """layout: {param name: (flat offset, shape)} relative to the flat fp32 bucket handed to pack();
+    flatten_names: Linear layers fed by torch's (c, p) flatten of the [64,4,4] conv output"""
     self.ops = ops
     self.layout = layout
     self.fwd, self.dgr = {}, {}
@@ -99,7 +100,7 @@ class TcWeights:
       if len(shape) == 4 and shape[2] > 1:
         stride = {8: 4, 4: 2, 3: 1}[shape[2]]
         f, d = _conv_tables(off, shape[0], shape[1], shape[2], shape[3], stride)
-      elif name == "encoder.visual_projector.projection.0.weight":
+      elif name in flatten_names:
         # torch flattens [64,4,4] as (c, p); our a3 is [16 positions, 64 channels] = (p, c)
         pp, cc = np.meshgrid(np.arange(16), np.arange(64), indexing="ij")
         f, d = _linear_tables(off, shape[0], shape[1], kperm=(cc * 16 + pp).ravel())
@@ -131,12 +132,13 @@ class TcWeights:
 class _PlanTC:
   """Shared machinery: workspace, packed weights, Linear helpers and the NatureCNN trunk."""
 
-  def __init__(self, ops, S, out_dim, layout, with_backward, head_prefix):
+  def __init__(self, ops, S, out_dim, layout, with_backward, head_prefix, flatten_names=None):
     self.ops, self.device = ops, ops.device
     self.S, self.Sp = S, _ceil(S, 64)
     self.out_dim = out_dim
     self.layout = layout
-    self.W = TcWeights(ops, layout, with_dgrad=with_backward)
+    self.W = (TcWeights(ops, layout, with_dgrad=with_backward, flatten_names=flatten_names) if flatten_names
+              else TcWeights(ops, layout, with_dgrad=with_backward))
     self._ws = {}
     self.world = 1                    # data-parallel world size (loss scale, see _begin_backward)
     self._rr, self._forked = 0, set()
@@ -297,18 +299,25 @@ class LocoPlanTC(_PlanTC):
   """LocoTransformer forward/backward on the tensor-core tier for one batch size."""
   family = "loco"
 
-  def __init__(self, ops, S, out_dim, layout, n_heads=(1, 1), with_backward=True):
+  def __init__(self, ops, S, out_dim, layout, n_heads=(1, 1), with_backward=True, has_state=True):
     super().__init__(ops, S, out_dim, layout, with_backward, "visual_seq_append_fcs.")
     self.n_heads = list(n_heads)
-    self.T, self.d = 17, 64
+    self.has_state = has_state          # False: vision-only Transformer (reference nets.py:784-906): 16 tokens, mean pool
+    self.T, self.d = (17 if has_state else 16), 64
+    self.first = 1 if has_state else 0  # token slot of the first depth token
+    self.pd = 2 * self.d if has_state else self.d
     self._diag = {}
 
   # ---- forward --------------------------------------------------------------------------------
-  def forward(self, flat, imgs, idx, st, B, out, out_map=None):
+  def forward(self, flat, imgs, idx, st, B, out, out_map=None, enc_from=None):
     """imgs [N,16,16,64] fp16 (whole rollout), idx int32 [B] or None, st [B,Sp] fp16 proprio rows,
-    out fp32 [B,out_dim].  `flat` = the fp32 bucket the layout offsets refer to (biases, LN)."""
+    out fp32 [B,out_dim].  `flat` = the fp32 bucket the layout offsets refer to (biases, LN).
+    enc_from: another plan of the same batch whose SHARED-ENCODER output (the 17 / 16 tokens) is reused instead
+    of running the conv trunk and the proprio branch again (actor + critic inference on one observation batch)."""
     ops, T, d = self.ops, self.T, self.d
     self._flat, self._B, self._imgs, self._idx, self._st = flat, B, imgs, idx, st
+    if enc_from is not None:
+      return self._forward_layers(flat, enc_from._ws[("tok0", B, T, d)], B, out, out_map)
     tok = self.buf("tok0", (B, T, d))
     s1 = self.buf("s1", (B, 256)); s2 = self.buf("s2", (B, 256))
 
@@ -316,10 +325,16 @@ class LocoPlanTC(_PlanTC):
       self._lin_fwd(flat, self.k_base[0], st, B, self.Sp, s1, RM.dense(256), True)
       self._lin_fwd(flat, self.k_base[1], s1, B, 256, s2, RM.dense(256), True)
       self._lin_fwd(flat, "encoder.state_projector.projection.0.weight", s2, B, 256, tok, RM.slots(1, T, d, 0), True)
-    self._side(state_branch, which=0)
+    if self.has_state:
+      self._side(state_branch, which=0)
     a3 = self._trunk_fwd(flat, imgs, idx, B, "encoder.depth_visual_base.layers.")
-    self._lin_fwd(flat, "encoder.depth_up_conv.weight", a3, B * 16, 64, tok, RM.slots(16, T, d, 1), False)
+    self._lin_fwd(flat, "encoder.depth_up_conv.weight", a3, B * 16, 64, tok, RM.slots(16, T, d, self.first), False)
     self._join_all()
+    return self._forward_layers(flat, tok, B, out, out_map)
+
+  def _forward_layers(self, flat, tok, B, out, out_map):
+    """encoder layers, pooling and the head on the token tensor"""
+    ops, T, d = self.ops, self.T, self.d
     R = B * T
     x = tok
     self._layers = []
@@ -359,10 +374,10 @@ class LocoPlanTC(_PlanTC):
       ops.ln_fwd_f16(f2, h, self._view(flat, p + "norm2.weight"), self._view(flat, p + "norm2.bias"), y, z2, st2, R, d)
       self._layers.append(dict(p=p, nh=nh, x=x, qkv=qkv, o=o, pr=pr, h=h, z1=z1, st1=st1, f1=f1, z2=z2, st2=st2))
       x = y
-    pooled = self.buf("pooled", (B, 2 * d))
-    ops.pool_fwd_f16(x, pooled, B, T, d, 0)
+    pooled = self.buf("pooled", (B, self.pd))
+    ops.pool_fwd_f16(x, pooled, B, T, d, 0 if self.has_state else 1)
     h1 = self.buf("h1", (B, 256)); h2 = self.buf("h2", (B, 256))
-    self._lin_fwd(flat, self.k_head[0], pooled, B, 2 * d, h1, RM.dense(256), True)
+    self._lin_fwd(flat, self.k_head[0], pooled, B, self.pd, h1, RM.dense(256), True)
     self._lin_fwd(flat, self.k_head[1], h1, B, 256, h2, RM.dense(256), True)
     self._lin_fwd(flat, self.k_head[2], h2, B, 256, out, out_map or RM.dense(self.out_dim), False, c_f32=True)
     return out
@@ -414,13 +429,14 @@ class LocoPlanTC(_PlanTC):
     ws = self._ws
     g16 = self._begin_backward(d_out, B)
     inv = self._inv_scale
-    h1, h2, pooled = ws[("h1", B, 256)], ws[("h2", B, 256)], ws[("pooled", B, 2 * d)]
-    dh2 = self.buf("dh2", (B, 256)); dh1 = self.buf("dh1", (B, 256)); dpool = self.buf("dpool", (B, 2 * d))
+    pd = self.pd
+    h1, h2, pooled = ws[("h1", B, 256)], ws[("h2", B, 256)], ws[("pooled", B, pd)]
+    dh2 = self.buf("dh2", (B, 256)); dh1 = self.buf("dh1", (B, 256)); dpool = self.buf("dpool", (B, pd))
     self._lin_bwd(gflat, self.k_head[2], h2, 256, g16, 16, B, dh2, RM.dense(256), mask=h2)
     self._lin_bwd(gflat, self.k_head[1], h1, 256, dh2, 256, B, dh1, RM.dense(256), mask=h1)
-    self._lin_bwd(gflat, self.k_head[0], pooled, 2 * d, dh1, 256, B, dpool, RM.dense(2 * d))
+    self._lin_bwd(gflat, self.k_head[0], pooled, pd, dh1, 256, B, dpool, RM.dense(pd))
     dx = self.buf("dx_top", (R, d))
-    ops.pool_bwd_f16(dpool, dx, B, T, d, 0)
+    ops.pool_bwd_f16(dpool, dx, B, T, d, 0 if self.has_state else 1)
     # every gradient tensor below is written once and then only read (no in-place accumulation,
     # per-layer buffers): the weight-gradient launches on the side stream can lag behind safely
     for l in reversed(range(len(self._layers))):
@@ -458,18 +474,20 @@ class LocoPlanTC(_PlanTC):
       self._lin_bwd(gflat, "encoder.state_projector.projection.0.weight", s2, 256, ds, d, B, ds2, RM.dense(256), mask=s2)
       self._lin_bwd(gflat, self.k_base[1], s1, 256, ds2, 256, B, ds1, RM.dense(256), mask=s1)
       self._lin_bwd(gflat, self.k_base[0], self._st, self.Sp, ds1, 256, B, need_dx=False)
-    self._side(state_branch, which=0)
+    if self.has_state:
+      self._side(state_branch, which=0)
     # depth tokens -> 1x1 up-conv (dY is the strided [B,16,64] window of the token gradient)
     a3 = ws[("a3", B, 16, 64)]
     up = "encoder.depth_up_conv.weight"
     strides = (d, T * d, T * d)
+    off = self.first * d
     self._side(lambda: ops.tc_wgrad(
       a3, (B, 1, 16, 64), dx, d, (B, 1, 16), (16, 1, 8), [(0, 0)], 64, self.W.fwd[up].dev_table, gflat,
-      dy_strides=strides, dy_off=d, out_scale=inv, dbias=self._view(gflat, "encoder.depth_up_conv.bias"), defer=True))
+      dy_strides=strides, dy_off=off, out_scale=inv, dbias=self._view(gflat, "encoder.depth_up_conv.bias"), defer=True))
     da3 = self.buf("da3", (B, 16, 64))
-    pd = self.W.dgr[up]
-    ops.tc_gemm(dx, (B, 1, 16, 64), (B, 1, 16), (16, 1, 8), [(0, 0)], 1, pd.w, pd.rows, 64, None, da3,
-                RM(16, 16 * 64, 64, 0), mask=a3, a_strides=strides, a_off=d)
+    pdw = self.W.dgr[up]
+    ops.tc_gemm(dx, (B, 1, 16, 64), (B, 1, 16), (16, 1, 8), [(0, 0)], 1, pdw.w, pdw.rows, 64, None, da3,
+                RM(16, 16 * 64, 64, 0), mask=a3, a_strides=strides, a_off=off)
     self._trunk_bwd(gflat, da3, B, "encoder.depth_visual_base.layers.")
     self._join_all()
     if flush:
@@ -486,16 +504,19 @@ class NaturePlanTC(_PlanTC):
     self.vd = layout[self.k_proj][1][0]
     self.sd = layout[self.k_base[-1]][1][0]
 
-  def forward(self, flat, imgs, idx, st, B, out, out_map=None):
+  def forward(self, flat, imgs, idx, st, B, out, out_map=None, enc_from=None):
     self._flat, self._B, self._imgs, self._idx, self._st = flat, B, imgs, idx, st
     W = self.vd + self.sd
-    a3 = self._trunk_fwd(flat, imgs, idx, B, "encoder.visual_base.layers.")
-    cat = self.buf("cat", (B, W))
-    # flatten + Linear(1024, vd) + ReLU: the (c,p) -> (p,c) reorder lives in the packing table
-    self._lin_fwd(flat, self.k_proj, a3, B, 1024, cat, RM(1, W, 0, 0), True)
-    s1 = self.buf("s1", (B, 256))
-    self._lin_fwd(flat, self.k_base[0], st, B, self.Sp, s1, RM.dense(256), True)
-    self._lin_fwd(flat, self.k_base[1], s1, B, 256, cat, RM(1, W, 0, self.vd), True)
+    if enc_from is not None:            # shared encoder output [visual | proprio] of another plan of this batch
+      cat = enc_from._ws[("cat", B, W)]
+    else:
+      a3 = self._trunk_fwd(flat, imgs, idx, B, "encoder.visual_base.layers.")
+      cat = self.buf("cat", (B, W))
+      # flatten + Linear(1024, vd) + ReLU: the (c,p) -> (p,c) reorder lives in the packing table
+      self._lin_fwd(flat, self.k_proj, a3, B, 1024, cat, RM(1, W, 0, 0), True)
+      s1 = self.buf("s1", (B, 256))
+      self._lin_fwd(flat, self.k_base[0], st, B, self.Sp, s1, RM.dense(256), True)
+      self._lin_fwd(flat, self.k_base[1], s1, B, 256, cat, RM(1, W, 0, self.vd), True)
     h1 = self.buf("h1", (B, 256)); h2 = self.buf("h2", (B, 256))
     self._lin_fwd(flat, self.k_head[0], cat, B, W, h1, RM.dense(256), True)
     self._lin_fwd(flat, self.k_head[1], h1, B, 256, h2, RM.dense(256), True)
@@ -524,4 +545,45 @@ class NaturePlanTC(_PlanTC):
       ops.tc_wgrad_flush()
 
 
-PLANS = {"loco": LocoPlanTC, "nature": NaturePlanTC}
+class VitPlanTC(LocoPlanTC):
+  """Vision-only Transformer policy / value net (reference nets.py:784-906 + base.py:388-494): the LocoTransformer
+  plan without the proprio token — 16 depth tokens, mean pooling, 64-wide head input."""
+  family = "vit"
+
+  def __init__(self, ops, S, out_dim, layout, n_heads=(1, 1), with_backward=True):
+    super().__init__(ops, 0, out_dim, layout, n_heads, with_backward, has_state=False)
+
+
+class NatureVOPlanTC(_PlanTC):
+  """Vision-only NatureCNN (reference nets.py:133-191 with a flattening NatureEncoder, base.py:334-342):
+  conv trunk -> flatten -> 3-layer head; torch's (c, p) flatten order lives in the first head layer's packing table."""
+  family = "nvo"
+
+  def __init__(self, ops, S, out_dim, layout, n_heads=None, with_backward=True):
+    super().__init__(ops, 0, out_dim, layout, with_backward, "seq_append_fcs.", flatten_names=("seq_append_fcs.0.weight",))
+
+  def forward(self, flat, imgs, idx, st, B, out, out_map=None, enc_from=None):
+    self._flat, self._B, self._imgs, self._idx, self._st = flat, B, imgs, idx, st
+    a3 = enc_from._ws[("a3", B, 16, 64)] if enc_from is not None else self._trunk_fwd(flat, imgs, idx, B, "encoder.layers.")
+    h1 = self.buf("h1", (B, 256)); h2 = self.buf("h2", (B, 256))
+    self._lin_fwd(flat, self.k_head[0], a3, B, 1024, h1, RM.dense(256), True)
+    self._lin_fwd(flat, self.k_head[1], h1, B, 256, h2, RM.dense(256), True)
+    self._lin_fwd(flat, self.k_head[2], h2, B, 256, out, out_map or RM.dense(self.out_dim), False, c_f32=True)
+    return out
+
+  def backward(self, gflat, d_out, flush=True):
+    ops, B, ws = self.ops, self._B, self._ws
+    g16 = self._begin_backward(d_out, B)
+    h1, h2, a3 = ws[("h1", B, 256)], ws[("h2", B, 256)], ws[("a3", B, 16, 64)]
+    dh2 = self.buf("dh2", (B, 256)); dh1 = self.buf("dh1", (B, 256)); da3 = self.buf("da3", (B, 16, 64))
+    self._lin_bwd(gflat, self.k_head[2], h2, 256, g16, 16, B, dh2, RM.dense(256), mask=h2)
+    self._lin_bwd(gflat, self.k_head[1], h1, 256, dh2, 256, B, dh1, RM.dense(256), mask=h1)
+    # first head layer: da3 comes out in our (p, c) order through the packing table, masked by the trunk's ReLU
+    self._lin_bwd(gflat, self.k_head[0], a3, 1024, dh1, 256, B, da3, RM.dense(1024), mask=a3)
+    self._trunk_bwd(gflat, da3, B, "encoder.layers.")
+    self._join_all()
+    if flush:
+      ops.tc_wgrad_flush()
+
+
+PLANS = {"loco": LocoPlanTC, "nature": NaturePlanTC, "vit": VitPlanTC, "nvo": NatureVOPlanTC}
