@@ -566,7 +566,7 @@ def test_tc_wgrad_conv1_single_load_matches_generic_and_torch():
                          device=DEV)
     dw = torch.full((32, 4, 8, 8), float("nan"), device=DEV); db = torch.full((32,), float("nan"), device=DEV)
     ops.tc_wgrad_conv1(s2d, idx, cells, B, index, dw, db, out_scale=0.5, defer=False)
-    x = img if idx is None else img[idx.long()]
+    x = img[:B] if idx is None else img[idx.long()]
     w = torch.zeros(32, 4, 8, 8, device=DEV, requires_grad=True)
     b = torch.zeros(32, device=DEV, requires_grad=True)
     F.conv2d(x.float(), w, b, stride=4).backward(dy.float().permute(0, 3, 1, 2))

@@ -231,7 +231,17 @@ class PPOUpdateEngine:
       raise V4LError("rollout observation width %d, expected %d" % (D, expect))
     self._pending_obs = None
     self._pending_half = None
-    if stream_obs:
+    resident = getattr(self, "_resident_rows", None)
+    self._resident_rows = set()
+    if resident is not None and len(resident) == T and self.precision == "f16":
+      # every time row of this epoch was written on the device by act(row=t): no observation H2D at all
+      self.h2d_bytes = 0
+      stream_obs, skip_obs = False, True
+    else:
+      skip_obs = False
+    if skip_obs:
+      pass
+    elif stream_obs:
       self._pending_obs = (obs, D)
       if self.precision == "f16" and self.has_img and host.get("obs_img16") is not None \
           and getattr(buf, "_half_S", None) == self.S:
@@ -239,7 +249,7 @@ class PPOUpdateEngine:
         self._pending_half = (host["obs_img16"], host["obs_state"])
     else:
       self._copy_obs_rows(obs, D, 0, T * E)
-    self.h2d_bytes = T * E * D * 4
+    self.h2d_bytes = 0 if skip_obs else T * E * D * 4
     if self._pending_half is not None:
       self.h2d_bytes = T * E * (engine.IMG_ELEMS * 2 + self.S * 4)
     for key in ("acts", "values", "rewards", "terminals"):
@@ -364,10 +374,13 @@ class PPOUpdateEngine:
       self._mb_bufs[key] = p
     return p
 
-  def infer(self, obs):
+  def infer(self, obs, imgs_out=None, state_out=None):
     """Action means and values of `obs` [n, D] (fp32 host array or device tensor) on the engine's
     precision tier with the CURRENT parameters: what the collector's `pf.explore` + `vf` evaluate
-    (reference collector/on_policy.py:90-100), one call for both networks.  Returns device tensors
+    (reference collector/on_policy.py:90-100), one call for both networks.  On the tensor-core tier the
+    shared encoder (conv trunk + proprio branch: 7.6 of 11 MFLOP) runs ONCE and feeds both networks — legal
+    here because no optimiser step intervenes between the two forwards.  imgs_out / state_out: optional device
+    destinations (rollout plane rows) for the converted observation.  Returns device tensors
     (mean [n, A], value [n, 1])."""
     x = torch.as_tensor(np.ascontiguousarray(obs, dtype=np.float32) if not torch.is_tensor(obs) else obs)
     x = x.to(self.device, torch.float32).reshape(-1, self.S + (engine.IMG_ELEMS if self.has_img else 0)).contiguous()
@@ -376,19 +389,49 @@ class PPOUpdateEngine:
     value = torch.empty((n, 1), device=self.device, dtype=torch.float32)
     ppf, pvf = self._aux_plan(n, "pf"), self._aux_plan(n, "vf")
     if self.precision == "f16":
-      imgs = torch.empty((n, 16, 16, 64), device=self.device, dtype=torch.float16)
+      imgs = imgs_out if imgs_out is not None else torch.empty((n, 16, 16, 64), device=self.device, dtype=torch.float16)
       self.ops.ingest_img(x[:, self.S:].contiguous(), imgs, n)
       st = torch.zeros((n, ppf.Sp), device=self.device, dtype=torch.float16)
-      self.ops.gather_rows_f16(x, True, None, st, n, self.S, x.shape[1], ppf.Sp)
+      if self.S:
+        self.ops.gather_rows_f16(x, True, None, st, n, self.S, x.shape[1], ppf.Sp)
+        if state_out is not None:
+          state_out.copy_(x[:, :self.S])
       ppf.pack(self.pf_flat)
       ppf.forward(self.pf_flat, imgs, None, st, n, mean)
       pvf.pack(self.vf_flat)
-      pvf.forward(self.vf_flat, imgs, None, st, n, value)
+      pvf.forward(self.vf_flat, imgs, None, st, n, value, enc_from=ppf)
     else:
       inp = engine.Input.from_flat(x, self.S, self.has_img)
       ppf.forward(self.P_pf, inp, mean)
       pvf.forward(self.P_vf, inp, value)
     return mean, value
+
+  def act(self, obs, noise=None, row=None):
+    """One collector step on the device (reference collector/on_policy.py:90-118 calls
+    `pf.explore(ob)` and `vf(ob)` separately, builds and drops two autograd graphs and round-trips twice):
+    actions a = mean + std * eps and values for the E observations of one env step, with one shared-encoder pass
+    (`infer`).  row = t: the converted observation rows are written straight into the device-resident rollout
+    planes at time row t (fp16 space-to-depth image + proprio), so that an epoch whose T rows were all acted on
+    here needs no observation H2D in `update_per_epoch` at all.  noise: optional [E, A] standard-normal draw (for
+    reproducible tests), else drawn on the device.  Returns host arrays shaped like the reference's outputs."""
+    E = int(np.shape(obs)[0]) if not torch.is_tensor(obs) else int(obs.shape[0])
+    imgs_out = state_out = None
+    r = self._roll
+    if row is not None and self.precision == "f16" and self.has_img and r is not None and r["E"] == E and 0 <= row < r["T"]:
+      imgs_out = r["imgs"][row * E:(row + 1) * E]
+      state_out = r["state"][row * E:(row + 1) * E] if self.S else None
+      self._resident_rows = getattr(self, "_resident_rows", set())
+      self._resident_rows.add(int(row))
+    mean, value = self.infer(obs, imgs_out, state_out)
+    log_std = torch.clamp(self.logstd, -5.0, 2.0)
+    std = torch.exp(log_std)
+    eps = torch.as_tensor(noise, dtype=torch.float32, device=self.device) if noise is not None else torch.randn_like(mean)
+    action = mean + std * eps
+    ent = (0.5 + 0.5 * np.log(2 * np.pi) + log_std).sum().expand(E, 1)
+    out = torch.cat([action, mean, value, ent], 1).cpu().numpy()          # ONE device -> host copy
+    A = self.A
+    return {"action": out[:, :A], "mean": out[:, A:2 * A], "value": out[:, 2 * A:2 * A + 1], "ent": out[:, 2 * A + 1:],
+            "log_std": log_std.cpu().numpy(), "std": std.cpu().numpy()}
 
   # ---------------------------------------------------------------------------------------------
   # one epoch
