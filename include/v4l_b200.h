@@ -144,8 +144,7 @@ int v4l_tc_attn_bwd(v4l_ctx* ctx, void* stream, const void* qkv, const float* p,
  * fp16 [N_pad, n_taps * C] (tap-major K).  x_idx (optional, P % 128 == 0): image i of the problem is
  * image x_idx[i] of x.  mode bits 0-3: 1 = one copy of the tile, shifted descriptor starts (default);
  * 0 = one pre-shifted copy per (shift mod 8), atom-aligned starts.  Bits 4-7: tiles whose MMAs are
- * issued interleaved (0 = 2).  Bit 8 (0x100): EXPERIMENTAL swapped operand roles for the conv1 shape
- * (weights as the 128-row operand, a whole 256-position image as N) — not used by the plans yet.   */
+ * issued interleaved (0 = 2).                                                                    */
 typedef struct v4l_tc_conv_flat_args {
   const void* x; int64_t x_rows; int32_t C, P, Wg, Hout, Wout;
   int32_t n_taps; int32_t tap_dw[16], tap_dh[16];

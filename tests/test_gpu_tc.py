@@ -523,29 +523,6 @@ def test_half_image_staging_is_bit_identical():
   assert outs[0][1] == outs[1][1]
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("V4L_EXPERIMENTAL"), reason="staged kernel (DESIGN.md §8.1a), not on the product path: V4L_EXPERIMENTAL=1 to run")
-def test_tc_conv_flat_swapped_roles_conv1():
-  """conv1 with the operand roles swapped (weights = 128-row A operand, one image = N of 256)."""
-  engine, ops = _ops()
-  from vision4leg_b200.engine import RM, RELU
-  torch.manual_seed(11)
-  B, Nimg = 37, 111
-  taps2 = [(dx, dy) for dy in range(2) for dx in range(2)]
-  x = (torch.randn(Nimg, 16, 16, 64, device=DEV) * 0.5).half()
-  idx = torch.randperm(Nimg, device=DEV)[:B].int().contiguous()
-  oh, ow = np.meshgrid(np.arange(15), np.arange(15), indexing="ij")
-  pos = torch.tensor((((oh // 2) * 8 + ow // 2) * 128 + ((oh % 2) * 2 + ow % 2) * 32).ravel().astype(np.int32), device=DEV)
-  w = (torch.randn(32, 256, device=DEV) * 0.05).half()
-  bias = torch.randn(32, device=DEV) * 0.1
-  ref = torch.zeros(B, 8, 8, 128, device=DEV, dtype=torch.float16)
-  out = torch.zeros(B, 8, 8, 128, device=DEV, dtype=torch.float16)
-  cm = lambda: RM(225, 8 * 8 * 128, 0, 0, pos_off=pos)
-  ops.tc_gemm(x, (Nimg, 16, 16, 64), (B, 15, 15), (15, 8, 1), taps2, 1, w, 32, 32, bias, ref, cm(), flags=RELU, a_idx=idx)
-  ops.tc_conv_flat(x, 64, 256, 16, 15, 15, taps2, w, 32, 32, bias, out, cm(), B, x_idx=idx, flags=RELU, mode=0x101)
-  torch.cuda.synchronize()
-  assert rel(out.float(), ref.float()) < 1e-3
-
-
 def test_tc_wgrad_conv1_single_load_matches_generic_and_torch():
   """v4l_tc_wgrad_conv1 (each pixel window / dY cell loaded once, sub-positions summed from TMEM) against the
   generic tap-box weight gradient on the same cell-layout gradient and against torch's conv2d backward."""

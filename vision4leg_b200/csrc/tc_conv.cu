@@ -268,198 +268,6 @@ __global__ void __launch_bounds__(CV_THREADS, 1) tc_conv_flat_kernel(const __gri
 }
 
 
-// ------------------------------------------------------------------------------------------------
-// EXPERIMENTAL (not on the product path; mode bit 0x100; round-2 item): the same
-// single-load convolution with the operand roles swapped for narrow layers.  A tcgen05.mma costs about
-// the same whatever its N is, so with 32 output channels as N only 1/8 of its width is used.  Here the
-// weights are the 128-row A operand (32 channels replicated 4x so that every TMEM lane quadrant holds
-// all channels) and a whole image — 256 flattened positions — is the N operand: D^T[ch, position],
-// half as many MMAs per row and each at full width.  The epilogue transposes 32x32 blocks through
-// shared memory (thread = channel on the TMEM side, thread = position on the store side).
-// Restricted to the conv1 shape: C = 64, P = 256 (16 x 16 grid), 32 output channels, <= 4 taps.
-constexpr int SW_THREADS = 64 + 2 * 128;
-constexpr int SW_W_CHUNK = 128 * 128;          // one tap: 128 rows (4 replicas of 32 channels) x 64 K
-constexpr int SW_STAGE = 256 * 128;            // one image: 256 positions x 64 channels
-constexpr int SW_SLACK = 4096;                 // rows read past the last stage by shifted descriptors
-constexpr int SW_TRANS = 32 * 64;              // per epilogue warp: 32 positions x 32 channels fp16
-
-struct ConvSwapParams {
-  CUtensorMap tm_a;            // [rows_total, 64] box {64, 256}
-  CUtensorMap tm_w;            // [32, n_taps * 64] box {64, 32}
-  int n_taps, shift[4];
-  int Hout, Wout;
-  long long n_img;
-  const int32_t* a_idx;
-  const float* bias;
-  int flags;
-  __half* c;
-  v4l_rowmap c_map;
-  int stages;
-};
-
-__global__ void __launch_bounds__(SW_THREADS, 1) tc_conv_flat_swapped_kernel(const __grid_constant__ ConvSwapParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t full_bar[CV_MAX_STAGES], empty_bar[CV_MAX_STAGES], tmem_full[2], tmem_empty[2], w_bar;
-  __shared__ uint32_t tmem_base_slot;
-
-  v4l_pdl_trigger();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* w_smem = smem;
-  uint8_t* ring = smem + p.n_taps * SW_W_CHUNK;
-  uint8_t* trans = ring + p.stages * SW_STAGE + SW_SLACK;
-  const int n_img = static_cast<int>(p.n_img);
-
-  if (threadIdx.x == 0) {
-    tc::tma_prefetch_desc(&p.tm_a);
-    tc::tma_prefetch_desc(&p.tm_w);
-    for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(&tmem_full[s], 1); tc::mbar_init(&tmem_empty[s], 128); }
-    tc::mbar_init(&w_bar, 1);
-    tc::fence_barrier_init();
-  }
-  if (warp == 1) tc::tmem_alloc(&tmem_base_slot, 512);
-  v4l_pdl_wait();
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem_base = tmem_base_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      tc::mbar_expect_tx(&w_bar, static_cast<uint32_t>(p.n_taps) * SW_W_CHUNK);
-      for (int t = 0; t < p.n_taps; ++t)
-        for (int rep = 0; rep < 4; ++rep)
-          tc::tma_load_2d(w_smem + t * SW_W_CHUNK + rep * 4096, &p.tm_w, &w_bar, t * 64, 0);
-      int stage = 0; uint32_t phase = 0;
-      int idx_next = (p.a_idx && static_cast<int>(blockIdx.x) < n_img) ? p.a_idx[blockIdx.x] : 0;
-      for (int img = blockIdx.x; img < n_img; img += gridDim.x) {
-        const int src = p.a_idx ? idx_next : img;
-        if (p.a_idx && img + static_cast<int>(gridDim.x) < n_img) idx_next = p.a_idx[img + gridDim.x];
-        tc::mbar_wait(&empty_bar[stage], phase ^ 1);
-        tc::mbar_expect_tx(&full_bar[stage], SW_STAGE);
-        tc::tma_load_2d(ring + stage * SW_STAGE, &p.tm_a, &full_bar[stage], 0, src * 256);
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = tc::umma_idesc_f16(128, 256, 0, 0);
-      const uint32_t wb = tc::smem_u32(w_smem), rb = tc::smem_u32(ring);
-      tc::mbar_wait(&w_bar, 0);
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int img = blockIdx.x; img < n_img; img += gridDim.x) {
-        tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tc::mbar_wait(&full_bar[stage], phase);
-        tc::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;
-        const uint32_t sb = rb + stage * SW_STAGE;
-        uint32_t first = 1;
-        for (int t = 0; t < p.n_taps; ++t) {
-          const uint32_t a0 = wb + t * SW_W_CHUNK;
-          const uint32_t b0 = sb + static_cast<uint32_t>(p.shift[t]) * 128u;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            tc::umma_f16(d_tmem, tc::umma_smem_desc(a0 + k * 32, 0, 1024), tc::umma_smem_desc(b0 + k * 32, 0, 1024), idesc,
-                         first ? 0u : 1u);
-            first = 0;
-          }
-        }
-        tc::umma_commit(&empty_bar[stage]);
-        tc::umma_commit(&tmem_full[acc]);
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      }
-    }
-  } else {
-    const int wg = (warp - 2) >> 2;
-    const int quad = warp & 3;                    // TMEM lanes 32*quad .. +31 = weight replica `quad`: lane = channel
-    const bool relu = p.flags & V4L_RELU;
-    const float bias = p.bias ? p.bias[lane] : 0.f;
-    uint8_t* sT = trans + (warp - 2) * SW_TRANS;
-    const int acc = wg;
-    uint32_t acc_phase = 0;
-    for (int img = blockIdx.x + wg * gridDim.x; img < n_img; img += 2 * gridDim.x) {
-      tc::mbar_wait(&tmem_full[acc], acc_phase);
-      tc::tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c0 = quad * 64 + cc * 32;       // this warp's positions c0 .. c0+31 of the image
-        uint32_t v[32];
-        tc::tmem_ld_32x32(taddr + c0, v);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {            // thread = channel: value of position c0+j
-          float f = __uint_as_float(v[j]) + bias;
-          if (relu) f = fmaxf(f, 0.f);
-          *reinterpret_cast<__half*>(sT + j * 64 + lane * 2) = __float2half(f);
-        }
-        __syncwarp();
-        const int pos = c0 + lane;                // thread = position: its 32 channels = 64 contiguous bytes
-        const int h = pos >> 4, w = pos & 15;
-        if (h < p.Hout && w < p.Wout) {
-          const long long addr = v4l_row_addr(p.c_map, (img * p.Hout + h) * p.Wout + w);
-          const uint4* src = reinterpret_cast<const uint4*>(sT + lane * 64);
-          uint4* dst = reinterpret_cast<uint4*>(p.c + addr);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) dst[q] = src[q];
-        }
-        __syncwarp();
-      }
-      tc::tc_fence_before();
-      tc::mbar_arrive(&tmem_empty[acc]);
-      acc_phase ^= 1;
-    }
-  }
-  __syncthreads();
-  if (warp == 1) {
-    tc::tc_fence_after();
-    tc::tmem_dealloc(tmem_base, 512);
-  }
-}
-
-static int launch_swapped(v4l_ctx* ctx, void* stream, const v4l_tc_conv_flat_args* a) {
-  V4L_REQUIRE(a->C == 64 && a->P == 256 && a->Wg == 16 && a->N_pad == 32 && a->N_valid == 32 && a->n_taps <= 4,
-              "v4l_tc_conv_flat (swapped roles): only the conv1 shape (C=64, 16x16 grid, 32 channels, <= 4 taps)");
-  ConvSwapParams p;
-  memset(&p, 0, sizeof(p));
-  p.n_taps = a->n_taps;
-  for (int t = 0; t < a->n_taps; ++t) {
-    V4L_REQUIRE(a->tap_dh[t] >= 0 && a->tap_dw[t] >= 0, "v4l_tc_conv_flat: taps must be non-negative");
-    p.shift[t] = a->tap_dh[t] * a->Wg + a->tap_dw[t];
-    V4L_REQUIRE(p.shift[t] <= 24, "v4l_tc_conv_flat (swapped roles): tap reach too large");
-  }
-  p.Hout = a->Hout; p.Wout = a->Wout; p.n_img = a->n_img;
-  p.a_idx = a->x_idx; p.bias = a->bias; p.flags = a->flags;
-  p.c = reinterpret_cast<__half*>(a->c); p.c_map = a->c_map;
-  const char* who = "v4l_tc_conv_flat(swapped)";
-  {
-    uint64_t dims[2] = {64, (uint64_t)a->x_rows};
-    uint64_t str[1] = {128};
-    uint32_t box[2] = {64, 256};
-    if (int r = v4l_encode_tmap(&p.tm_a, a->x, 2, dims, str, box, who, nullptr)) return r;
-  }
-  {
-    uint64_t dims[2] = {(uint64_t)a->n_taps * 64, 32};
-    uint64_t str[1] = {(uint64_t)a->n_taps * 64 * 2};
-    uint32_t box[2] = {64, 32};
-    if (int r = v4l_encode_tmap(&p.tm_w, a->w, 2, dims, str, box, who, nullptr)) return r;
-  }
-  p.stages = 4;
-  const size_t smem = (size_t)a->n_taps * SW_W_CHUNK + (size_t)p.stages * SW_STAGE + SW_SLACK + 8 * SW_TRANS + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    V4L_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_flat_swapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    attr_set = true;
-  }
-  V4L_LAUNCH(tc_conv_flat_swapped_kernel, (int)min((long long)ctx->sm_count, (long long)a->n_img), SW_THREADS, smem,
-             (cudaStream_t)stream, p);
-  V4L_CHECK_LAUNCH();
-  return 0;
-}
-
 }  // namespace
 
 extern "C" int v4l_tc_conv_flat(v4l_ctx* ctx, void* stream, const v4l_tc_conv_flat_args* a) {
@@ -473,7 +281,6 @@ extern "C" int v4l_tc_conv_flat(v4l_ctx* ctx, void* stream, const v4l_tc_conv_fl
               "v4l_tc_conv_flat: bad grid");
   V4L_REQUIRE(!a->x_idx || a->P % 128 == 0, "v4l_tc_conv_flat: gathered images need P %% 128 == 0");
   if (a->n_img == 0) return 0;
-  if (a->mode & 0x100) return launch_swapped(ctx, stream, a);
   ConvFlatParams p;
   memset(&p, 0, sizeof(p));
   p.P = a->P; p.Wg = a->Wg; p.Hout = a->Hout; p.Wout = a->Wout;
