@@ -317,6 +317,24 @@ int v4l_tc_wgrad_conv1(v4l_ctx* ctx, void* stream, const void* x_s2d, int64_t n_
                        const void* dy_cells, int B, const int32_t* index, float* dw, float* dbias,
                        float out_scale, int defer, int accumulate);
 
+/* ---- a chain of up to three Linear layers in one launch (csrc/tc_mlp.cu): the actor / critic MLP heads
+ * (reference torchrl/networks/nets.py:973-992,1036), the proprio MLP + projector (base.py:8-44,209-230) and
+ * their data-gradient chains.  Per 128-row tile: h = act(x W1^T + b1) [* (mask1 > 0)] stays in shared memory
+ * as the next layer's operand; every layer can also store its result (saved activation / row gradient / fp32
+ * output through a row map).  x: f16 [M, x_cols] with row pitch x_ld; layer l: packed f16 W [N_pad, K]
+ * (v4l_pack_f16 layout, K a multiple of 64; K_l <= 256 for l > 0 = the previous layer's width padded to 64). */
+typedef struct {
+  const void* w; int32_t K, N_pad, N_valid; const float* bias; int32_t relu;
+  const void* mask; int64_t mask_ld;        /* optional f16 [M, mask_ld]: result *= (mask > 0) */
+  void* out; int32_t out_f32; v4l_rowmap out_map;   /* optional global output */
+} v4l_tc_mlp_layer;
+typedef struct {
+  const void* x; int32_t M, x_cols; int64_t x_ld;
+  int32_t n_layers;
+  v4l_tc_mlp_layer layer[3];
+} v4l_tc_mlp_chain_args;
+int v4l_tc_mlp_chain(v4l_ctx* ctx, void* stream, const v4l_tc_mlp_chain_args* args);
+
 /* ---- fused optimiser tail of one network pass (tensor-core tier; csrc/step_ops.cu):
  * phase 1  split-K reduction of all deferred weight-gradient partials into the fp32 gradient bucket
  *          (accumulating the squared norm of what it writes);

@@ -552,3 +552,60 @@ def test_tc_wgrad_conv1_single_load_matches_generic_and_torch():
     # accumulate: a second pass adds onto the first
     ops.tc_wgrad_conv1(s2d, idx, cells, B, index, dw, db, out_scale=0.5, defer=False, accumulate=True)
     assert rel(dw, w.grad) < 1e-4 and rel(db, b.grad) < 1e-4
+
+
+@pytest.mark.parametrize("M,K0,out_dim", [(1024, 128, 12), (300, 512, 1), (77, 64, 64)])
+def test_tc_mlp_chain_forward_and_dgrad(M, K0, out_dim):
+  """v4l_tc_mlp_chain: three Linear layers (ReLU, ReLU, linear) in one launch against torch, every layer's
+  stored output; then the data-gradient chain (masked by the forward activations) against autograd."""
+  engine, ops = _ops()
+  RM = engine.RM
+  torch.manual_seed(M + K0)
+  dims = [(256, K0), (256, 256), (out_dim, 256)]
+  Ws = [bf(torch.randn(n, k, device=DEV) / math.sqrt(k)) for n, k in dims]
+  bs = [torch.randn(n, device=DEV) * 0.1 for n, _ in dims]
+  x = bf(torch.randn(M, K0, device=DEV))
+
+  def pack(w):      # [N, K] -> [ceil16(N), ceil64(K)] zero padded
+    n, k = w.shape
+    p = torch.zeros((n + 15) // 16 * 16, (k + 63) // 64 * 64, device=DEV, dtype=torch.float16)
+    p[:n, :k] = w
+    return p
+  h1 = torch.full((M, 256), float("nan"), device=DEV, dtype=torch.float16)
+  h2 = torch.full((M, 256), float("nan"), device=DEV, dtype=torch.float16)
+  y = torch.full((M, out_dim), float("nan"), device=DEV)
+  layers = []
+  for (n, k), w, b, out, relu, f32 in zip(dims, Ws, bs, (h1, h2, y), (True, True, False), (False, False, True)):
+    pw = pack(w)
+    layers.append(dict(w=pw, K=pw.shape[1], N_pad=pw.shape[0], N_valid=n, bias=b, relu=relu, out=out, out_f32=f32,
+                       out_map=RM.dense(out.shape[1])))
+  ops.tc_mlp_chain(x, M, K0, K0, layers)
+  torch.cuda.synchronize()
+  r1 = F.relu(F.linear(x.float(), Ws[0].float(), bs[0]))
+  r2 = F.relu(F.linear(r1.half().float(), Ws[1].float(), bs[1]))
+  r3 = F.linear(r2.half().float(), Ws[2].float(), bs[2])
+  assert rel(h1.float(), r1) < 5e-3 and rel(h2.float(), r2) < 5e-3 and rel(y, r3) < 5e-3
+  # data-gradient chain: g [M, 16] (out_dim valid) -> dh2 (gate h2) -> dh1 (gate h1) -> dx
+  g = torch.zeros(M, 16 if out_dim <= 16 else 64, device=DEV, dtype=torch.float16)
+  g[:, :out_dim] = bf(torch.randn(M, out_dim, device=DEV))
+  dh2 = torch.full((M, 256), float("nan"), device=DEV, dtype=torch.float16)
+  dh1 = torch.full((M, 256), float("nan"), device=DEV, dtype=torch.float16)
+  dx = torch.full((M, K0), float("nan"), device=DEV, dtype=torch.float16)
+  back = []
+  for w, out, mask in ((Ws[2], dh2, h2), (Ws[1], dh1, h1), (Ws[0], dx, None)):
+    pw = pack(w.t().contiguous())        # [K, N] -> rows = fwd K (outputs of the data gradient), cols = fwd N
+    back.append(dict(w=pw, K=pw.shape[1], N_pad=pw.shape[0], N_valid=w.shape[1], relu=False, mask=mask,
+                     mask_ld=(mask.shape[1] if mask is not None else 0), out=out, out_f32=False, out_map=RM.dense(out.shape[1])))
+  if K0 <= 256:
+    ops.tc_mlp_chain(g, M, g.shape[1], g.shape[1], back)
+    n_back = 3
+  else:                                  # a 512-wide last data gradient does not fit one MMA N: two-layer chain
+    ops.tc_mlp_chain(g, M, g.shape[1], g.shape[1], back[:2])
+    n_back = 2
+  torch.cuda.synchronize()
+  gg = g[:, :out_dim].float()
+  e2 = (gg @ Ws[2].float()) * (h2.float() > 0)
+  e1 = (e2.half().float() @ Ws[1].float()) * (h1.float() > 0)
+  assert rel(dh2.float(), e2) < 5e-3 and rel(dh1.float(), e1) < 5e-3
+  if n_back == 3:
+    assert rel(dx.float(), e1.half().float() @ Ws[0].float()) < 5e-3

@@ -76,6 +76,17 @@ class TcWgradArgs(C.Structure):
               ("dbias", C.c_void_p), ("defer", C.c_int32), ("accumulate", C.c_int32)]
 
 
+class TcMlpLayer(C.Structure):
+  _fields_ = [("w", C.c_void_p), ("K", C.c_int32), ("N_pad", C.c_int32), ("N_valid", C.c_int32), ("bias", C.c_void_p),
+              ("relu", C.c_int32), ("mask", C.c_void_p), ("mask_ld", C.c_int64), ("out", C.c_void_p),
+              ("out_f32", C.c_int32), ("out_map", RowMap)]
+
+
+class TcMlpChainArgs(C.Structure):
+  _fields_ = [("x", C.c_void_p), ("M", C.c_int32), ("x_cols", C.c_int32), ("x_ld", C.c_int64), ("n_layers", C.c_int32),
+              ("layer", TcMlpLayer * 3)]
+
+
 class OptTailArgs(C.Structure):
   _fields_ = [("phases", C.c_int32), ("param", C.c_void_p), ("grad", C.c_void_p), ("m", C.c_void_p),
               ("v", C.c_void_p), ("n", C.c_int64), ("hyper", C.c_void_p), ("info", C.c_void_p),
@@ -149,6 +160,7 @@ SIGNATURES = {
   "v4l_tc_wgrad": [_vp, _vp, C.POINTER(TcWgradArgs)],
   "v4l_tc_wgrad_flush": [_vp, _vp],
   "v4l_tc_wgrad_conv1": [_vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _f, _i, _i],
+  "v4l_tc_mlp_chain": [_vp, _vp, C.POINTER(TcMlpChainArgs)],
   "v4l_opt_tail": [_vp, _vp, C.POINTER(OptTailArgs)],
   "v4l_opt_tail_error": [_vp],
   "v4l_mb_begin": [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i],

@@ -24,6 +24,7 @@ from ... import engine_tc
 from ..._lib import INFO_KEYS, INFO_STRIDE, INFO_GRAD_NORM_PF, INFO_GRAD_NORM_VF, V4LError
 
 _ALIGN = 4   # floats (16 B)
+GRAPH_GROUP = 4   # minibatches per CUDA-graph replay in the later opt-epochs
 
 
 def _round_up(n, a):
@@ -635,12 +636,17 @@ class PPOUpdateEngine:
       if pending is not None:
         with self.ops.fork(2):          # order the copy stream after the index upload / previous epoch
           pass
-      for k in range(n_mb):
+      k = 0
+      while k < n_mb:
         if pending is not None and k < n_full:
           # interleaved with the launches so the CPU never runs far behind the GPU
           ev = self._stream_chunk(pending[0], pending[1], perms[0][k * rows:(k + 1) * rows], E, k, rows)
           cur.wait_event(ev)               # rows of minibatch k (first opt-epoch) have landed
-        self._launch(B, with_target=k < n_full)
+        # later opt-epochs need no per-minibatch gating: GRAPH_GROUP minibatches per graph replay (one launch
+        # latency per group instead of per minibatch)
+        group = GRAPH_GROUP if (k >= n_full and n_mb - k >= GRAPH_GROUP and self.precision == "f16") else 1
+        self._launch(B, with_target=k < n_full, count=group)
+        k += group
     else:
       if getattr(self, "_pending_obs", None) is not None:
         obs, D = self._pending_obs
@@ -655,27 +661,31 @@ class PPOUpdateEngine:
     self.d2h_bytes = info.nbytes
     return [dict(zip(INFO_KEYS, (float(x) for x in row))) for row in info]
 
-  def _launch(self, B, with_target=True):
+  def _launch(self, B, with_target=True, count=1):
     """with_target: this minibatch visits its rows for the first time in this epoch (first opt-epoch):
-    the graph variant that also runs the frozen target policy's forward."""
+    the graph variant that also runs the frozen target policy's forward.  count: consecutive minibatches
+    captured in (and replayed as) one graph."""
     if self.precision != "f16":
       with_target = True                      # the exact tier recomputes the target forward every time
     if not self.use_cuda_graph:
-      self._minibatch(B, with_target)
+      for _ in range(count):
+        self._minibatch(B, with_target)
       return
-    key = (B, with_target)
+    key = (B, with_target, count)
     g = self._graphs.get(key)
     if g is None:
       if not self._graphs.get(("warm", B)):
         # first minibatch at this size runs eagerly: allocates workspaces, loads modules
-        self._minibatch(B, with_target)
+        for _ in range(count):
+          self._minibatch(B, with_target)
         self._graphs[("warm", B)] = True
         return
       torch.cuda.synchronize(self.device)
       g = torch.cuda.CUDAGraph()
       launches0 = self.ops.launches
       with torch.cuda.graph(g):
-        self._minibatch(B, with_target)
+        for _ in range(count):
+          self._minibatch(B, with_target)
       self._graphs[key] = (g, self.ops.launches - launches0)
       g = self._graphs[key]
     else:

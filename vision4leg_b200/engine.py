@@ -227,6 +227,24 @@ class Ops:
       algo_flops = 2.0 * out_grid[0] * out_grid[1] * out_grid[2] * N_valid * (len(taps) * x_shape[3] + 1)
     self._note("v4l_tc_wgrad", g, algo_flops)
 
+  def tc_mlp_chain(self, x, M, x_cols, x_ld, layers):
+    """up to three chained Linear layers in one launch (v4l_tc_mlp_chain).  layers: list of dicts with keys
+    w, K, N_pad, N_valid, bias, relu, mask, mask_ld, out, out_f32, out_map (RM)"""
+    g = _lib.TcMlpChainArgs()
+    g.x, g.M, g.x_cols, g.x_ld, g.n_layers = ptr(x), M, x_cols, x_ld, len(layers)
+    flops = 0.0
+    for i, L in enumerate(layers):
+      e = g.layer[i]
+      e.w, e.K, e.N_pad, e.N_valid = ptr(L["w"]), L["K"], L["N_pad"], L["N_valid"]
+      e.bias, e.relu = ptr(L.get("bias")), 1 if L.get("relu") else 0
+      e.mask, e.mask_ld = ptr(L.get("mask")), L.get("mask_ld", 0)
+      e.out, e.out_f32 = ptr(L.get("out")), 1 if L.get("out_f32") else 0
+      e.out_map = (L.get("out_map") or RM()).c()
+      flops += 2.0 * M * L["N_valid"] * L.get("K_true", L["K"])
+    check(self.lib.v4l_tc_mlp_chain(self.h, self.ctx.stream(), C.byref(g)))
+    self.launches += 1
+    self._note("v4l_tc_mlp_chain", g, flops, tuple(layers))
+
   def tc_wgrad_conv1(self, x_s2d, x_idx, dy_cells, B, index, dw, dbias, out_scale=1.0, defer=True, accumulate=False):
     """conv1 weight + bias gradient on the space-to-depth image / cell layouts (v4l_tc_wgrad_conv1)"""
     check(self.lib.v4l_tc_wgrad_conv1(self.h, self.ctx.stream(), ptr(x_s2d), x_s2d.shape[0], ptr(x_idx), ptr(dy_cells),

@@ -80,6 +80,10 @@ def _conv_tables(off, N, C, KH, KW, s):
 FUSED_LAYER = True
 N_WGRAD_STREAMS = 4
 FLAT_CONV1 = True
+# 3-layer heads / proprio MLP and their data-gradient chains as ONE launch (csrc/tc_mlp.cu).  Correct (tests) but
+# NOT faster at minibatch 1024, so off: 8 row tiles = 8 CTAs each streaming all 200 KB of weights (17-24 us per chain)
+# against three launches that slice N over 32 CTAs (5-6 us each); profiles/r2_mlp_chain_note.txt
+MLP_CHAIN = False
 CONV1_WGRAD_S2D = True            # conv1 weight gradient by the single-load kernel (False: generic v4l_tc_wgrad)
 
 
@@ -174,6 +178,20 @@ class _PlanTC:
     bias = self._view(flat, wname[:-6] + "bias")
     self.ops.tc_gemm(x, (M, 1, 1, K), (M, 1, 1), (1, 1, 128), [(0, 0)], pk.cols // 64, pk.w, pk.rows, N, bias,
                      out, out_map, c_f32=c_f32, flags=RELU if relu else 0)
+
+  def _chain(self, flat, x, M, x_cols, x_ld, specs, dgrad=False):
+    """Linear layers `specs` = [(weight name, relu, out, out_map, out_f32, mask)] chained in one launch.
+    dgrad: use the data-gradient (transposed) packing and no bias."""
+    layers = []
+    for wname, relu, out, out_map, f32, mask in specs:
+      pk = (self.W.dgr if dgrad else self.W.fwd)[wname]
+      shape = self.layout[wname][1]
+      N_out, K_in = (int(np.prod(shape[1:])), shape[0]) if dgrad else (shape[0], int(np.prod(shape[1:])))
+      layers.append(dict(w=pk.w, K=pk.cols, N_pad=pk.rows, N_valid=N_out, K_true=K_in,
+                         bias=None if dgrad else self._view(flat, wname[:-6] + "bias"), relu=relu,
+                         mask=mask, mask_ld=(mask.shape[-1] if mask is not None else 0),
+                         out=out, out_f32=f32, out_map=out_map))
+    self.ops.tc_mlp_chain(x, M, x_cols, x_ld, layers)
 
   def _side(self, fn, which=None):
     """Run `fn` on a side stream, ordered after what has been issued so far.  Weight-gradient
@@ -322,6 +340,11 @@ class LocoPlanTC(_PlanTC):
     s1 = self.buf("s1", (B, 256)); s2 = self.buf("s2", (B, 256))
 
     def state_branch():      # proprio MLP -> token 0: independent of the conv trunk
+      if MLP_CHAIN:
+        self._chain(flat, st, B, self.Sp, self.Sp, [
+          (self.k_base[0], True, s1, RM.dense(256), False, None), (self.k_base[1], True, s2, RM.dense(256), False, None),
+          ("encoder.state_projector.projection.0.weight", True, tok, RM.slots(1, T, d, 0), False, None)])
+        return
       self._lin_fwd(flat, self.k_base[0], st, B, self.Sp, s1, RM.dense(256), True)
       self._lin_fwd(flat, self.k_base[1], s1, B, 256, s2, RM.dense(256), True)
       self._lin_fwd(flat, "encoder.state_projector.projection.0.weight", s2, B, 256, tok, RM.slots(1, T, d, 0), True)
@@ -377,6 +400,11 @@ class LocoPlanTC(_PlanTC):
     pooled = self.buf("pooled", (B, self.pd))
     ops.pool_fwd_f16(x, pooled, B, T, d, 0 if self.has_state else 1)
     h1 = self.buf("h1", (B, 256)); h2 = self.buf("h2", (B, 256))
+    if MLP_CHAIN:
+      self._chain(flat, pooled, B, self.pd, self.pd, [
+        (self.k_head[0], True, h1, RM.dense(256), False, None), (self.k_head[1], True, h2, RM.dense(256), False, None),
+        (self.k_head[2], False, out, out_map or RM.dense(self.out_dim), True, None)])
+      return out
     self._lin_fwd(flat, self.k_head[0], pooled, B, self.pd, h1, RM.dense(256), True)
     self._lin_fwd(flat, self.k_head[1], h1, B, 256, h2, RM.dense(256), True)
     self._lin_fwd(flat, self.k_head[2], h2, B, 256, out, out_map or RM.dense(self.out_dim), False, c_f32=True)
@@ -432,9 +460,14 @@ class LocoPlanTC(_PlanTC):
     pd = self.pd
     h1, h2, pooled = ws[("h1", B, 256)], ws[("h2", B, 256)], ws[("pooled", B, pd)]
     dh2 = self.buf("dh2", (B, 256)); dh1 = self.buf("dh1", (B, 256)); dpool = self.buf("dpool", (B, pd))
-    self._lin_bwd(gflat, self.k_head[2], h2, 256, g16, 16, B, dh2, RM.dense(256), mask=h2)
-    self._lin_bwd(gflat, self.k_head[1], h1, 256, dh2, 256, B, dh1, RM.dense(256), mask=h1)
-    self._lin_bwd(gflat, self.k_head[0], pooled, pd, dh1, 256, B, dpool, RM.dense(pd))
+    if MLP_CHAIN:      # the three data gradients in one launch, then the weight gradients (side streams) from its outputs
+      self._chain(flat, g16, B, 16, 16, [
+        (self.k_head[2], False, dh2, RM.dense(256), False, h2), (self.k_head[1], False, dh1, RM.dense(256), False, h1),
+        (self.k_head[0], False, dpool, RM.dense(pd), False, None)], dgrad=True)
+    chain = MLP_CHAIN
+    self._lin_bwd(gflat, self.k_head[2], h2, 256, g16, 16, B, dh2, RM.dense(256), mask=h2, need_dx=not chain)
+    self._lin_bwd(gflat, self.k_head[1], h1, 256, dh2, 256, B, dh1, RM.dense(256), mask=h1, need_dx=not chain)
+    self._lin_bwd(gflat, self.k_head[0], pooled, pd, dh1, 256, B, dpool, RM.dense(pd), need_dx=not chain)
     dx = self.buf("dx_top", (R, d))
     ops.pool_bwd_f16(dpool, dx, B, T, d, 0 if self.has_state else 1)
     # every gradient tensor below is written once and then only read (no in-place accumulation,
@@ -471,8 +504,12 @@ class LocoPlanTC(_PlanTC):
 
     def state_branch():      # whole proprio-branch backward off the critical path
       ops.relu_bwd_f16(dx, smap, tok, smap, ds, RM.dense(d), B, d)
-      self._lin_bwd(gflat, "encoder.state_projector.projection.0.weight", s2, 256, ds, d, B, ds2, RM.dense(256), mask=s2)
-      self._lin_bwd(gflat, self.k_base[1], s1, 256, ds2, 256, B, ds1, RM.dense(256), mask=s1)
+      proj = "encoder.state_projector.projection.0.weight"
+      if MLP_CHAIN:
+        self._chain(flat, ds, B, d, d, [(proj, False, ds2, RM.dense(256), False, s2),
+                                        (self.k_base[1], False, ds1, RM.dense(256), False, s1)], dgrad=True)
+      self._lin_bwd(gflat, proj, s2, 256, ds, d, B, ds2, RM.dense(256), mask=s2, need_dx=not MLP_CHAIN)
+      self._lin_bwd(gflat, self.k_base[1], s1, 256, ds2, 256, B, ds1, RM.dense(256), mask=s1, need_dx=not MLP_CHAIN)
       self._lin_bwd(gflat, self.k_base[0], self._st, self.Sp, ds1, 256, B, need_dx=False)
     if self.has_state:
       self._side(state_branch, which=0)
@@ -518,6 +555,11 @@ class NaturePlanTC(_PlanTC):
       self._lin_fwd(flat, self.k_base[0], st, B, self.Sp, s1, RM.dense(256), True)
       self._lin_fwd(flat, self.k_base[1], s1, B, 256, cat, RM(1, W, 0, self.vd), True)
     h1 = self.buf("h1", (B, 256)); h2 = self.buf("h2", (B, 256))
+    if MLP_CHAIN:
+      self._chain(flat, cat, B, W, W, [
+        (self.k_head[0], True, h1, RM.dense(256), False, None), (self.k_head[1], True, h2, RM.dense(256), False, None),
+        (self.k_head[2], False, out, out_map or RM.dense(self.out_dim), True, None)])
+      return out
     self._lin_fwd(flat, self.k_head[0], cat, B, W, h1, RM.dense(256), True)
     self._lin_fwd(flat, self.k_head[1], h1, B, 256, h2, RM.dense(256), True)
     self._lin_fwd(flat, self.k_head[2], h2, B, 256, out, out_map or RM.dense(self.out_dim), False, c_f32=True)
@@ -529,8 +571,11 @@ class NaturePlanTC(_PlanTC):
     g16 = self._begin_backward(d_out, B)
     cat, h1, h2, s1, a3 = ws[("cat", B, W)], ws[("h1", B, 256)], ws[("h2", B, 256)], ws[("s1", B, 256)], ws[("a3", B, 16, 64)]
     dh2 = self.buf("dh2", (B, 256)); dh1 = self.buf("dh1", (B, 256)); dcat = self.buf("dcat", (B, W))
-    self._lin_bwd(gflat, self.k_head[2], h2, 256, g16, 16, B, dh2, RM.dense(256), mask=h2)
-    self._lin_bwd(gflat, self.k_head[1], h1, 256, dh2, 256, B, dh1, RM.dense(256), mask=h1)
+    if MLP_CHAIN:      # the first two data gradients in one launch (the third is 512 wide: its own GEMM)
+      self._chain(self._flat, g16, B, 16, 16, [(self.k_head[2], False, dh2, RM.dense(256), False, h2),
+                                               (self.k_head[1], False, dh1, RM.dense(256), False, h1)], dgrad=True)
+    self._lin_bwd(gflat, self.k_head[2], h2, 256, g16, 16, B, dh2, RM.dense(256), mask=h2, need_dx=not MLP_CHAIN)
+    self._lin_bwd(gflat, self.k_head[1], h1, 256, dh2, 256, B, dh1, RM.dense(256), mask=h1, need_dx=not MLP_CHAIN)
     self._lin_bwd(gflat, self.k_head[0], cat, W, dh1, 256, B, dcat, RM.dense(W), mask=cat)
     # proprio MLP: dy = dcat[:, vd:]
     ds1 = self.buf("ds1", (B, 256))
@@ -566,6 +611,11 @@ class NatureVOPlanTC(_PlanTC):
     self._flat, self._B, self._imgs, self._idx, self._st = flat, B, imgs, idx, st
     a3 = enc_from._ws[("a3", B, 16, 64)] if enc_from is not None else self._trunk_fwd(flat, imgs, idx, B, "encoder.layers.")
     h1 = self.buf("h1", (B, 256)); h2 = self.buf("h2", (B, 256))
+    if MLP_CHAIN:
+      self._chain(flat, a3, B, 1024, 1024, [
+        (self.k_head[0], True, h1, RM.dense(256), False, None), (self.k_head[1], True, h2, RM.dense(256), False, None),
+        (self.k_head[2], False, out, out_map or RM.dense(self.out_dim), True, None)])
+      return out
     self._lin_fwd(flat, self.k_head[0], a3, B, 1024, h1, RM.dense(256), True)
     self._lin_fwd(flat, self.k_head[1], h1, B, 256, h2, RM.dense(256), True)
     self._lin_fwd(flat, self.k_head[2], h2, B, 256, out, out_map or RM.dense(self.out_dim), False, c_f32=True)
@@ -576,8 +626,11 @@ class NatureVOPlanTC(_PlanTC):
     g16 = self._begin_backward(d_out, B)
     h1, h2, a3 = ws[("h1", B, 256)], ws[("h2", B, 256)], ws[("a3", B, 16, 64)]
     dh2 = self.buf("dh2", (B, 256)); dh1 = self.buf("dh1", (B, 256)); da3 = self.buf("da3", (B, 16, 64))
-    self._lin_bwd(gflat, self.k_head[2], h2, 256, g16, 16, B, dh2, RM.dense(256), mask=h2)
-    self._lin_bwd(gflat, self.k_head[1], h1, 256, dh2, 256, B, dh1, RM.dense(256), mask=h1)
+    if MLP_CHAIN:
+      self._chain(self._flat, g16, B, 16, 16, [(self.k_head[2], False, dh2, RM.dense(256), False, h2),
+                                               (self.k_head[1], False, dh1, RM.dense(256), False, h1)], dgrad=True)
+    self._lin_bwd(gflat, self.k_head[2], h2, 256, g16, 16, B, dh2, RM.dense(256), mask=h2, need_dx=not MLP_CHAIN)
+    self._lin_bwd(gflat, self.k_head[1], h1, 256, dh2, 256, B, dh1, RM.dense(256), mask=h1, need_dx=not MLP_CHAIN)
     # first head layer: da3 comes out in our (p, c) order through the packing table, masked by the trunk's ReLU
     self._lin_bwd(gflat, self.k_head[0], a3, 1024, dh1, 256, B, da3, RM.dense(1024), mask=a3)
     self._trunk_bwd(gflat, da3, B, "encoder.layers.")
