@@ -70,6 +70,7 @@ def parse():
   ap.add_argument("--sweep-batch", type=int, default=65536, help="GLOBAL minibatch of the strong-scaling sweep")
   ap.add_argument("--sweep-steps", type=int, default=1)
   ap.add_argument("--sweep-timeout", type=int, default=300)
+  ap.add_argument("--sweep-envs", type=int, default=8, help="env columns of the sweep's rollout (8 = BASELINE configs[4])")
   ap.add_argument("--no-roofline", action="store_true")
   return ap.parse_args()
 
@@ -645,7 +646,7 @@ def strong_sweep(args, dev, pg, world, rank, pf_np, vf_np, barrier, max_over_ran
   generated ON THE DEVICE in the layouts the engine keeps resident (fp16 space-to-depth image, fp32 proprio
   rows): this is the resident (`value`) figure of the sweep; the end-to-end figure is the weak line's."""
   from benchutil.harness import build_nets, load_np_sd, make_ppo
-  S, A, E = args.S, args.A, 8
+  S, A, E = args.S, args.A, args.sweep_envs
   if world > E or E % world or args.sweep_batch % world or (args.sweep_batch // world) % (E // world):
     return {"skipped": "world size %d does not divide the %d env columns / the minibatch" % (world, E)}
   El = E // world

@@ -63,3 +63,21 @@ def test_act_matches_modules_and_feeds_the_update(family):
   assert runs["host"][1] == runs["host"][2]
   # ... and trained on exactly the same data: bit-identical parameters
   assert torch.equal(runs["host"][0], runs["device"][0])
+
+
+def test_single_env_bootstrap_value_and_act():
+  """E = 1 (one env column per rank in the 8-GPU strong-scaling sweep): a one-row slice x[:, S:] is already
+  "contiguous" and keeps its 4*S-byte offset — the image must still reach the vectorised ingest kernel aligned."""
+  S, A = g.FAMILIES["loco"]
+  T, E, B = 8, 1, 4
+  roll = synth.make_rollout(78, T, E, S, A, p_term=0.1)
+  buf = fill_buffer(roll, T, E)
+  agent, pf, vf = _agent("loco", buf, B, T * E)
+  agent.current_epoch = 1
+  np.random.seed(5)
+  agent.update_per_epoch()
+  out = agent.engine.act(roll["obs"][0], noise=np.zeros((E, A), np.float32))
+  torch.cuda.synchronize()
+  with torch.no_grad():
+    ref = vf(torch.tensor(roll["obs"][0], device=DEV)).cpu().numpy()
+  assert g.rel_err(out["value"], ref) < 1e-2

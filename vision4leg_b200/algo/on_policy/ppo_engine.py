@@ -344,7 +344,7 @@ class PPOUpdateEngine:
     plan = self._aux_plan(E)
     if self.precision == "f16":
       imgs = torch.empty((E, 16, 16, 64), device=self.device, dtype=torch.float16)
-      self.ops.ingest_img(x[:, self.S:].contiguous(), imgs, E)
+      self.ops.ingest_img(x[:, self.S:].clone(memory_format=torch.contiguous_format), imgs, E)
       st = torch.empty((E, plan.Sp), device=self.device, dtype=torch.float16)
       self.ops.gather_rows_f16(x, True, None, st, E, self.S, x.shape[1], plan.Sp)
       plan.pack(self.vf_flat)
@@ -391,7 +391,7 @@ class PPOUpdateEngine:
     ppf, pvf = self._aux_plan(n, "pf"), self._aux_plan(n, "vf")
     if self.precision == "f16":
       imgs = imgs_out if imgs_out is not None else torch.empty((n, 16, 16, 64), device=self.device, dtype=torch.float16)
-      self.ops.ingest_img(x[:, self.S:].contiguous(), imgs, n)
+      self.ops.ingest_img(x[:, self.S:].clone(memory_format=torch.contiguous_format), imgs, n)
       st = torch.zeros((n, ppf.Sp), device=self.device, dtype=torch.float16)
       if self.S:
         self.ops.gather_rows_f16(x, True, None, st, n, self.S, x.shape[1], ppf.Sp)

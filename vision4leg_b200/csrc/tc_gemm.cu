@@ -891,6 +891,8 @@ __global__ void relu_bwd_f16_kernel(const __half* __restrict__ dy, const v4l_row
 extern "C" int v4l_ingest_img(v4l_ctx* ctx, void* stream, const float* img, void* out_s2d, int64_t n_img,
                               const int32_t* idx) {
   V4L_REQUIRE(ctx && img && out_s2d && n_img >= 0, "v4l_ingest_img: bad argument");
+  V4L_REQUIRE(((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(out_s2d)) & 15) == 0,
+              "v4l_ingest_img: img / out_s2d must be 16-byte aligned (vector loads)");
   if (n_img == 0) return 0;
   const long long total = n_img * 1024;
   const int blocks = (int)min((long long)16 * ctx->sm_count, (total + 255) / 256);
@@ -902,6 +904,8 @@ extern "C" int v4l_ingest_img(v4l_ctx* ctx, void* stream, const float* img, void
 extern "C" int v4l_ingest_img_f16(v4l_ctx* ctx, void* stream, const void* img_f16, void* out_s2d, int64_t n_img,
                                   const int32_t* idx) {
   V4L_REQUIRE(ctx && img_f16 && out_s2d && n_img >= 0, "v4l_ingest_img_f16: bad argument");
+  V4L_REQUIRE(((reinterpret_cast<uintptr_t>(img_f16) | reinterpret_cast<uintptr_t>(out_s2d)) & 15) == 0,
+              "v4l_ingest_img_f16: img / out_s2d must be 16-byte aligned (vector loads)");
   if (n_img == 0) return 0;
   const long long total = n_img * 1024;
   const int blocks = (int)min((long long)16 * ctx->sm_count, (total + 255) / 256);
