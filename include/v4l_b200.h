@@ -317,6 +317,25 @@ int v4l_tc_wgrad_conv1(v4l_ctx* ctx, void* stream, const void* x_s2d, int64_t n_
                        const void* dy_cells, int B, const int32_t* index, float* dw, float* dbias,
                        float out_scale, int defer, int accumulate);
 
+/* ---- observation pipeline on the device (csrc/obs_ops.cu) -----------------------------------
+ * v4l_depth_frame: OpenGL depth-buffer values zbuf [E,64,64] -> far*near/(far-(far-near) z) -> clip [0.3,10] ->
+ * sqrt(log(d+1)) into slot `head` of the per-env frame ring [E, n_slots, 64, 64] fp32 — into EVERY slot of env e when
+ * reset[e] != 0 (reset may be NULL; an episode start fills the history, :635-637)
+ * (reference vision4leg/envs/locomotion_gym_env_with_rich_information.py:620-633).
+ * v4l_stack_frames: the observation's 4 channels = ring slots slots[e*4 + c] (the reference's deque indices
+ * frame_idx, :315-336,549-554,641-648), optionally (x-1.25)/0.425 (:649-650), written as the f16 4x4
+ * space-to-depth image [E,16,16,64] (v4l_ingest_img layout) and / or as fp32 CHW rows (row stride chw_stride).
+ * v4l_normalizer: running-mean observation normaliser over x [n,S]: if update, merge the batch mean / population
+ * variance into (mean, var, count) (torchrl/env/base_wrapper.py:44-61,84-86), then
+ * out = clip((x - mean) / (sqrt(var) + 1e-4), +-clip) (:88-90,119-122).  mean/var: double[S] on the device; count (1e-4 + rows merged so far) is tracked by the caller,
+ * who adds n after an updating call.  out may be NULL (update only) or alias x. */
+int v4l_depth_frame(v4l_ctx* ctx, void* stream, const float* zbuf, float* ring, const uint8_t* reset, int E,
+                    int n_slots, int head, float near_plane, float far_plane);
+int v4l_stack_frames(v4l_ctx* ctx, void* stream, const float* ring, const int32_t* slots, int E, int n_slots,
+                     int normalise, void* out_s2d, float* out_chw, int64_t chw_stride);
+int v4l_normalizer(v4l_ctx* ctx, void* stream, const float* x, int n, int S, double* mean, double* var,
+                   double count, int update, float clip, float* out);
+
 /* ---- a chain of up to three Linear layers in one launch (csrc/tc_mlp.cu): the actor / critic MLP heads
  * (reference torchrl/networks/nets.py:973-992,1036), the proprio MLP + projector (base.py:8-44,209-230) and
  * their data-gradient chains.  Per 128-row tile: h = act(x W1^T + b1) [* (mask1 > 0)] stays in shared memory

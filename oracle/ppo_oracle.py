@@ -408,6 +408,43 @@ class PPOOracle:
     return advs, rets, infos
 
 
+class A2COracle:
+  """Restates A2C.update (reference torchrl/algo/on_policy/a2c.py:42-107) for SEPARATE actor / critic networks
+  (with shared tensors the reference's step order raises inside torch, so only this case has a reference answer).
+  Pinned by tests/golden/a2c_mlp.npz (oracle/make_golden_a2c.py)."""
+
+  def __init__(self, family, pf_sd, vf_sd, S, plr=3e-4, vlr=3e-4, entropy_coeff=0.001):
+    self.fwd, self.S = FORWARD[family], S
+    self.pf, self.vf = pf_sd, vf_sd
+    self.pf_keys, self.vf_keys = list(pf_sd.keys()), list(vf_sd.keys())
+    self.pf_opt = Adam([pf_sd[k] for k in self.pf_keys], plr)
+    self.vf_opt = Adam([vf_sd[k] for k in self.vf_keys], vlr)
+    self.entropy_coeff = entropy_coeff
+
+  def update(self, batch):
+    obs, acts, advs, rets = (torch.as_tensor(batch[k], dtype=torch.float32)
+                             for k in ("obs", "acts", "advs", "estimate_returns"))
+    pparams = [self.pf[k] for k in self.pf_keys]
+    vparams = [self.vf[k] for k in self.vf_keys]
+    for p in pparams + vparams:
+      p.requires_grad_(True)
+    lp, ent, logstd = gaussian_update(self.fwd(self.pf, obs, self.S), self.pf["logstd"], acts)
+    advs = (advs - advs.mean()) / (advs.std() + 1e-5)
+    ploss = (-lp * advs).mean() - self.entropy_coeff * ent.mean()
+    values = self.fwd(self.vf, obs, self.S)
+    vloss = ((values - rets) ** 2).mean()
+    pgrads = list(torch.autograd.grad(ploss, pparams))
+    vgrads = list(torch.autograd.grad(vloss, vparams))
+    for p in pparams + vparams:
+      p.requires_grad_(False)
+    clip_grad_norm(pgrads, 0.5)
+    self.pf_opt.step(pgrads)
+    clip_grad_norm(vgrads, 0.5)
+    self.vf_opt.step(vgrads)
+    return {"Training/policy_loss": ploss.item(), "Training/vf_loss": vloss.item(), "ent": ent.mean().item(),
+            "log_prob": lp.mean().item(), "v_pred/mean": values.mean().item(), "v_pred/std": values.std().item()}
+
+
 def sd_to_torch(pf_np, vf_np, shared_prefixes=("encoder.", "base."), dtype=torch.float32):
   """numpy state dicts -> torch, keeping shared tensors shared (one tensor object)."""
   pf = {k: torch.tensor(v, dtype=dtype) for k, v in pf_np.items()}

@@ -94,3 +94,20 @@ def test_update_per_epoch_matches_reference(family):
   g.check_summary(G, "epoch/target", [(k, v.numpy()) for k, v in orc.target_pf.items()], 5e-4)
   lr = 1e-4 * (1 - 30 / 1500.0)
   np.testing.assert_allclose(G["epoch/lr"], [lr, lr], rtol=1e-12)
+
+
+def test_a2c_update_matches_reference():
+  """oracle A2C restatement vs the live reference's two A2C.update calls (oracle/make_golden_a2c.py)"""
+  from oracle import make_golden_a2c as mk
+  from oracle import synth
+  G = g.load("a2c_mlp")
+  pf_np, vf_np = synth.make_family_weights(1000, "mlp", mk.S, mk.A)
+  pf, vf = po.sd_to_torch(pf_np, vf_np, shared_prefixes=())
+  orc = po.A2COracle("mlp", pf, vf, mk.S)
+  for i, b in enumerate(mk.batches()):
+    info = orc.update(b)
+    for k, v in info.items():
+      want = float(G["info%d/%s" % (i, k)])
+      assert abs(v - want) <= 1e-6 + 2e-5 * abs(want), (i, k, v, want)
+  g.check_summary(G, "pf", [(k, v.numpy()) for k, v in pf.items()], 2e-5, "a2c oracle")
+  g.check_summary(G, "vf", [(k, v.numpy()) for k, v in vf.items()], 2e-5, "a2c oracle")

@@ -161,6 +161,9 @@ SIGNATURES = {
   "v4l_tc_wgrad_flush": [_vp, _vp],
   "v4l_tc_wgrad_conv1": [_vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _f, _i, _i],
   "v4l_tc_mlp_chain": [_vp, _vp, C.POINTER(TcMlpChainArgs)],
+  "v4l_depth_frame": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f],
+  "v4l_stack_frames": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i64],
+  "v4l_normalizer": [_vp, _vp, _vp, _i, _i, _vp, _vp, C.c_double, _i, _f, _vp],
   "v4l_opt_tail": [_vp, _vp, C.POINTER(OptTailArgs)],
   "v4l_opt_tail_error": [_vp],
   "v4l_mb_begin": [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i],

@@ -52,8 +52,7 @@ def build(force=False, verbose=False):
   if failed:
     raise RuntimeError("nvcc failed")
   tmp = LIB + ".tmp.%d" % os.getpid()
-  subprocess.check_call([nvcc, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                        "-lcuda"])
+  subprocess.check_call([nvcc, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
   os.replace(tmp, LIB)
   return LIB
 

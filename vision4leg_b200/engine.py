@@ -433,6 +433,21 @@ class Ops:
     check(self.lib.v4l_adv_stats_epoch(self.h, self.ctx.stream(), ptr(flat_idx), n_mb, n, ptr(adv), ptr(stats)))
     self.launches += 1
 
+  def depth_frame(self, zbuf, ring, reset, E, n_slots, head, near=0.01, far=1000.0):
+    check(self.lib.v4l_depth_frame(self.h, self.ctx.stream(), ptr(zbuf), ptr(ring), ptr(reset), E, n_slots, head,
+                                   near, far))
+    self.launches += 1
+
+  def stack_frames(self, ring, slots, E, n_slots, normalise, out_s2d=None, out_chw=None, chw_stride=0):
+    check(self.lib.v4l_stack_frames(self.h, self.ctx.stream(), ptr(ring), ptr(slots), E, n_slots, int(normalise),
+                                    ptr(out_s2d), ptr(out_chw), chw_stride))
+    self.launches += 1
+
+  def normalizer(self, x, n, S, mean, var, count, update, clip, out=None):
+    check(self.lib.v4l_normalizer(self.h, self.ctx.stream(), ptr(x), n, S, ptr(mean), ptr(var), float(count),
+                                  int(update), float(clip), ptr(out)))
+    self.launches += 1
+
   def mb_begin(self, flat_idx, slot, cur_idx, n, adv, stats, state=None, S=0, state_f16=None, Sp=0):
     """minibatch prologue: row selection + advantage statistics (+ proprio rows -> fp16), one launch"""
     check(self.lib.v4l_mb_begin(self.h, self.ctx.stream(), ptr(flat_idx), ptr(slot), ptr(cur_idx), n, ptr(adv),

@@ -1,0 +1,132 @@
+"""Observation pipeline on the device: what the reference does to an observation between the
+simulator and the policy, for E environments at once, without a host round trip.
+
+  DepthFrameStack  depth-buffer frames -> sqrt(log(clip(depth)+1)) -> per-env history -> the 4-frame observation
+                   (reference vision4leg/envs/locomotion_gym_env_with_rich_information.py:312-336,549-554,620-650)
+  Normalizer       the running-mean observation normaliser of NormObs over a vectorised env
+                   (reference torchrl/env/base_wrapper.py:44-122), same attribute / method names
+
+Both call the C-ABI kernels of csrc/obs_ops.cu; there is no CPU path.
+"""
+import numpy as np
+import torch
+
+from .engine import Ops
+
+
+def fixed_frame_idx(frame_extract):
+  """reference :317-323 (fixed_delay_observation)"""
+  return [frame_extract - 1, 2 * frame_extract - 1, 3 * frame_extract - 1, 4 * frame_extract - 1]
+
+
+class DepthFrameStack:
+  """The reference keeps a deque of processed frames per env (newest at index 0) and builds the observation from
+  depth_frames[frame_idx[k]], k = 0..3.  Here the history is a ring [E, n_slots, 64, 64] fp32 in HBM: deque index
+  i is ring slot (head - i) mod n_slots, so a push is one slot write and the observation is a 4-slot gather."""
+
+  def __init__(self, n_envs, num_stored_frames, frame_idx, depth_norm=True, device=None, ops=None):
+    self.device = torch.device(device if device is not None else "cuda")
+    self.ops = ops if ops is not None else Ops(self.device)
+    self.E, self.n = int(n_envs), int(num_stored_frames)
+    self.depth_norm = bool(depth_norm)
+    self.ring = torch.zeros(self.E, self.n, 64, 64, device=self.device)
+    self.head = 0
+    self.slots = torch.zeros(self.E, 4, dtype=torch.int32, device=self.device)
+    self._reset = torch.zeros(self.E, dtype=torch.uint8, device=self.device)
+    self.set_frame_idx(frame_idx)
+    self.s2d = torch.empty(self.E, 16, 16, 64, dtype=torch.float16, device=self.device)
+
+  def set_frame_idx(self, frame_idx):
+    """frame_idx: 4 deque indices, shared ([4]) or per env ([E, 4]) (reference :315-336, re-drawn per step at
+    :549-554 when reset_frame_idx_each_step)"""
+    fi = np.asarray(frame_idx, np.int64)
+    fi = np.broadcast_to(fi, (self.E, 4)) if fi.ndim == 1 else fi
+    if fi.shape != (self.E, 4) or fi.min() < 0 or fi.max() >= self.n:
+      raise ValueError("frame_idx must hold 4 indices in [0, num_stored_frames) per env")
+    self.frame_idx = torch.as_tensor(np.ascontiguousarray(fi), dtype=torch.int32).to(self.device)
+
+  def push(self, zbuf, reset=None):
+    """zbuf: [E, 64, 64] fp32 depth-buffer values on the device; reset: optional [E] bool (episode starts: the new
+    frame fills that env's whole history, reference :635-637)"""
+    if zbuf.shape != (self.E, 64, 64) or zbuf.dtype != torch.float32 or not zbuf.is_cuda:
+      raise ValueError("zbuf must be a CUDA float32 tensor [E, 64, 64]")
+    zbuf = zbuf.contiguous()
+    self.head = (self.head + 1) % self.n
+    rs = None
+    if reset is not None:
+      self._reset.copy_(torch.as_tensor(reset).to(self.device, torch.uint8))
+      rs = self._reset
+    self.ops.depth_frame(zbuf, self.ring, rs, self.E, self.n, self.head)
+
+  def observe(self, out_chw=None, out_s2d=True):
+    """the stacked observation: fp16 space-to-depth image [E,16,16,64] (what the tensor-core tier's conv1 reads)
+    and / or fp32 CHW pixels written into out_chw [E, >=16384] (a view of the observation rows' image part)"""
+    torch.remainder(self.head - self.frame_idx, self.n, out=self.slots)
+    stride = 0
+    if out_chw is not None:
+      if out_chw.dtype != torch.float32 or out_chw.shape[0] != self.E or out_chw.stride(-1) != 1:
+        raise ValueError("out_chw must be float32 [E, 16384] with unit inner stride")
+      stride = out_chw.stride(0)
+    self.ops.stack_frames(self.ring, self.slots, self.E, self.n, self.depth_norm,
+                          self.s2d if out_s2d else None, out_chw, stride)
+    return self.s2d if out_s2d else out_chw
+
+
+class Normalizer:
+  """reference torchrl/env/base_wrapper.py:64-105 for a vectorised env (observations [n, S]); mean and variance live
+  on the device in float64, the count on the host (it is 1e-4 + the rows merged so far)."""
+
+  def __init__(self, shape, clip=10., device=None, ops=None):
+    self.device = torch.device(device if device is not None else "cuda")
+    self.ops = ops if ops is not None else Ops(self.device)
+    self.shape = shape
+    self.S = int(np.prod(shape))
+    self._mean_d = torch.zeros(self.S, dtype=torch.float64, device=self.device)
+    self._var_d = torch.ones(self.S, dtype=torch.float64, device=self.device)
+    self._count = 1e-4
+    self.clip = clip
+    self.should_estimate = True
+
+  @property
+  def _mean(self):
+    return self._mean_d.cpu().numpy().reshape(self.shape)
+
+  @property
+  def _var(self):
+    return self._var_d.cpu().numpy().reshape(self.shape)
+
+  def stop_update_estimate(self):
+    self.should_estimate = False
+
+  def _rows(self, data):
+    if data.dtype != torch.float32 or not data.is_cuda or data.shape[-1] != self.S or data.dim() != 2:
+      raise ValueError("observations must be a CUDA float32 tensor [n, %d]" % self.S)
+    return data.contiguous()
+
+  def update_estimate(self, data):
+    if not self.should_estimate:
+      return
+    x = self._rows(data)
+    self.ops.normalizer(x, x.shape[0], self.S, self._mean_d, self._var_d, self._count, True, self.clip, None)
+    self._count += x.shape[0]
+
+  def filt(self, raw, out=None):
+    x = self._rows(raw)
+    out = torch.empty_like(x) if out is None else out
+    self.ops.normalizer(x, x.shape[0], self.S, self._mean_d, self._var_d, self._count, False, self.clip, out)
+    return out
+
+  filt_torch = filt
+
+  def observation(self, observation, training=True, out=None):
+    """NormObs.observation (reference :119-122): update (when training) then filter, one launch"""
+    x = self._rows(observation)
+    out = torch.empty_like(x) if out is None else out
+    upd = bool(training and self.should_estimate)
+    self.ops.normalizer(x, x.shape[0], self.S, self._mean_d, self._var_d, self._count, upd, self.clip, out)
+    if upd:
+      self._count += x.shape[0]
+    return out
+
+  def inverse_torch(self, raw):
+    return raw * torch.sqrt(self._var_d).to(raw.dtype) + self._mean_d.to(raw.dtype)
