@@ -33,10 +33,16 @@ typedef struct v4l_ctx v4l_ctx;
 /* ---- library / context ------------------------------------------------------------------- */
 int         v4l_version(void);
 const char* v4l_last_error(void);
-/* scratch_bytes: size of the context-owned scratch buffer (0 = default 256 MiB). */
+/* scratch_bytes: size of the context-owned scratch buffer (0 = default 1 GiB: half for immediate users, half for deferred
+ * weight-gradient partials). */
 int         v4l_ctx_create(v4l_ctx** out, int device, size_t scratch_bytes);
 int         v4l_ctx_destroy(v4l_ctx* ctx);
 int         v4l_ctx_sm_count(const v4l_ctx* ctx);
+/* How many times a deferred weight-gradient job found the scratch too full for its split count and reduced the
+ * pending jobs early, ON ITS OWN STREAM.  That is only ordered after the other pending jobs when they were all
+ * launched on that stream: a caller that spreads weight-gradient launches over several streams must size the
+ * scratch so that this stays constant (the default, 1 GiB, does for every shipped network at any minibatch). */
+int         v4l_ctx_early_flushes(const v4l_ctx* ctx);
 
 /* ---- addressing ---------------------------------------------------------------------------
  * A "row map" addresses logical row m of a matrix that lives inside a larger activation

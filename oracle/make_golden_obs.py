@@ -23,7 +23,10 @@ def inputs():
   rng = np.random.RandomState(SEED)
   scale = rng.uniform(0.1, 30.0, size=S)
   shift = rng.uniform(-5.0, 5.0, size=S)
-  return [(rng.randn(N, S) * scale + shift).astype(np.float32) for _ in range(STEPS)]
+  # float64 arrays, as the reference's environments produce them (env_utils.flatten_observations concatenates
+  # float64 sensor readings with the float32 image), holding float32-representable values so that the device
+  # path's float32 rows carry the same numbers
+  return [(rng.randn(N, S) * scale + shift).astype(np.float32).astype(np.float64) for _ in range(STEPS)]
 
 
 def main():

@@ -76,11 +76,12 @@ class Normalizer:
     self.clip = clip
 
   def update(self, x):
-    x = np.asarray(x)
+    x = np.asarray(x, np.float64)      # the environments hand float64 rows to NormObs (flatten_observations)
     if x.ndim == 1:
       x = x[None]
     self.mean, self.var, self.count = merge_mean_var_count(
       self.mean, self.var, self.count, np.mean(x, axis=0), np.var(x, axis=0), x.shape[0])
 
   def filt(self, x):
+    x = np.asarray(x, np.float64)
     return np.clip((x - self.mean) / (np.sqrt(self.var) + 1e-4), -self.clip, self.clip)

@@ -65,7 +65,7 @@ def test_normalizer_matches_reference_fixture():
   for i, x in enumerate(mk.inputs()):
     if i == mk.STEPS - 1:
       nz.stop_update_estimate()
-    xt = torch.from_numpy(x).to(dev)
+    xt = torch.from_numpy(x.astype(np.float32)).to(dev)          # lossless: the fixture's inputs are fp32 values
     if i % 2:                                             # both call shapes of the reference: update + filt, observation()
       nz.update_estimate(xt)
       out = nz.filt(xt)
@@ -95,4 +95,7 @@ def test_normalizer_whole_observation_rows():
     want = ref.filt(x)
     assert np.allclose(out.cpu().numpy(), want, rtol=1e-6, atol=1e-6)
   assert np.allclose(nz._var, ref.var, rtol=1e-11, atol=1e-300)
-  assert out.abs().max().item() == 10.0
+  x[1, 20], x[2, 21] = 1e9, -1e9                          # the evaluation path: filter only, clipping active
+  out = nz.filt(torch.from_numpy(x).to(dev))
+  assert np.allclose(out.cpu().numpy(), ref.filt(x), rtol=1e-6, atol=1e-6)
+  assert out[1, 20].item() == 10.0 and out[2, 21].item() == -10.0

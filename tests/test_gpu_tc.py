@@ -163,6 +163,29 @@ def test_tc_wgrad_bias_and_deferred_reduce():
     assert rel(db, 0.5 * dy.float().sum(0)) < 1e-4
 
 
+def test_tc_wgrad_deferred_scratch_overflow_flushes_early():
+  """a deferred job that does not fit what is left of the scratch with its full split count reduces the pending
+  jobs first (same stream) instead of running on the few splits that fit; both results stay right and the
+  context counts the event (v4l_ctx_early_flushes) so that multi-stream callers can refuse it"""
+  from vision4leg_b200 import _lib, engine
+  ctx = _lib.Context(DEV, scratch_bytes=16 << 20)          # 8 MB of deferred partials: one of the jobs below is 6.3 MB
+  ops = engine.Ops(DEV, ctx=ctx)
+  torch.manual_seed(8)
+  assert ops.lib.v4l_ctx_early_flushes(ops.h) == 0
+  jobs = []
+  for M, N, K in [(16384, 256, 256), (16384, 256, 256), (512, 64, 128)]:
+    x = bf(torch.randn(M, K, device=DEV)); dy = bf(torch.randn(M, N, device=DEV))
+    dw = torch.full((N, K), float("nan"), device=DEV); db = torch.full((N,), float("nan"), device=DEV)
+    ops.tc_wgrad(x, (M, 1, 1, K), dy, N, (M, 1, 1), (1, 1, 128), [(0, 0)], N, None, dw, dbias=db, defer=True)
+    jobs.append((x, dy, dw, db))
+  assert ops.lib.v4l_ctx_early_flushes(ops.h) == 1
+  ops.tc_wgrad_flush()
+  torch.cuda.synchronize()
+  for x, dy, dw, db in jobs:
+    assert rel(dw, dy.float().t() @ x.float()) < 1e-4
+    assert rel(db, dy.float().sum(0)) < 1e-4
+
+
 def test_tc_wgrad_conv3_and_conv1():
   engine, ops = _ops()
   torch.manual_seed(11)

@@ -124,6 +124,7 @@ SIGNATURES = {
   "v4l_ctx_create": [C.POINTER(_vp), _i, _sz],
   "v4l_ctx_destroy": [_vp],
   "v4l_ctx_sm_count": [_vp],
+  "v4l_ctx_early_flushes": [_vp],
   "v4l_gemm_rows": [_vp, _vp, C.POINTER(GemmArgs)],
   "v4l_gemm_wgrad": [_vp, _vp, C.POINTER(WgradArgs)],
   "v4l_relu_bwd": [_vp, _vp, _vp, C.POINTER(RowMap), _vp, C.POINTER(RowMap), _vp, C.POINTER(RowMap),

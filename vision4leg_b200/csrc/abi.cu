@@ -47,13 +47,16 @@ extern "C" int v4l_ctx_create(v4l_ctx** out, int device, size_t scratch_bytes) {
   v4l_ctx* c = new v4l_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
-  if (scratch_bytes == 0) scratch_bytes = (size_t)256 << 20;
+  // default 1 GiB: the upper half holds the split-K partials of every weight gradient of one backward pass until the
+  // optimiser tail reduces them — at most ~21 jobs x 148 CTAs x 128 x 256 floats = 410 MB however large the minibatch
+  if (scratch_bytes == 0) scratch_bytes = (size_t)1 << 30;
   const size_t total_elems = scratch_bytes / sizeof(float);
   c->scratch_elems = total_elems / 2;
   c->defer_elems = total_elems - c->scratch_elems;
   c->defer_cursor = 0;
   c->n_jobs = 0;
   c->early_flush = 0;
+  c->early_flush_count = 0;
   cudaError_t e = cudaMalloc(&c->scratch, scratch_bytes);
   if (e != cudaSuccess) {
     v4l_set_error("v4l_ctx_create: cudaMalloc(%zu) -> %s", scratch_bytes, cudaGetErrorString(e));
@@ -83,6 +86,7 @@ extern "C" int v4l_ctx_destroy(v4l_ctx* ctx) {
 }
 
 extern "C" int v4l_ctx_sm_count(const v4l_ctx* ctx) { return ctx ? ctx->sm_count : -1; }
+extern "C" int v4l_ctx_early_flushes(const v4l_ctx* ctx) { return ctx ? ctx->early_flush_count : -1; }
 
 extern "C" int v4l_h2d_2d(void* stream, void* dst, size_t dpitch, const void* h_src, size_t spitch,
                           size_t width, size_t height) {

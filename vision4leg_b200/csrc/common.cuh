@@ -28,6 +28,7 @@ struct v4l_ctx {
   size_t defer_elems, defer_cursor;
   v4l_reduce_job jobs[V4L_MAX_JOBS];
   int n_jobs;
+  int early_flush_count;    // how many times that happened since the context was created (v4l_ctx_early_flushes)
   int early_flush;          // a deferred reduction was flushed before the optimiser tail (scratch full): the
                             // tail then takes the gradient norm from the bucket instead of from its own writes
   unsigned int* counters;   // V4L_N_COUNTERS zero-initialised device words: last-CTA arrival counters and

@@ -15,33 +15,42 @@
 
 namespace {
 
-// one thread per pixel of one env's new frame
+__device__ __forceinline__ float depth_feature(float z, float farp, float far_near, float far_minus_near) {
+  // numpy evaluates this as separately rounded fp32 operations and the expression cancels badly near z = 1 (the far
+  // field): no fused multiply-add here, or the result differs from the reference's by 1e-5
+  float d = __fdiv_rn(far_near, __fsub_rn(farp, __fmul_rn(far_minus_near, z)));
+  d = fminf(fmaxf(d, 0.3f), 10.f);
+  return sqrtf(logf(d + 1.f));
+}
+
+// one thread per 4 pixels of one env's new frame (16-byte loads and stores)
 __global__ void depth_frame_kernel(const float* __restrict__ z, float* __restrict__ ring, const uint8_t* __restrict__ reset,
-                                   int E, int n_slots, int head, float nearp, float farp) {
+                                   int E, int n_slots, int head, float farp, float far_near, float far_minus_near) {
   v4l_pdl_enter();
-  const long long total = (long long)E * 4096;
+  const long long total = (long long)E * 1024;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int e = (int)(i >> 12), px = (int)(i & 4095);
-    float d = farp * nearp / (farp - (farp - nearp) * z[i]);
-    d = fminf(fmaxf(d, 0.3f), 10.f);
-    const float f = sqrtf(logf(d + 1.f));
-    float* mine = ring + (long long)e * n_slots * 4096 + px;
+    const int e = (int)(i >> 10), q = (int)(i & 1023);
+    const float4 zz = __ldcs(reinterpret_cast<const float4*>(z) + i);
+    const float4 f = make_float4(depth_feature(zz.x, farp, far_near, far_minus_near), depth_feature(zz.y, farp, far_near, far_minus_near),
+                                 depth_feature(zz.z, farp, far_near, far_minus_near), depth_feature(zz.w, farp, far_near, far_minus_near));
+    float4* mine = reinterpret_cast<float4*>(ring + (long long)e * n_slots * 4096) + q;
     if (reset && reset[e]) {                         // an episode start fills the whole history (reference :635-637)
-      for (int s = 0; s < n_slots; ++s) mine[(long long)s * 4096] = f;
+      for (int s = 0; s < n_slots; ++s) mine[(long long)s * 1024] = f;
     } else {
-      mine[(long long)head * 4096] = f;
+      mine[(long long)head * 1024] = f;
     }
   }
 }
 
-// thread per (env, Y, X, py): 4 px x 4 channels = 16 fp16 = two 16-byte stores of the s2d image
+// thread per (env, Y, X, py), py fastest: 4 px x 4 channels = 16 fp16 = 32 bytes of the s2d image, so four
+// neighbouring threads fill one 128-byte line of it
 __global__ void stack_frames_kernel(const float* __restrict__ ring, const int32_t* __restrict__ slots, int E, int n_slots,
                                     int normalise, __half* __restrict__ s2d, float* __restrict__ chw, long long chw_stride,
                                     int chw_vec) {
   v4l_pdl_enter();
   const long long total = (long long)E * 16 * 16 * 4;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int X = (int)(t & 15), py = (int)((t >> 4) & 3), Y = (int)((t >> 6) & 15), e = (int)(t >> 10);
+    const int py = (int)(t & 3), X = (int)((t >> 2) & 15), Y = (int)((t >> 6) & 15), e = (int)(t >> 10);
     const int row = 4 * Y + py, col = 4 * X;
     float v[4][4];                                   // [channel][px]
 #pragma unroll
@@ -112,9 +121,11 @@ __global__ void __launch_bounds__(256) normalizer_kernel(const float* __restrict
 extern "C" int v4l_depth_frame(v4l_ctx* ctx, void* stream, const float* zbuf, float* ring, const uint8_t* reset, int E,
                                int n_slots, int head, float near_plane, float far_plane) {
   V4L_REQUIRE(ctx && zbuf && ring && E > 0 && n_slots > 0 && head >= 0 && head < n_slots, "v4l_depth_frame: bad argument");
-  const long long total = (long long)E * 4096;
+  V4L_REQUIRE((((uintptr_t)zbuf | (uintptr_t)ring) & 15) == 0, "v4l_depth_frame: zbuf and ring must be 16-byte aligned");
+  const long long total = (long long)E * 1024;
   V4L_LAUNCH(depth_frame_kernel, (int)min((long long)8 * ctx->sm_count, (total + 255) / 256), 256, 0, (cudaStream_t)stream,
-             zbuf, ring, reset, E, n_slots, head, near_plane, far_plane);
+             zbuf, ring, reset, E, n_slots, head, far_plane, (float)((double)far_plane * (double)near_plane),
+             (float)((double)far_plane - (double)near_plane));   // Python-float scalars, rounded once (NumPy weak scalars)
   V4L_CHECK_LAUNCH();
   return 0;
 }
@@ -122,6 +133,7 @@ extern "C" int v4l_depth_frame(v4l_ctx* ctx, void* stream, const float* zbuf, fl
 extern "C" int v4l_stack_frames(v4l_ctx* ctx, void* stream, const float* ring, const int32_t* slots, int E, int n_slots,
                                 int normalise, void* out_s2d, float* out_chw, int64_t chw_stride) {
   V4L_REQUIRE(ctx && ring && slots && E > 0 && n_slots > 0 && (out_s2d || out_chw), "v4l_stack_frames: bad argument");
+  V4L_REQUIRE((((uintptr_t)ring | (uintptr_t)out_s2d) & 15) == 0, "v4l_stack_frames: ring and out_s2d must be 16-byte aligned");
   V4L_REQUIRE(!out_chw || chw_stride >= 16384, "v4l_stack_frames: the fp32 CHW row stride must be at least 16384");
   const int chw_vec = out_chw && chw_stride % 4 == 0 && ((uintptr_t)out_chw & 15) == 0;
   const long long total = (long long)E * 1024;

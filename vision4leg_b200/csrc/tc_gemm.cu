@@ -434,7 +434,7 @@ struct TcWgradParams {
   CUtensorMap tmap_dy;
   int B, Hout, Wout;
   int bw, bh, bb;
-  int h_tiles, num_tiles, tiles_per_split;
+  int h_tiles, num_tiles;
   int n_taps, x_C;
   int tap_dw[MAX_TAPS], tap_dh[MAX_TAPS];
   int n_atoms;                 // dY atoms of 64 channels (UMMA N = 64 * n_atoms)
@@ -460,8 +460,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
   const int box_rows = p.bw * p.bh * p.bb;
   const int ksteps = (box_rows + 15) / 16;
   const uint32_t stage_bytes = (2 + p.n_atoms) * ATOM_BYTES;
-  const int tile_lo = split * p.tiles_per_split;
-  const int tile_hi = min(p.num_tiles, tile_lo + p.tiles_per_split);
+  // row tiles are dealt round-robin over the splits: the CTAs of a launch stream through one contiguous window of
+  // tiles at a time (contiguous ranges per split are 2^k-strided concurrent streams at power-of-two minibatches)
+  const int tile_lo = split, tile_step = gridDim.x, tile_hi = p.num_tiles;
+  const int my_tiles = tile_lo < tile_hi ? (tile_hi - tile_lo + tile_step - 1) / tile_step : 0;
 
   // Rows of a stage beyond the TMA box (box rows not a multiple of the 16-row K step) must read as zero for
   // the whole kernel: zero just those rows of every atom, once.  The bias slice (an extra K slice whose "X" is
@@ -512,7 +514,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
         a_tap[j] = tap; a_c0[j] = c0;
       }
       int stage = 0; uint32_t phase = 0;
-      for (int tile = tile_lo; tile < tile_hi; ++tile) {
+      for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
         int b0, h0;
         if (p.bb == 1) { b0 = tile / p.h_tiles; h0 = (tile - b0 * p.h_tiles) * p.bh; }
         else           { b0 = tile * p.bb; h0 = 0; }
@@ -541,7 +543,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
       const uint32_t idesc = tc::umma_idesc_f16(128, Nmma, 1, 1);     // both operands MN-major
       int stage = 0; uint32_t phase = 0;
       uint32_t first = 1;
-      for (int it = (tile_hi - tile_lo) * p.n_sub; it > 0; --it) {
+      for (int it = my_tiles * p.n_sub; it > 0; --it) {
         tc::mbar_wait(&full_bar[stage], phase);
         tc::tc_fence_after();
         const uint32_t sa = tc::smem_u32(smem + stage * stage_bytes);
@@ -705,20 +707,22 @@ extern "C" int v4l_tc_wgrad(v4l_ctx* ctx, void* stream, const v4l_tc_wgrad_args*
   const int ytiles = kin_tiles + has_bias;
   p.kin_tiles = kin_tiles;
   // deferred reductions keep their partials in the upper half of the scratch until the flush
-  if (a->defer && (ctx->n_jobs == V4L_MAX_JOBS ||
-                   ctx->defer_elems - ctx->defer_cursor < (size_t)ytiles * 128 * Nmma)) {
-    if (int r = v4l_tc_wgrad_flush(ctx, stream)) return r;
-    ctx->early_flush = 1;
-  }
-  float* region = a->defer ? ctx->defer_base + ctx->defer_cursor : ctx->scratch;
-  const size_t avail = a->defer ? ctx->defer_elems - ctx->defer_cursor : ctx->scratch_elems;
   // split-K over the row tiles: >= 8 row tiles per CTA (the partial sums cost 128 x Nmma floats of
   // traffic per CTA, twice), at most one wave; several of these launches run side by side
   int splits = max(1, min(p.num_tiles / 8, min(48, ctx->sm_count / ytiles)));
+  // a deferred job that cannot get its split count from what is left of the scratch flushes the pending jobs first
+  // (running on the few splits that still fit would serialise the launch on a handful of SMs)
+  if (a->defer && ctx->n_jobs > 0 && (ctx->n_jobs == V4L_MAX_JOBS ||
+                   ctx->defer_elems - ctx->defer_cursor < (size_t)splits * ytiles * 128 * Nmma)) {
+    if (int r = v4l_tc_wgrad_flush(ctx, stream)) return r;
+    ctx->early_flush = 1;
+    ++ctx->early_flush_count;
+  }
+  float* region = a->defer ? ctx->defer_base + ctx->defer_cursor : ctx->scratch;
+  const size_t avail = a->defer ? ctx->defer_elems - ctx->defer_cursor : ctx->scratch_elems;
   splits = (int)min((size_t)splits, avail / ((size_t)ytiles * 128 * Nmma));
   V4L_REQUIRE(splits >= 1, "v4l_tc_wgrad: scratch too small (flush deferred reductions more often)");
-  p.tiles_per_split = v4l_cdiv(p.num_tiles, splits);
-  splits = v4l_cdiv(p.num_tiles, p.tiles_per_split);
+  splits = v4l_cdiv(p.num_tiles, v4l_cdiv(p.num_tiles, splits));     // no split without a tile
   p.partial = region;
 
   static bool attr_set = false;

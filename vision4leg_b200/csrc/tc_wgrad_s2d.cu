@@ -37,7 +37,6 @@ struct Conv1WgradParams {
   CUtensorMap tmap_dy;           // {128, 8, 8, B}, box {64, 8, 8, 1}
   const int32_t* x_idx;          // minibatch row list or NULL
   int B;
-  int imgs_per_cta;
   float* partial;                // [gridDim.x][3][32][128]
 };
 
@@ -49,8 +48,12 @@ __global__ void __launch_bounds__(W1_THREADS, 1) tc_wgrad_conv1_kernel(const __g
 
   v4l_pdl_trigger();
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
-  const int img_lo = blockIdx.x * p.imgs_per_cta;
-  const int img_hi = min(p.B, img_lo + p.imgs_per_cta);
+  // Images are dealt round-robin: at any moment the CTAs of the grid stream through ONE contiguous window of
+  // gridDim.x images.  With a contiguous range per CTA the concurrent streams are 2^k-strided at power-of-two
+  // minibatches and collide in the memory system (measured: 101 ns / sample at minibatch 32768 against 17 at 16384,
+  // profiles/r2_trace_sizes.txt).
+  const int img_lo = blockIdx.x, img_step = gridDim.x;
+  const int img_hi = p.B;
   uint8_t* ones = smem + N_STAGES * STAGE_BYTES;
   {
     const uint32_t one2 = 0x3C003C00u;     // two fp16 1.0
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(W1_THREADS, 1) tc_wgrad_conv1_kernel(const __g
   // instead of ~48: tools/ubench/mma_rate.cu, profiles/r2_mma_issue_rate.txt).
   if (warp == 0) {
     int stage = 0; uint32_t phase = 0;
-    for (int img = img_lo; img < img_hi; ++img) {
+    for (int img = img_lo; img < img_hi; img += img_step) {
       int xi = img;
       if (p.x_idx) xi = __shfl_sync(0xffffffffu, p.x_idx[img], 0);
       tc::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(W1_THREADS, 1) tc_wgrad_conv1_kernel(const __g
     const uint64_t ones_desc = tc::umma_smem_desc(ones_a, 0, 1024);
     int stage = 0; uint32_t phase = 0;
     uint32_t acc = 0;
-    for (int img = img_lo; img < img_hi; ++img) {
+    for (int img = img_lo; img < img_hi; img += img_step) {
       tc::mbar_wait(&full_bar[stage], phase);
       tc::tc_fence_after();
       const uint32_t sx = tc::smem_u32(smem + stage * STAGE_BYTES);
@@ -209,16 +212,19 @@ extern "C" int v4l_tc_wgrad_conv1(v4l_ctx* ctx, void* stream, const void* x_s2d,
   p.x_idx = x_idx;
   p.B = B;
   const size_t per_split = (size_t)3 * 32 * 128;
-  if (defer && (ctx->n_jobs == V4L_MAX_JOBS || ctx->defer_elems - ctx->defer_cursor < per_split)) {
+  // a deferred job that cannot get its full split count from what is left of the scratch flushes the pending jobs
+  // first: running with the few splits that still fit serialises the whole minibatch on a handful of SMs (minibatch
+  // 32768 ran this kernel at 1/6 of its speed that way, profiles/r2_trace_sizes.txt)
+  const size_t want = (size_t)min(ctx->sm_count, B) * per_split;
+  if (defer && ctx->n_jobs > 0 && (ctx->n_jobs == V4L_MAX_JOBS || ctx->defer_elems - ctx->defer_cursor < want)) {
     if (int r = v4l_tc_wgrad_flush(ctx, stream)) return r;
     ctx->early_flush = 1;
+    ++ctx->early_flush_count;
   }
   float* region = defer ? ctx->defer_base + ctx->defer_cursor : ctx->scratch;
   const size_t avail = defer ? ctx->defer_elems - ctx->defer_cursor : ctx->scratch_elems;
   int splits = (int)min((size_t)min(ctx->sm_count, B), avail / per_split);
   V4L_REQUIRE(splits >= 1, "v4l_tc_wgrad_conv1: scratch too small");
-  p.imgs_per_cta = v4l_cdiv(B, splits);
-  splits = v4l_cdiv(B, p.imgs_per_cta);
   p.partial = region;
   static bool attr_set = false;
   const size_t smem = (size_t)N_STAGES * STAGE_BYTES + ONES_BYTES + 1024;

@@ -71,8 +71,8 @@ class Input:
 class Ops:
   """Typed wrappers over the C ABI for one device."""
 
-  def __init__(self, device):
-    self.ctx = _lib.ctx(device)
+  def __init__(self, device, ctx=None):
+    self.ctx = ctx if ctx is not None else _lib.ctx(device)     # ctx: a private _lib.Context (own scratch size)
     self.lib = self.ctx.lib
     self.h = self.ctx.handle
     self.device = self.ctx.device

@@ -201,6 +201,8 @@ class _PlanTC:
     if which is None:
       which = "w%d" % (self._rr % N_WGRAD_STREAMS)
       self._rr += 1
+    if not self._forked:
+      self._flushes_at_fork = self.ops.lib.v4l_ctx_early_flushes(self.ops.h)
     self._forked.add(which)
     with self.ops.fork(which):
       fn()
@@ -208,6 +210,14 @@ class _PlanTC:
   def _join_all(self):
     for w in sorted(self._forked, key=str):
       self.ops.join(w)
+    # A deferred weight gradient that found the scratch full reduced the pending ones early on ITS stream, which is
+    # not ordered after the other side streams' launches: refuse to go on rather than race (the default scratch
+    # holds a whole backward pass of every shipped network at any minibatch, so this means a custom, smaller one).
+    overflowed = len(self._forked) > 1 and self.ops.lib.v4l_ctx_early_flushes(self.ops.h) != self._flushes_at_fork
+    if overflowed:
+      self._forked.clear()
+      raise V4LError("weight-gradient scratch overflowed while launches were spread over side streams: "
+                     "create the context with a larger scratch (v4l_ctx_create scratch_bytes)")
     self._forked.clear()
 
   def _lin_bwd(self, gflat, wname, x, x_cols, dy, dy_cols, M, dx=None, dx_map=None, mask=None, res=None,
