@@ -4,7 +4,8 @@
 
 torchrl/env/base_wrapper.py is loaded on its own (importlib, with a stub `gym` that provides the three wrapper base
 classes it subclasses); the file is not modified.  Inputs are regenerated from the seed by the tests; the fixture
-holds the reference's outputs only.  TEST INFRASTRUCTURE — not imported by the product.
+holds the reference's outputs only, plus `obs_normalizer_ref.pkl`: the reference object pickled the way
+RLAlgo.snapshot does (the `_obs_normalizer_{epoch}.pkl` wire format).  TEST INFRASTRUCTURE — not imported by the product.
 """
 import importlib.util
 import os
@@ -35,8 +36,11 @@ def main():
   for name in ("Wrapper", "RewardWrapper", "ObservationWrapper"):
     setattr(gym, name, type(name, (), {}))
   sys.modules["gym"] = gym
-  spec = importlib.util.spec_from_file_location("ref_base_wrapper", os.path.join(REF, "torchrl/env/base_wrapper.py"))
+  # under its real module path, so that the pickle written below names the class the way the reference's own
+  # snapshot does (rl_algo.py:84-90)
+  spec = importlib.util.spec_from_file_location("torchrl.env.base_wrapper", os.path.join(REF, "torchrl/env/base_wrapper.py"))
   mod = importlib.util.module_from_spec(spec)
+  sys.modules["torchrl.env.base_wrapper"] = mod
   spec.loader.exec_module(mod)
   nz = mod.Normalizer((S,))
   outs = []
@@ -47,6 +51,9 @@ def main():
     outs.append(nz.filt(x))
   np.savez_compressed(os.path.join(OUT, "obs_normalizer.npz"), filt=np.stack(outs), mean=nz._mean, var=nz._var,
                       count=np.float64(nz._count))
+  import pickle
+  with open(os.path.join(OUT, "obs_normalizer_ref.pkl"), "wb") as f:      # the checkpoint wire format
+    pickle.dump(nz, f)
   print("wrote obs_normalizer.npz", np.stack(outs).shape, nz._count)
 
 

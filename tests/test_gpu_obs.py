@@ -99,3 +99,26 @@ def test_normalizer_whole_observation_rows():
   out = nz.filt(torch.from_numpy(x).to(dev))
   assert np.allclose(out.cpu().numpy(), ref.filt(x), rtol=1e-6, atol=1e-6)
   assert out[1, 20].item() == 10.0 and out[2, 21].item() == -10.0
+
+
+def test_normalizer_checkpoint_roundtrip():
+  """pickle.dump(env._obs_normalizer) (RLAlgo.snapshot, reference rl_algo.py:84-90) writes the reference's wire
+  format — no name of this package in the stream — and the statistics come back onto a device bit-exactly"""
+  import io
+  import pickle
+  from vision4leg_b200 import obs_pipeline as op
+  dev = torch.device("cuda", 0)
+  S = 93
+  rng = np.random.RandomState(2)
+  nz = op.Normalizer((S,), device=dev)
+  for _ in range(3):
+    nz.update_estimate(torch.from_numpy((rng.randn(8, S) * 3 + 1).astype(np.float32)).to(dev))
+  raw = pickle.dumps(nz)
+  assert b"vision4leg_b200" not in raw
+  st = op.load_reference_normalizer(io.BytesIO(raw))
+  assert np.array_equal(st["_mean"], nz._mean) and np.array_equal(st["_var"], nz._var) and st["_count"] == nz._count
+  nz2 = op.Normalizer((S,), device=dev).load_reference(st)
+  x = torch.from_numpy(rng.randn(5, S).astype(np.float32)).to(dev)
+  assert torch.equal(nz2.filt(x), nz.filt(x))
+  nz2.update_estimate(x); nz.update_estimate(x)
+  assert np.array_equal(nz2._var, nz._var) and nz2._count == nz._count

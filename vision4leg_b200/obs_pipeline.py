@@ -8,10 +8,62 @@ simulator and the policy, for E environments at once, without a host round trip.
 
 Both call the C-ABI kernels of csrc/obs_ops.cu; there is no CPU path.
 """
+import copyreg
+import importlib
+import pickle
+import sys
+import types
+
 import numpy as np
 import torch
 
 from .engine import Ops
+
+REFERENCE_NORMALIZER = ("torchrl.env.base_wrapper", "Normalizer")
+
+
+def _reference_normalizer_class():
+  """The class a `_obs_normalizer_{epoch}.pkl` names (reference torchrl/algo/rl_algo.py:84-90 pickles
+  env._obs_normalizer; the viewers unpickle it, starter/*_viewer.py).  The real class when a reference checkout is
+  importable; otherwise a stand-in registered under the same module path, so that pickle writes the same GLOBAL and
+  the untouched reference can load the file."""
+  mod_name, cls_name = REFERENCE_NORMALIZER
+  try:
+    return getattr(importlib.import_module(mod_name), cls_name)
+  except Exception:      # no checkout on the path, or its imports (gym) are missing here
+    mod = sys.modules.get(mod_name)
+    if mod is None or not hasattr(mod, cls_name):
+      mod = types.ModuleType(mod_name)
+      mod.__doc__ = "stand-in written by vision4leg_b200.obs_pipeline (wire format of the normaliser pickle only)"
+      cls = type(cls_name, (), {"__module__": mod_name, "__qualname__": cls_name})
+      setattr(mod, cls_name, cls)
+      sys.modules[mod_name] = mod
+    return getattr(mod, cls_name)
+
+
+def reference_normalizer_object(shape, mean, var, count, clip=10., should_estimate=True):
+  """an instance of the reference's Normalizer class carrying these statistics (attribute names and order of
+  reference torchrl/env/base_wrapper.py:64-71)"""
+  cls = _reference_normalizer_class()
+  obj = cls.__new__(cls)
+  obj.__dict__.update(dict(shape=shape, _mean=np.asarray(mean, np.float64).reshape(shape),
+                           _var=np.asarray(var, np.float64).reshape(shape), _count=float(count), clip=clip,
+                           should_estimate=bool(should_estimate)))
+  return obj
+
+
+class _WireUnpickler(pickle.Unpickler):
+  """reads a normaliser pickle without needing the reference (or gym) to be importable"""
+
+  def find_class(self, module, name):
+    if (module, name) == REFERENCE_NORMALIZER:
+      return _reference_normalizer_class()
+    return super().find_class(module, name)
+
+
+def load_reference_normalizer(f):
+  """-> dict(shape, _mean, _var, _count, clip, should_estimate) from an `_obs_normalizer_*.pkl` stream"""
+  return dict(_WireUnpickler(f).load().__dict__)
 
 
 def fixed_frame_idx(frame_extract):
@@ -130,3 +182,28 @@ class Normalizer:
 
   def inverse_torch(self, raw):
     return raw * torch.sqrt(self._var_d).to(raw.dtype) + self._mean_d.to(raw.dtype)
+
+  # ---- checkpoint wire format: RLAlgo.snapshot pickles env._obs_normalizer; what lands in the file
+  # is an instance of the REFERENCE's class (numpy statistics), loadable by the untouched viewers
+  def __reduce__(self):
+    # copyreg._reconstructor(cls, object, None) + BUILD(state): stdlib names and the reference's class only, so the
+    # file loads where this package is not installed.  Unpickling therefore yields the reference-format object
+    # (host statistics); Normalizer(shape).load_reference(obj) puts it back on a device.
+    ref = self.to_reference()
+    return (copyreg._reconstructor, (type(ref), object, None), dict(ref.__dict__))
+
+  def to_reference(self):
+    return reference_normalizer_object(self.shape, self._mean, self._var, self._count, self.clip, self.should_estimate)
+
+  def load_reference(self, state):
+    """state: a reference Normalizer instance, or the dict of load_reference_normalizer"""
+    st = state if isinstance(state, dict) else state.__dict__
+    if int(np.prod(st["shape"])) != self.S:
+      raise ValueError("normaliser of shape %s loaded into one of shape %s" % (st["shape"], self.shape))
+    self._mean_d.copy_(torch.as_tensor(np.asarray(st["_mean"], np.float64).reshape(-1)))
+    self._var_d.copy_(torch.as_tensor(np.asarray(st["_var"], np.float64).reshape(-1)))
+    self._count = float(st["_count"])
+    self.clip = st["clip"]
+    self.should_estimate = bool(st["should_estimate"])
+    return self
+
