@@ -334,7 +334,8 @@ int v4l_tc_wgrad_conv1(v4l_ctx* ctx, void* stream, const void* x_s2d, int64_t n_
  * v4l_normalizer: running-mean observation normaliser over x [n,S]: if update, merge the batch mean / population
  * variance into (mean, var, count) (torchrl/env/base_wrapper.py:44-61,84-86), then
  * out = clip((x - mean) / (sqrt(var) + 1e-4), +-clip) (:88-90,119-122).  mean/var: double[S] on the device; count (1e-4 + rows merged so far) is tracked by the caller,
- * who adds n after an updating call.  out may be NULL (update only) or alias x. */
+ * who adds n after an updating call.  out may be NULL (update only) or alias x.  update = 2: write the BATCH mean /
+ * population variance of x into mean / var and do nothing else (data-parallel callers merge them across ranks). */
 int v4l_depth_frame(v4l_ctx* ctx, void* stream, const float* zbuf, float* ring, const uint8_t* reset, int E,
                     int n_slots, int head, float near_plane, float far_plane);
 int v4l_stack_frames(v4l_ctx* ctx, void* stream, const float* ring, const int32_t* slots, int E, int n_slots,

@@ -118,3 +118,50 @@ def test_entropy_bonus_share_formula():
   s_local = np.random.default_rng(0).standard_normal(world)
   summed = sum(s - c * n_local * inv_global for s in s_local)
   assert abs(summed - (s_local.sum() - c)) < 1e-12
+
+
+def _norm_worker(rank, world, port, q):
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  try:
+    from oracle import obs_oracle as oo
+    from vision4leg_b200 import obs_pipeline as op
+    S = 23
+    rng = np.random.RandomState(17)
+    ref = oo.Normalizer((S,))
+    mean, var, count = torch.zeros(S, dtype=torch.float64), torch.ones(S, dtype=torch.float64), 1e-4
+    for step, sizes in enumerate([(3, 5), (4, 4), (0, 6), (7, 1)]):            # rows per rank: uneven, one rank empty once
+      rows = [(rng.randn(n, S) * (1 + 10 * step) + step).astype(np.float32) for n in sizes]
+      mine = rows[rank].astype(np.float64)
+      # what kernel mode 2 produces on a rank: batch mean / population variance of ITS rows
+      bm = torch.from_numpy(mine.mean(0) if len(mine) else np.zeros(S))
+      bv = torch.from_numpy(mine.var(0) if len(mine) else np.zeros(S))
+      gm, gv, gn = op.gather_batch_stats(bm, bv, len(mine), dist.group.WORLD)
+      mean, var, count = op.merge_mean_var_count(mean, var, count, gm, gv, gn)
+      ref.update(np.concatenate(rows).astype(np.float64))                        # one process over the union of the rows
+      np.testing.assert_allclose(mean.numpy(), ref.mean, rtol=1e-12, atol=1e-13)
+      np.testing.assert_allclose(var.numpy(), ref.var, rtol=1e-12, atol=1e-13)
+      assert abs(count - ref.count) < 1e-9
+    q.put((rank, "ok"))
+  except Exception:
+    import traceback
+    q.put((rank, traceback.format_exc()))
+  finally:
+    dist.destroy_process_group()
+
+
+def test_data_parallel_normalizer_statistics_world2():
+  """the observation normaliser under data parallelism: per-rank batch statistics all-gathered and combined equal
+  the statistics of ONE process over the union of the ranks' rows (reference base_wrapper.py:44-61,76-86)"""
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_norm_worker, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  results = [q.get(timeout=240) for _ in procs]
+  for p in procs:
+    p.join(timeout=60)
+  for rank, msg in results:
+    assert msg == "ok", "rank %d: %s" % (rank, msg)

@@ -122,3 +122,29 @@ def test_normalizer_checkpoint_roundtrip():
   assert torch.equal(nz2.filt(x), nz.filt(x))
   nz2.update_estimate(x); nz.update_estimate(x)
   assert np.array_equal(nz2._var, nz._var) and nz2._count == nz._count
+
+
+def test_normalizer_batch_statistics_mode_and_rank_merge():
+  """update = 2 writes the batch mean / population variance only; two 'ranks' (halves of one batch) combined with the
+  data-parallel formulas give the statistics of one update over the whole batch"""
+  from vision4leg_b200 import obs_pipeline as op
+  dev = torch.device("cuda", 0)
+  S = 16477
+  rng = np.random.RandomState(9)
+  x = (rng.randn(12, S) * rng.uniform(0.1, 50, S) + 3).astype(np.float32)
+  xt = torch.from_numpy(x).to(dev)
+  nz = op.Normalizer((S,), device=dev)
+  parts = []
+  for sl in (slice(0, 5), slice(5, 12)):
+    bm, bv = torch.empty(S, dtype=torch.float64, device=dev), torch.empty(S, dtype=torch.float64, device=dev)
+    nz.ops.normalizer(xt[sl].contiguous(), sl.stop - sl.start, S, bm, bv, 1.0, 2, 10.0, None)
+    x64 = x[sl].astype(np.float64)
+    assert np.allclose(bm.cpu().numpy(), x64.mean(0), rtol=1e-13, atol=1e-13)
+    assert np.allclose(bv.cpu().numpy(), x64.var(0), rtol=1e-12, atol=1e-13)
+    parts.append((bm, bv, sl.stop - sl.start))
+  gm, gv, gn = op.merge_mean_var_count(parts[0][0], parts[0][1], parts[0][2], parts[1][0], parts[1][1], parts[1][2])
+  m, v, c = op.merge_mean_var_count(nz._mean_d, nz._var_d, nz._count, gm, gv, gn)
+  nz.update_estimate(xt)                                   # one process over the union
+  assert np.allclose(m.cpu().numpy(), nz._mean, rtol=1e-12, atol=1e-13)
+  assert np.allclose(v.cpu().numpy(), nz._var, rtol=1e-12, atol=1e-13) and abs(c - nz._count) < 1e-9
+  assert float(torch.zeros(1, device=dev).sum()) == 0.0    # no sticky error from the launches above

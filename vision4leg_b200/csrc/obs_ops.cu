@@ -94,6 +94,15 @@ __global__ void __launch_bounds__(256) normalizer_kernel(const float* __restrict
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= S) return;
   double m = mean[c], v = var[c];
+  if (update == 2) {                                         // batch statistics only (the data-parallel merge is the caller's)
+    double bs = 0.0;
+    for (int i = 0; i < n; ++i) bs += x[(long long)i * S + c];
+    const double bm = n > 0 ? bs / n : 0.0;
+    double bv = 0.0;
+    for (int i = 0; i < n; ++i) { const double d = x[(long long)i * S + c] - bm; bv += d * d; }
+    mean[c] = bm; var[c] = n > 0 ? bv / n : 0.0;
+    return;
+  }
   if (update && n > 0) {
     double bs = 0.0;
     for (int i = 0; i < n; ++i) bs += x[(long long)i * S + c];
@@ -145,7 +154,9 @@ extern "C" int v4l_stack_frames(v4l_ctx* ctx, void* stream, const float* ring, c
 
 extern "C" int v4l_normalizer(v4l_ctx* ctx, void* stream, const float* x, int n, int S, double* mean, double* var,
                               double count, int update, float clip, float* out) {
-  V4L_REQUIRE(ctx && x && mean && var && n >= 0 && S > 0 && count > 0.0, "v4l_normalizer: bad argument");
+  V4L_REQUIRE(ctx && x && mean && var && n >= 0 && S > 0 && count > 0.0 && update >= 0 && update <= 2,
+              "v4l_normalizer: bad argument");
+  V4L_REQUIRE(update != 2 || out == nullptr, "v4l_normalizer: update = 2 (batch statistics only) does not filter");
   V4L_LAUNCH(normalizer_kernel, (S + 255) / 256, 256, 0, (cudaStream_t)stream, x, n, S, mean, var, count, update, clip, out);
   V4L_CHECK_LAUNCH();
   return 0;

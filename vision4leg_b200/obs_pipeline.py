@@ -52,6 +52,38 @@ def reference_normalizer_object(shape, mean, var, count, clip=10., should_estima
   return obj
 
 
+def merge_mean_var_count(mean, var, count, batch_mean, batch_var, batch_count):
+  """the reference's update_mean_var_count (torchrl/env/base_wrapper.py:44-61) on float64 tensors"""
+  delta = batch_mean - mean
+  tot = count + batch_count
+  new_mean = mean + delta * (batch_count / tot)
+  m2 = var * count + batch_var * batch_count + delta * delta * (count * batch_count / tot)
+  return new_mean, m2 / tot, tot
+
+
+def gather_batch_stats(batch_mean, batch_var, n, process_group):
+  """Data-parallel NormObs: every rank holds the statistics of ITS env columns' rows; the batch the reference would
+  have seen is their union.  One all-gather of (mean, variance, count) per rank, combined in rank order with the
+  same pairwise formula (exact for population variances), so every rank ends with the same float64 numbers as one
+  process over all the rows (up to the rounding of the combination, ~1e-15)."""
+  import torch.distributed as dist
+  world = dist.get_world_size(process_group)
+  S = batch_mean.numel()
+  mine = torch.cat([batch_mean.reshape(-1), batch_var.reshape(-1),
+                    torch.tensor([float(n)], dtype=torch.float64, device=batch_mean.device)])
+  allr = [torch.empty_like(mine) for _ in range(world)]
+  dist.all_gather(allr, mine, group=process_group)
+  m, v, c = allr[0][:S], allr[0][S:2 * S], float(allr[0][2 * S])
+  for r in range(1, world):
+    cr = float(allr[r][2 * S])
+    if cr > 0:
+      if c > 0:
+        m, v, c = merge_mean_var_count(m, v, c, allr[r][:S], allr[r][S:2 * S], cr)
+      else:
+        m, v, c = allr[r][:S], allr[r][S:2 * S], cr
+  return m, v, c
+
+
 class _WireUnpickler(pickle.Unpickler):
   """reads a normaliser pickle without needing the reference (or gym) to be importable"""
 
@@ -155,12 +187,23 @@ class Normalizer:
       raise ValueError("observations must be a CUDA float32 tensor [n, %d]" % self.S)
     return data.contiguous()
 
-  def update_estimate(self, data):
+  def update_estimate(self, data, process_group=None):
+    """process_group: data-parallel training — the statistics are those of the union of the ranks' rows, identical on
+    every rank (the reference is single-process; this is what one process over all the env columns would compute)"""
     if not self.should_estimate:
       return
     x = self._rows(data)
-    self.ops.normalizer(x, x.shape[0], self.S, self._mean_d, self._var_d, self._count, True, self.clip, None)
-    self._count += x.shape[0]
+    if process_group is None or torch.distributed.get_world_size(process_group) == 1:
+      self.ops.normalizer(x, x.shape[0], self.S, self._mean_d, self._var_d, self._count, 1, self.clip, None)
+      self._count += x.shape[0]
+      return
+    bm, bv = torch.empty_like(self._mean_d), torch.empty_like(self._var_d)
+    self.ops.normalizer(x, x.shape[0], self.S, bm, bv, 1.0, 2, self.clip, None)          # this rank's batch statistics
+    bm, bv, n = gather_batch_stats(bm, bv, x.shape[0], process_group)
+    if n > 0:
+      m, v, c = merge_mean_var_count(self._mean_d, self._var_d, self._count, bm, bv, n)
+      self._mean_d.copy_(m); self._var_d.copy_(v)
+      self._count = c
 
   def filt(self, raw, out=None):
     x = self._rows(raw)
@@ -170,11 +213,14 @@ class Normalizer:
 
   filt_torch = filt
 
-  def observation(self, observation, training=True, out=None):
+  def observation(self, observation, training=True, out=None, process_group=None):
     """NormObs.observation (reference :119-122): update (when training) then filter, one launch"""
     x = self._rows(observation)
     out = torch.empty_like(x) if out is None else out
     upd = bool(training and self.should_estimate)
+    if upd and process_group is not None and torch.distributed.get_world_size(process_group) > 1:
+      self.update_estimate(x, process_group)
+      return self.filt(x, out)
     self.ops.normalizer(x, x.shape[0], self.S, self._mean_d, self._var_d, self._count, upd, self.clip, out)
     if upd:
       self._count += x.shape[0]
