@@ -36,6 +36,11 @@ def random_frame_idx(rng, frame_extract):
   return [int(r[0]), int(r[1]) + frame_extract, int(r[2]) + 2 * frame_extract, int(r[3]) + 3 * frame_extract]
 
 
+def step_frame_idx(rng, frame_idx, frame_extract):
+  """reference :549-554 (reset_frame_idx_each_step)."""
+  return [rng.randint(1, frame_extract)] + [frame_idx[i] + frame_extract for i in range(3)]
+
+
 class DepthStack:
   """One environment's depth_frames deque (reference :635-650): newest frame at index 0; a reset fills every slot
   with the first frame; the observation concatenates depth_frames[idx] for idx in frame_idx, then (x-1.25)/0.425."""

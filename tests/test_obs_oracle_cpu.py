@@ -52,3 +52,15 @@ def test_depth_stack_is_a_deque_of_processed_frames():
     assert np.array_equal(o[c], ((oo.depth_feature(frames[19 - i]) - 1.25) / 0.425).astype(np.float32))
   r = oo.random_frame_idx(np.random.RandomState(3), 4)
   assert all(4 * k <= r[k] < 4 * (k + 1) for k in range(4))
+
+
+def test_frame_index_helpers_of_the_product_match_the_oracle():
+  """host logic of vision4leg_b200.obs_pipeline (no device needed): same draws from the same generator state"""
+  from vision4leg_b200 import obs_pipeline as op
+  assert op.fixed_frame_idx(4) == oo.fixed_frame_idx(4)
+  assert op.random_frame_idx(np.random.RandomState(5), 4) == oo.random_frame_idx(np.random.RandomState(5), 4)
+  a, b = np.random.RandomState(6), np.random.RandomState(6)
+  fa = fb = oo.fixed_frame_idx(4)
+  for _ in range(5):
+    fa, fb = op.step_frame_idx(a, fa, 4), oo.step_frame_idx(b, fb, 4)
+    assert fa == [int(v) for v in fb] and 1 <= fa[0] < 4

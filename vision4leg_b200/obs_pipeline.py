@@ -103,6 +103,18 @@ def fixed_frame_idx(frame_extract):
   return [frame_extract - 1, 2 * frame_extract - 1, 3 * frame_extract - 1, 4 * frame_extract - 1]
 
 
+def random_frame_idx(rng, frame_extract):
+  """reference :325-331 (reset with random delays): one index per block of frame_extract frames"""
+  r = rng.randint(0, frame_extract, 4)
+  return [int(r[k]) + k * frame_extract for k in range(4)]
+
+
+def step_frame_idx(rng, frame_idx, frame_extract):
+  """reference :549-554 (reset_frame_idx_each_step): a fresh delay in [1, frame_extract) for the newest channel, the
+  older channels follow the PREVIOUS indices by one block"""
+  return [int(rng.randint(1, frame_extract))] + [int(frame_idx[i]) + frame_extract for i in range(3)]
+
+
 class DepthFrameStack:
   """The reference keeps a deque of processed frames per env (newest at index 0) and builds the observation from
   depth_frames[frame_idx[k]], k = 0..3.  Here the history is a ring [E, n_slots, 64, 64] fp32 in HBM: deque index
